@@ -1,0 +1,119 @@
+/* kb200.h — C ABI of kadal_b200: the B200-native drop-in for KADAL's Kriging hot path.
+ *
+ * KADAL (flowdiagnosticsitb/KADAL) has no FFI on this path: the boundary is two Python
+ * callables and the KrigInfo dict.  These entry points are what a ctypes /
+ * cffi / pybind binding of that path binds; each one names the reference interface it
+ * replaces (paths relative to the KADAL repository root).
+ *
+ * Conventions
+ *   - all matrices are C-contiguous row-major fp64; the caller owns every buffer;
+ *   - the library owns only the opaque kb200_model (device copies + workspaces);
+ *   - functions return 0 on success, <0 on a CUDA / argument error (kb200_last_error());
+ *   - numerical failure is reported per item in info[] (0 ok, k>0 = first non-positive
+ *     pivot at row k-1), never as a crash;
+ *   - `*_dev` variants take device pointers and a cudaStream_t (as void*) and do no
+ *     host<->device copies; the plain variants take host pointers.
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef KB200_H
+#define KB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kb200_model kb200_model;
+
+/* kernel ids = KrigInfo['kernel'] entries (kernelfunc.py:22-31) */
+#define KB200_KERNEL_GAUSSIAN 0      /* also 'iso_gaussian' with KB200_FLAG_ISO */
+#define KB200_KERNEL_EXPONENTIAL 1
+#define KB200_KERNEL_MATERN32 2
+#define KB200_KERNEL_MATERN52 3
+
+#define KB200_FLAG_ISO 1             /* KrigInfo['kernel'] == ['iso_gaussian'] (likelihood_func.py:60-61) */
+#define KB200_FLAG_NAIVE 2           /* debug: plain-FMA GEMM kernels instead of the DMMA pipeline */
+
+/* outputs of kb200_predict (bit mask `want`), prediction.py:258-314 + akmcs.py:281-285 */
+#define KB200_OUT_PRED 1
+#define KB200_OUT_SSQR 2
+#define KB200_OUT_S 4
+#define KB200_OUT_EI 8
+#define KB200_OUT_POI 16
+#define KB200_OUT_POF 32
+#define KB200_OUT_UFUN 64
+
+#define KB200_NORM_NONE 0
+#define KB200_NORM_DEFAULT 1         /* ((x-lb)/(ub-lb)-0.5)*2  samplingplan.py:77-83 */
+#define KB200_NORM_STD 2             /* (x-mean)/std            prediction.py:164-165 */
+
+int kb200_version(void);
+const char* kb200_last_error(void);
+int kb200_device_count(void);
+
+/* Pinned host memory for the host-pointer entry points (optional; pageable works too). */
+void* kb200_host_alloc(unsigned long long bytes);
+void kb200_host_free(void* p);
+
+/* Device-resident model = the part of KrigInfo that likelihood()/prediction() read:
+ * X_norm|X (n x d), y|y_norm (n), F (n x p), plscoeff (d x h or NULL), kernel list.
+ * Replaces the unpacking in likelihood_func.py:38-68 and prediction.py:122-157.
+ * nsamp = KrigInfo['nsamp'] (used by the trainvar branch, likelihood_func.py:197). */
+int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h,
+                       const double* X, const double* y, const double* F, const double* pls,
+                       const int* kernel_ids, int nkernel, double nsamp, int flags);
+void kb200_model_destroy(kb200_model* m);
+
+/* Batched negative concentrated ln-likelihood: one call evaluates
+ *   likelihood(x[i], KrigInfo, 'default', trainvar)   for i < P
+ * (likelihood_func.py:6-118 incl. nuggetset :121-165 and maincalc :168-213).
+ * x is P x nbhyp with the reference's layout [log10 theta | log10 sigma2 | log10 nugget |
+ * kernel weights]; nugget_log10 = KrigInfo['nugget'] when it is not tuned.
+ * Non-PD candidates get nll = +inf and info != 0 (the reference raises LinAlgError). */
+int kb200_lik_batch(kb200_model* m, const double* x, int P, int nbhyp, int trainvar,
+                    double nugget_log10, double* nll, int* info);
+int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int trainvar,
+                        double nugget_log10, double* d_nll, int* d_info, void* stream);
+
+/* likelihood(x, KrigInfo, mode='all'): the quantities the reference writes back into
+ * KrigInfo (likelihood_func.py:107-111): U (n x n, upper, with nugget), Psi (n x n, without
+ * nugget), BE (p), SigmaSqr, NegLnLike; plus the decoded Theta (ntheta, log10), nugget
+ * (log10) and wgkf (nkernel) of :82-84.  Any output pointer may be NULL.
+ * Also installs the predictor state of this fit in the model. */
+int kb200_fit_state(kb200_model* m, const double* x, int nbhyp, int trainvar,
+                    double nugget_log10, double* U, double* Psi, double* BE, double* sigma2,
+                    double* nll, int* info, double* theta_log10, double* nugget_out,
+                    double* wgkf);
+
+/* Install a predictor from an existing KrigInfo (Theta, wgkf, U, BE, SigmaSqr), as
+ * prediction() reads them (prediction.py:148-154).  U is n x n row-major upper. */
+int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double* wgkf,
+                         const double* U, const double* BE, double sigma2);
+
+/* prediction(x, KrigInfo, predtypes) for npred raw points (prediction.py:71-323):
+ * standardise -> psi -> mean -> SSqr -> acquisition values.  Output pointers are npred
+ * doubles each (NULL if not wanted, must match `want`).  stats[0] = #(SSqr == 0),
+ * stats[1] = 1 if any EI term is non-zero (needed for the batch-level shortcuts of
+ * prediction.py:273-274, 287-290).  ymin = min(y) (:272), limit/limit_ge = KrigInfo
+ * ['limit'], ['limittype'] in ('>','>=') (:299-308). */
+int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype,
+                  const double* norm_a, const double* norm_b, unsigned want, double ymin,
+                  double limit, int limit_ge, double* pred, double* ssqr, double* s, double* ei,
+                  double* poi, double* pof, double* ufun, unsigned long long* stats);
+int kb200_predict_dev(kb200_model* m, const double* d_x, long long npred, int normtype,
+                      const double* norm_a, const double* norm_b, unsigned want, double ymin,
+                      double limit, int limit_ge, double* d_pred, double* d_ssqr, double* d_s,
+                      double* d_ei, double* d_poi, double* d_pof, double* d_ufun,
+                      unsigned long long* stats, void* stream);
+
+/* Introspection used by the tests / bench. */
+int kb200_model_dims(const kb200_model* m, int* n, int* d, int* p, int* ntheta, int* nkernel);
+/* kernel launches issued by this model since creation (bench.py "gpu_launches") */
+unsigned long long kb200_launch_count(const kb200_model* m);
+/* debug / parity: assemble Psi (+ nugget if add_eps) for one candidate into row-major n x n */
+int kb200_debug_psi(kb200_model* m, const double* x, int nbhyp, int trainvar,
+                    double nugget_log10, int add_eps, double* Psi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KB200_H */

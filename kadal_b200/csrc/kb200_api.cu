@@ -1,0 +1,739 @@
+// kadal_b200 — C ABI (include/kb200.h).  Host-side orchestration only: every numeric
+// step is a CUDA kernel from kb200_kernels.cu; there is no CPU compute path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/kb200.h"
+#include "kb200_kernels.h"
+
+using namespace kb200;
+
+static thread_local std::string g_err;
+
+static int fail(const char* where, cudaError_t e) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return -(int)e - 1000;
+}
+static int fail_arg(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) return fail(#call, e__); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  double* d() const { return static_cast<double*>(p); }
+};
+
+struct PredSlot {
+  cudaStream_t stream = nullptr;
+  DevBuf x, chunk, fdot, udot, ssq, out[7];
+};
+
+struct kb200_model {
+  int device = 0;
+  int n = 0, d = 0, p = 0, h = 0, ntheta = 0, nkernel = 0, nq = 0, nt = 0, npad = 0;
+  long tiles_per_mat = 0;
+  double nsamp = 0;
+  int flags = 0;
+  int kid[MAXK];
+  int cstride = 0;
+  std::vector<double> hy, hF;
+  DevBuf X, R, pls, pls2;
+  cudaStream_t stream = nullptr;
+  // likelihood workspace
+  DevBuf tiles, W, Z, cand, xdev, nll, info, logdet, sigma2, beta, btb, resid, rhs2, sol2;
+  // predictor state
+  bool has_pred = false;
+  DevBuf pL, pW, palpha, pw, pcand;
+  double pbeta = 0, psigma2 = 0, pbtb = 0;
+  PredSlot slot[2];
+  DevBuf norm_a, norm_b, stats;
+  unsigned long long launches = 0;
+  size_t ws_cap_bytes = 0;
+};
+
+static CorrSpec make_spec(const kb200_model* m) {
+  CorrSpec sp;
+  sp.d = m->d;
+  sp.ntheta = m->ntheta;
+  sp.nkernel = m->nkernel;
+  sp.kpls = m->h > 0 ? 1 : 0;
+  for (int i = 0; i < MAXK; ++i) sp.kid[i] = m->kid[i];
+  sp.pls = m->pls.d();
+  sp.pls2 = m->pls2.d();
+  return sp;
+}
+
+extern "C" {
+
+int kb200_version(void) { return 100; }
+const char* kb200_last_error(void) { return g_err.c_str(); }
+int kb200_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+  return c;
+}
+void* kb200_host_alloc(unsigned long long bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void kb200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h,
+                       const double* X, const double* y, const double* F, const double* pls,
+                       const int* kernel_ids, int nkernel, double nsamp, int flags) {
+  if (!out || !X || !y || !F || !kernel_ids) return fail_arg("kb200_model_create: null argument");
+  if (n < 1 || d < 1 || p < 1) return fail_arg("kb200_model_create: n, d, p must be >= 1");
+  if (p + 1 > MAXQ) return fail_arg("kb200_model_create: at most 7 trend columns (p) are supported");
+  if (nkernel < 1 || nkernel > MAXK - 1) return fail_arg("kb200_model_create: 1..7 kernels supported");
+  if (h < 0 || (h > 0 && !pls)) return fail_arg("kb200_model_create: plscoeff missing");
+  for (int i = 0; i < nkernel; ++i) {
+    if (kernel_ids[i] < 0 || kernel_ids[i] > 3) return fail_arg("Kernel option not available!");
+    if (h > 0 && kernel_ids[i] >= KB200_KERNEL_MATERN32)
+      return fail_arg("KPLS for matern32/matern52 is not yet implemented");
+  }
+  const int red_len = h > 0 ? h : d;
+  if (red_len > 128) return fail_arg("kb200_model_create: more than 128 length scales not supported");
+  if ((size_t)(2 * 128 * (d | 1) + 2) * 8 > 227 * 1024)
+    return fail_arg("kb200_model_create: input dimension d > 110 not supported yet");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return fail_arg("kb200: no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail_arg("kb200_model_create: bad device index");
+  CK(cudaSetDevice(device));
+
+  kb200_model* m = new kb200_model();
+  m->device = device;
+  m->n = n; m->d = d; m->p = p; m->h = h;
+  m->ntheta = h > 0 ? h : d;
+  m->nkernel = nkernel;
+  m->nq = p + 1;
+  m->nt = (n + TB - 1) / TB;
+  m->npad = m->nt * TB;
+  m->tiles_per_mat = (long)m->nt * (m->nt + 1) / 2;
+  m->nsamp = nsamp;
+  m->flags = flags;
+  for (int i = 0; i < MAXK; ++i) m->kid[i] = i < nkernel ? kernel_ids[i] : 0;
+  m->cstride = cand_stride(m->ntheta, nkernel);
+  m->hy.assign(y, y + n);
+  m->hF.assign(F, F + (size_t)n * p);
+  cudaError_t e;
+#define MCK(call)                      \
+  do {                                 \
+    e = (call);                        \
+    if (e != cudaSuccess) {            \
+      int rc = fail(#call, e);         \
+      kb200_model_destroy(m);          \
+      return rc;                       \
+    }                                  \
+  } while (0)
+  MCK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; ++s) MCK(cudaStreamCreateWithFlags(&m->slot[s].stream, cudaStreamNonBlocking));
+  MCK(m->X.reserve((size_t)n * d * 8));
+  MCK(cudaMemcpy(m->X.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice));
+  // R = [y F]^T, zero padded: [nq][npad]
+  {
+    std::vector<double> R((size_t)m->nq * m->npad, 0.0);
+    for (int i = 0; i < n; ++i) {
+      R[i] = y[i];
+      for (int k = 0; k < p; ++k) R[(size_t)(k + 1) * m->npad + i] = F[(size_t)i * p + k];
+    }
+    MCK(m->R.reserve(R.size() * 8));
+    MCK(cudaMemcpy(m->R.p, R.data(), R.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if (h > 0) {
+    std::vector<double> p2((size_t)d * h);
+    for (size_t i = 0; i < p2.size(); ++i) p2[i] = pls[i] * pls[i];
+    MCK(m->pls.reserve(p2.size() * 8));
+    MCK(m->pls2.reserve(p2.size() * 8));
+    MCK(cudaMemcpy(m->pls.p, pls, p2.size() * 8, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(m->pls2.p, p2.data(), p2.size() * 8, cudaMemcpyHostToDevice));
+  }
+  MCK(m->stats.reserve(16));
+  {
+    size_t fr = 0, tot = 0;
+    MCK(cudaMemGetInfo(&fr, &tot));
+    const char* envc = getenv("KB200_WORKSPACE_GB");
+    size_t cap = envc ? (size_t)(atof(envc) * (1ull << 30)) : (size_t)(fr * 0.6);
+    m->ws_cap_bytes = std::max<size_t>(cap, (size_t)256 << 20);
+  }
+#undef MCK
+  *out = m;
+  return 0;
+}
+
+void kb200_model_destroy(kb200_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  DevBuf* bufs[] = {&m->X, &m->R, &m->pls, &m->pls2, &m->tiles, &m->W, &m->Z, &m->cand, &m->xdev,
+                    &m->nll, &m->info, &m->logdet, &m->sigma2, &m->beta, &m->btb, &m->resid,
+                    &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand,
+                    &m->norm_a, &m->norm_b, &m->stats};
+  for (DevBuf* b : bufs) b->release();
+  for (int s = 0; s < 2; ++s) {
+    PredSlot& sl = m->slot[s];
+    sl.x.release(); sl.chunk.release(); sl.fdot.release(); sl.udot.release(); sl.ssq.release();
+    for (auto& o : sl.out) o.release();
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int kb200_model_dims(const kb200_model* m, int* n, int* d, int* p, int* ntheta, int* nkernel) {
+  if (!m) return fail_arg("null model");
+  if (n) *n = m->n;
+  if (d) *d = m->d;
+  if (p) *p = m->p;
+  if (ntheta) *ntheta = m->ntheta;
+  if (nkernel) *nkernel = m->nkernel;
+  return 0;
+}
+unsigned long long kb200_launch_count(const kb200_model* m) { return m ? m->launches : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ internal drivers
+static int layout_from_nbhyp(const kb200_model* m, int nbhyp, int trainvar, int* layout) {
+  const bool iso = m->flags & KB200_FLAG_ISO;
+  const int base = (iso ? 1 : m->ntheta) + (trainvar ? 1 : 0);
+  const int extra = nbhyp - base;
+  if (iso && (trainvar || extra != 0)) return fail_arg("iso_gaussian supports only a single theta");
+  if (extra == 0) {
+    if (m->nkernel != 1) return fail_arg("Nugget setting is not available");
+    *layout = 0;
+  } else if (extra == 1) {
+    if (m->nkernel != 1) return fail_arg("Nugget setting is not available");
+    *layout = 1;
+  } else if (extra == m->nkernel) {
+    *layout = 2;
+  } else if (extra == m->nkernel + 1) {
+    *layout = 3;
+  } else {
+    return fail_arg("Nugget setting is not available");
+  }
+  return 0;
+}
+
+static int decode(kb200_model* m, const double* d_x, long P, int nbhyp, int trainvar,
+                  double nugget_log10, double* d_cand, cudaStream_t st) {
+  int layout = 0;
+  int rc = layout_from_nbhyp(m, nbhyp, trainvar, &layout);
+  if (rc) return rc;
+  DecodeArgs a;
+  a.x = d_x; a.P = P; a.nbhyp = nbhyp; a.ntheta = m->ntheta; a.nkernel = m->nkernel;
+  a.iso = (m->flags & KB200_FLAG_ISO) ? 1 : 0;
+  a.theta_is_linear = 0;
+  a.trainvar = trainvar;
+  a.layout = layout;
+  a.eps_fixed = pow(10.0, nugget_log10);
+  a.wgkf_given = nullptr;
+  a.cand = d_cand;
+  a.cand_stride = m->cstride;
+  CK(launch_decode(a, st));
+  m->launches++;
+  return 0;
+}
+
+static CholArgs chol_args(kb200_model* m, double* tiles, double* W, double* Z, double* logdet, int* info) {
+  CholArgs a;
+  memset(&a, 0, sizeof(a));
+  a.L = tiles; a.W = W; a.tiles_per_mat = m->tiles_per_mat;
+  a.nt = m->nt; a.npad = m->npad; a.n = m->n;
+  a.nq = m->nq; a.R = m->R.d(); a.Z = Z; a.logdet = logdet; a.info = info;
+  a.naive = (m->flags & KB200_FLAG_NAIVE) ? 1 : 0;
+  a.pred_mode = 0;
+  return a;
+}
+
+// assemble + factorise Pb candidates whose parameter rows start at d_cand
+static int assemble(kb200_model* m, const double* d_cand, int Pb, double* tiles, int add_eps, cudaStream_t st) {
+  CorrArgs c;
+  memset(&c, 0, sizeof(c));
+  c.spec = make_spec(m);
+  c.mode = CORR_ASSEMBLE;
+  c.n = m->n; c.nt = m->nt; c.X = m->X.d();
+  c.cand = d_cand; c.cand_stride = m->cstride;
+  c.out = tiles; c.tiles_per_mat = m->tiles_per_mat; c.add_eps = add_eps;
+  CK(launch_corr(c, (int)m->tiles_per_mat, Pb, st));
+  m->launches++;
+  return 0;
+}
+
+static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z, double* logdet,
+                     int* info, cudaStream_t st) {
+  CholArgs a = chol_args(m, tiles, W, Z, logdet, info);
+  for (int j = 0; j < m->nt; ++j) {
+    CK(launch_chol_diag(a, j, Pb, st));
+    m->launches++;
+    if (j + 1 < m->nt) {
+      CK(launch_chol_panel(a, j, m->nt - 1 - j, Pb, st));
+      m->launches++;
+    }
+  }
+  return 0;
+}
+
+static size_t per_matrix_bytes(const kb200_model* m) {
+  return (size_t)(m->tiles_per_mat + m->nt) * TILE_ELEMS * 8 + (size_t)m->nq * m->npad * 8 + 64;
+}
+
+static int reserve_lik(kb200_model* m, long P, int Pb) {
+  CK(m->tiles.reserve((size_t)Pb * m->tiles_per_mat * TILE_ELEMS * 8));
+  CK(m->W.reserve((size_t)Pb * m->nt * TILE_ELEMS * 8));
+  CK(m->Z.reserve((size_t)Pb * m->nq * m->npad * 8));
+  CK(m->cand.reserve((size_t)P * m->cstride * 8));
+  CK(m->logdet.reserve((size_t)Pb * 8));
+  return 0;
+}
+
+extern "C" {
+
+int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int trainvar,
+                        double nugget_log10, double* d_nll, int* d_info, void* stream) {
+  if (!m || !d_x || !d_nll || !d_info) return fail_arg("kb200_lik_batch_dev: null argument");
+  if (P < 1) return 0;
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  int Pb = (int)std::min<size_t>((size_t)P, std::max<size_t>(1, m->ws_cap_bytes / per_matrix_bytes(m)));
+  Pb = std::min(Pb, 32768);
+  int rc = reserve_lik(m, P, Pb);
+  if (rc) return rc;
+  rc = decode(m, d_x, P, nbhyp, trainvar, nugget_log10, m->cand.d(), st);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(d_info, 0, (size_t)P * sizeof(int), st));
+  for (int p0 = 0; p0 < P; p0 += Pb) {
+    const int pb = std::min(Pb, P - p0);
+    const double* cand = m->cand.d() + (size_t)p0 * m->cstride;
+    rc = assemble(m, cand, pb, m->tiles.d(), 1, st);
+    if (rc) return rc;
+    rc = factorize(m, pb, m->tiles.d(), m->W.d(), m->Z.d(), m->logdet.d(), d_info + p0, st);
+    if (rc) return rc;
+    FinArgs f;
+    memset(&f, 0, sizeof(f));
+    f.Z = m->Z.d(); f.logdet = m->logdet.d(); f.info = d_info + p0;
+    f.cand = cand; f.cand_stride = m->cstride;
+    f.nq = m->nq; f.npad = m->npad; f.n = m->n;
+    f.trainvar = trainvar; f.nsamp = m->nsamp;
+    f.nll = d_nll + p0;
+    CK(launch_finalize(f, pb, st));
+    m->launches++;
+  }
+  return 0;
+}
+
+int kb200_lik_batch(kb200_model* m, const double* x, int P, int nbhyp, int trainvar,
+                    double nugget_log10, double* nll, int* info) {
+  if (!m || !x || !nll || !info) return fail_arg("kb200_lik_batch: null argument");
+  if (P < 1) return 0;
+  CK(cudaSetDevice(m->device));
+  CK(m->xdev.reserve((size_t)P * nbhyp * 8));
+  CK(m->nll.reserve((size_t)P * 8));
+  CK(m->info.reserve((size_t)P * 4));
+  CK(cudaMemcpyAsync(m->xdev.p, x, (size_t)P * nbhyp * 8, cudaMemcpyHostToDevice, m->stream));
+  int rc = kb200_lik_batch_dev(m, m->xdev.d(), P, nbhyp, trainvar, nugget_log10, m->nll.d(),
+                               static_cast<int*>(m->info.p), m->stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(nll, m->nll.p, (size_t)P * 8, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(info, m->info.p, (size_t)P * 4, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int kb200_debug_psi(kb200_model* m, const double* x, int nbhyp, int trainvar,
+                    double nugget_log10, int add_eps, double* Psi) {
+  if (!m || !x || !Psi) return fail_arg("kb200_debug_psi: null argument");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = m->stream;
+  int rc = reserve_lik(m, 1, 1);
+  if (rc) return rc;
+  CK(m->xdev.reserve((size_t)nbhyp * 8));
+  CK(cudaMemcpyAsync(m->xdev.p, x, (size_t)nbhyp * 8, cudaMemcpyHostToDevice, st));
+  rc = decode(m, m->xdev.d(), 1, nbhyp, trainvar, nugget_log10, m->cand.d(), st);
+  if (rc) return rc;
+  rc = assemble(m, m->cand.d(), 1, m->tiles.d(), add_eps, st);
+  if (rc) return rc;
+  CK(m->sol2.reserve((size_t)m->n * m->n * 8));
+  CK(launch_export(m->tiles.d(), m->n, m->sol2.d(), 1, st));
+  m->launches++;
+  CK(cudaMemcpyAsync(Psi, m->sol2.p, (size_t)m->n * m->n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// predictor constants from Z-space quantities: alpha = L^-T resid, w = L^-T b
+static int install_predictor(kb200_model* m, const double* tiles, const double* W, const double* d_resid,
+                             const double* d_b, const double* d_cand_row, double beta, double sigma2,
+                             double btb, cudaStream_t st) {
+  const size_t tb = (size_t)m->tiles_per_mat * TILE_ELEMS * 8, wb = (size_t)m->nt * TILE_ELEMS * 8;
+  CK(m->pL.reserve(tb));
+  CK(m->pW.reserve(wb));
+  CK(m->pcand.reserve((size_t)m->cstride * 8));
+  CK(m->rhs2.reserve((size_t)2 * m->npad * 8));
+  CK(m->sol2.reserve(std::max((size_t)2 * m->npad * 8, m->sol2.cap)));
+  CK(m->palpha.reserve((size_t)m->npad * 8));
+  CK(m->pw.reserve((size_t)m->npad * 8));
+  if (tiles != m->pL.d()) CK(cudaMemcpyAsync(m->pL.p, tiles, tb, cudaMemcpyDeviceToDevice, st));
+  if (W != m->pW.d()) CK(cudaMemcpyAsync(m->pW.p, W, wb, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(m->pcand.p, d_cand_row, (size_t)m->cstride * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(m->rhs2.d(), d_resid, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(m->rhs2.d() + m->npad, d_b, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
+  BackArgs b;
+  b.L = m->pL.d(); b.W = m->pW.d(); b.nt = m->nt; b.npad = m->npad; b.nq = 2;
+  b.rhs = m->rhs2.d(); b.out = m->sol2.d();
+  CK(launch_backsolve(b, st));
+  m->launches++;
+  CK(cudaMemcpyAsync(m->palpha.p, m->sol2.d(), (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(m->pw.p, m->sol2.d() + m->npad, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
+  m->pbeta = beta; m->psigma2 = sigma2; m->pbtb = btb;
+  m->has_pred = true;
+  return 0;
+}
+
+int kb200_fit_state(kb200_model* m, const double* x, int nbhyp, int trainvar,
+                    double nugget_log10, double* U, double* Psi, double* BE, double* sigma2,
+                    double* nll, int* info, double* theta_log10, double* nugget_out,
+                    double* wgkf) {
+  if (!m || !x) return fail_arg("kb200_fit_state: null argument");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = m->stream;
+  int rc = reserve_lik(m, 1, 1);
+  if (rc) return rc;
+  CK(m->xdev.reserve((size_t)nbhyp * 8));
+  CK(m->nll.reserve(8));
+  CK(m->info.reserve(4));
+  CK(m->sigma2.reserve(8));
+  CK(m->beta.reserve((size_t)m->p * 8));
+  CK(m->btb.reserve(8));
+  CK(m->resid.reserve((size_t)m->npad * 8));
+  const size_t nn = (size_t)m->n * m->n * 8;
+  CK(m->sol2.reserve(std::max(nn, (size_t)2 * m->npad * 8)));
+  CK(cudaMemcpyAsync(m->xdev.p, x, (size_t)nbhyp * 8, cudaMemcpyHostToDevice, st));
+  rc = decode(m, m->xdev.d(), 1, nbhyp, trainvar, nugget_log10, m->cand.d(), st);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(m->info.p, 0, 4, st));
+  // Psi without the nugget (KrigInfo['Psi'], likelihood_func.py:108), then + eps*I (:171)
+  rc = assemble(m, m->cand.d(), 1, m->tiles.d(), 0, st);
+  if (rc) return rc;
+  if (Psi) {
+    CK(launch_export(m->tiles.d(), m->n, m->sol2.d(), 1, st));
+    m->launches++;
+    CK(cudaMemcpyAsync(Psi, m->sol2.p, nn, cudaMemcpyDeviceToHost, st));
+  }
+  CK(launch_add_diag(m->tiles.d(), m->n, m->cand.d() + 4 * m->ntheta + m->nkernel, st));
+  m->launches++;
+  rc = factorize(m, 1, m->tiles.d(), m->W.d(), m->Z.d(), m->logdet.d(), static_cast<int*>(m->info.p), st);
+  if (rc) return rc;
+  FinArgs f;
+  memset(&f, 0, sizeof(f));
+  f.Z = m->Z.d(); f.logdet = m->logdet.d(); f.info = static_cast<int*>(m->info.p);
+  f.cand = m->cand.d(); f.cand_stride = m->cstride;
+  f.nq = m->nq; f.npad = m->npad; f.n = m->n; f.trainvar = trainvar; f.nsamp = m->nsamp;
+  f.nll = m->nll.d(); f.sigma2 = m->sigma2.d(); f.beta = m->beta.d(); f.btb = m->btb.d();
+  f.resid = m->resid.d();
+  CK(launch_finalize(f, 1, st));
+  m->launches++;
+  if (U) {
+    CK(launch_export(m->tiles.d(), m->n, m->sol2.d(), 0, st));
+    m->launches++;
+    CK(cudaMemcpyAsync(U, m->sol2.p, nn, cudaMemcpyDeviceToHost, st));
+  }
+  std::vector<double> hc(m->cstride), hbeta(m->p);
+  double h_nll = 0, h_s2 = 0, h_btb = 0;
+  int h_info = 0;
+  CK(cudaMemcpyAsync(hc.data(), m->cand.p, (size_t)m->cstride * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hbeta.data(), m->beta.p, (size_t)m->p * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&h_nll, m->nll.p, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&h_s2, m->sigma2.p, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&h_btb, m->btb.p, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&h_info, m->info.p, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (BE) memcpy(BE, hbeta.data(), (size_t)m->p * 8);
+  if (sigma2) *sigma2 = h_s2;
+  if (nll) *nll = h_nll;
+  if (info) *info = h_info;
+  {
+    const bool iso = m->flags & KB200_FLAG_ISO;
+    int layout = 0;
+    layout_from_nbhyp(m, nbhyp, trainvar, &layout);
+    const int off = (iso ? 1 : m->ntheta) + (trainvar ? 1 : 0);
+    if (theta_log10) for (int k = 0; k < m->ntheta; ++k) theta_log10[k] = iso ? x[0] : x[k];
+    if (nugget_out) *nugget_out = (layout & 1) ? x[off] : nugget_log10;
+    if (wgkf) for (int k = 0; k < m->nkernel; ++k) wgkf[k] = hc[4 * m->ntheta + k];
+  }
+  if (h_info == 0 && m->p == 1) {
+    rc = install_predictor(m, m->tiles.d(), m->W.d(), m->resid.d(), m->Z.d() + m->npad,
+                           m->cand.d(), hbeta[0], h_s2, h_btb, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+  } else {
+    m->has_pred = false;
+  }
+  return 0;
+}
+
+int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double* wgkf,
+                         const double* U, const double* BE, double sigma2) {
+  if (!m || !theta_log10 || !wgkf || !U || !BE) return fail_arg("kb200_predictor_load: null argument");
+  if (m->p != 1)
+    return fail_arg("prediction with TrendOrder >= 1 is broken in the reference (prediction.py:250) and not supported");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = m->stream;
+  const size_t nn = (size_t)m->n * m->n * 8;
+  CK(m->sol2.reserve(std::max(nn, (size_t)2 * m->npad * 8)));
+  CK(m->pL.reserve((size_t)m->tiles_per_mat * TILE_ELEMS * 8));
+  CK(m->pW.reserve((size_t)m->nt * TILE_ELEMS * 8));
+  CK(m->pcand.reserve((size_t)m->cstride * 8));
+  CK(m->xdev.reserve((size_t)(m->ntheta + m->nkernel) * 8));
+  // candidate row from Theta / wgkf (theta = 10**Theta, prediction.py:148)
+  {
+    std::vector<double> hx(m->ntheta + m->nkernel);
+    for (int k = 0; k < m->ntheta; ++k) hx[k] = theta_log10[k];
+    for (int k = 0; k < m->nkernel; ++k) hx[m->ntheta + k] = wgkf[k];
+    CK(cudaMemcpyAsync(m->xdev.p, hx.data(), hx.size() * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = m->xdev.d(); a.P = 1; a.nbhyp = m->ntheta; a.ntheta = m->ntheta; a.nkernel = m->nkernel;
+    a.iso = 0; a.trainvar = 0; a.layout = 0; a.eps_fixed = 0.0;
+    a.wgkf_given = m->xdev.d() + m->ntheta;
+    a.cand = m->pcand.d(); a.cand_stride = m->cstride;
+    CK(launch_decode(a, st));
+    m->launches++;
+  }
+  CK(cudaMemcpyAsync(m->sol2.p, U, nn, cudaMemcpyHostToDevice, st));
+  CK(launch_import_U(m->sol2.d(), m->n, m->nt, m->pL.d(), st));
+  m->launches++;
+  CholArgs ca = chol_args(m, m->pL.d(), m->pW.d(), nullptr, nullptr, nullptr);
+  CK(launch_diag_inverse(ca, 1, st));
+  m->launches++;
+  // forward solve of [y - F*BE | F]
+  CK(m->rhs2.reserve((size_t)2 * m->npad * 8));
+  std::vector<double> rhs((size_t)2 * m->npad, 0.0);
+  for (int i = 0; i < m->n; ++i) {
+    rhs[i] = m->hy[i] - m->hF[i] * BE[0];
+    rhs[m->npad + i] = m->hF[i];
+  }
+  CK(cudaStreamSynchronize(st));  // sol2 (U staging) consumed before reuse below
+  CK(cudaMemcpyAsync(m->rhs2.p, rhs.data(), rhs.size() * 8, cudaMemcpyHostToDevice, st));
+  CK(m->Z.reserve((size_t)2 * m->npad * 8));
+  BackArgs f;
+  f.L = m->pL.d(); f.W = m->pW.d(); f.nt = m->nt; f.npad = m->npad; f.nq = 2;
+  f.rhs = m->rhs2.d(); f.out = m->Z.d();
+  CK(launch_forwardsolve(f, st));
+  m->launches++;
+  std::vector<double> hb(m->npad);
+  CK(cudaMemcpyAsync(hb.data(), m->Z.d() + m->npad, (size_t)m->npad * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  double btb = 0.0;
+  for (int i = 0; i < m->n; ++i) btb = fma(hb[i], hb[i], btb);
+  CK(m->resid.reserve((size_t)m->npad * 8));
+  CK(cudaMemcpyAsync(m->resid.p, m->Z.d(), (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
+  CK(m->beta.reserve((size_t)m->npad * 8));
+  CK(cudaMemcpyAsync(m->beta.p, m->Z.d() + m->npad, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
+  int rc = install_predictor(m, m->pL.d(), m->pW.d(), m->resid.d(), m->beta.d(), m->pcand.d(), BE[0],
+                             sigma2, btb, st);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------- prediction
+static long chunk_tiles_for(const kb200_model* m) {
+  // point tiles per variance chunk: a multiple of the SM count, chunk buffer ~ 64-160 MiB
+  long t = 148L * std::max(1L, 4L / m->nt);
+  return t;
+}
+
+static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long npts, int normtype,
+                        unsigned want, double ymin, double limit, int limit_ge, double* outs[7],
+                        cudaStream_t st) {
+  const bool need_var = (want & ~KB200_OUT_PRED) != 0;
+  CK(sl.fdot.reserve((size_t)npts * 8));
+  CorrArgs c;
+  memset(&c, 0, sizeof(c));
+  c.spec = make_spec(m);
+  c.mode = CORR_PREDICT;
+  c.n = m->n; c.nt = m->nt; c.X = m->X.d();
+  c.cand = m->pcand.d(); c.cand_stride = m->cstride;
+  c.normtype = normtype; c.norm_a = m->norm_a.d(); c.norm_b = m->norm_b.d();
+  c.alpha = m->palpha.d();
+  EpiArgs e;
+  memset(&e, 0, sizeof(e));
+  e.beta = m->pbeta; e.sigma2 = m->psigma2; e.btb = m->pbtb; e.ymin = ymin; e.limit = limit;
+  e.limit_ge = limit_ge; e.need_var = need_var ? 1 : 0;
+  e.stats = static_cast<unsigned long long*>(m->stats.p);
+  if (!need_var) {
+    c.xpts = d_x; c.npts = npts; c.out = nullptr; c.wvec = nullptr;
+    c.fdot = sl.fdot.d(); c.udot = nullptr;
+    const long tiles = (npts + TB - 1) / TB;
+    for (long t0 = 0; t0 < tiles; t0 += 1 << 20) {   // grid.x limit is 2^31-1; keep launches bounded
+      const long tn = std::min<long>(1 << 20, tiles - t0);
+      CorrArgs cc = c;
+      cc.xpts = d_x + (size_t)t0 * TB * m->d;
+      cc.npts = std::min<long>(npts - t0 * TB, tn * TB);
+      cc.fdot = sl.fdot.d() + t0 * TB;
+      CK(launch_corr(cc, (int)tn, 1, st));
+      m->launches++;
+    }
+    e.npts = npts; e.fdot = sl.fdot.d(); e.pred = outs[0];
+    CK(launch_epilogue(e, st));
+    m->launches++;
+    return 0;
+  }
+  const long ct = chunk_tiles_for(m);
+  const long cpts = ct * TB;
+  CK(sl.chunk.reserve((size_t)ct * m->nt * TILE_ELEMS * 8));
+  CK(sl.udot.reserve((size_t)npts * 8));
+  CK(sl.ssq.reserve((size_t)cpts * 8));
+  CholArgs pa = chol_args(m, m->pL.d(), m->pW.d(), nullptr, nullptr, nullptr);
+  pa.pred_mode = 1;
+  pa.chunk = sl.chunk.d();
+  pa.ssq = sl.ssq.d();
+  for (long p0 = 0; p0 < npts; p0 += cpts) {
+    const long np = std::min(cpts, npts - p0);
+    const int tiles = (int)((np + TB - 1) / TB);
+    CorrArgs cc = c;
+    cc.xpts = d_x + (size_t)p0 * m->d; cc.npts = np; cc.out = sl.chunk.d();
+    cc.wvec = m->pw.d(); cc.fdot = sl.fdot.d() + p0; cc.udot = sl.udot.d() + p0;
+    CK(launch_corr(cc, tiles, 1, st));
+    m->launches++;
+    for (int j = 0; j < m->nt; ++j) {
+      CK(launch_chol_panel(pa, j, tiles, 1, st));
+      m->launches++;
+    }
+    EpiArgs ee = e;
+    ee.npts = np; ee.fdot = sl.fdot.d() + p0; ee.udot = sl.udot.d() + p0; ee.ssq = sl.ssq.d();
+    ee.pred = outs[0] ? outs[0] + p0 : nullptr;
+    ee.ssqr = outs[1] ? outs[1] + p0 : nullptr;
+    ee.s = outs[2] ? outs[2] + p0 : nullptr;
+    ee.ei = outs[3] ? outs[3] + p0 : nullptr;
+    ee.poi = outs[4] ? outs[4] + p0 : nullptr;
+    ee.pof = outs[5] ? outs[5] + p0 : nullptr;
+    ee.ufun = outs[6] ? outs[6] + p0 : nullptr;
+    CK(launch_epilogue(ee, st));
+    m->launches++;
+  }
+  return 0;
+}
+
+static int predict_prepare(kb200_model* m, int normtype, const double* norm_a, const double* norm_b,
+                           unsigned want, double* const outs[7], cudaStream_t st) {
+  if (!m->has_pred) return fail_arg("kb200_predict: no predictor installed (call kb200_fit_state or kb200_predictor_load)");
+  if (m->p != 1) return fail_arg("prediction with TrendOrder >= 1 is not supported (broken in the reference)");
+  if (want == 0) return fail_arg("kb200_predict: nothing requested");
+  for (int i = 0; i < 7; ++i)
+    if (((want >> i) & 1u) && !outs[i]) return fail_arg("kb200_predict: requested output has a null pointer");
+  if (normtype != KB200_NORM_NONE) {
+    if (!norm_a || !norm_b) return fail_arg("kb200_predict: normalisation vectors missing");
+    CK(m->norm_a.reserve((size_t)m->d * 8));
+    CK(m->norm_b.reserve((size_t)m->d * 8));
+    CK(cudaMemcpyAsync(m->norm_a.p, norm_a, (size_t)m->d * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->norm_b.p, norm_b, (size_t)m->d * 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemsetAsync(m->stats.p, 0, 16, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" {
+
+int kb200_predict_dev(kb200_model* m, const double* d_x, long long npred, int normtype,
+                      const double* norm_a, const double* norm_b, unsigned want, double ymin,
+                      double limit, int limit_ge, double* d_pred, double* d_ssqr, double* d_s,
+                      double* d_ei, double* d_poi, double* d_pof, double* d_ufun,
+                      unsigned long long* stats, void* stream) {
+  if (!m || !d_x) return fail_arg("kb200_predict_dev: null argument");
+  if (npred < 1) return 0;
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  double* outs[7] = {d_pred, d_ssqr, d_s, d_ei, d_poi, d_pof, d_ufun};
+  int rc = predict_prepare(m, normtype, norm_a, norm_b, want, outs, st);
+  if (rc) return rc;
+  for (int i = 0; i < 7; ++i)
+    if (!((want >> i) & 1u)) outs[i] = nullptr;
+  rc = predict_core(m, m->slot[0], d_x, (long)npred, normtype, want, ymin, limit, limit_ge, outs, st);
+  if (rc) return rc;
+  if (stats) {
+    CK(cudaMemcpyAsync(stats, m->stats.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype,
+                  const double* norm_a, const double* norm_b, unsigned want, double ymin,
+                  double limit, int limit_ge, double* pred, double* ssqr, double* s, double* ei,
+                  double* poi, double* pof, double* ufun, unsigned long long* stats) {
+  if (!m || !x) return fail_arg("kb200_predict: null argument");
+  if (npred < 1) return 0;
+  CK(cudaSetDevice(m->device));
+  double* houts[7] = {pred, ssqr, s, ei, poi, pof, ufun};
+  int rc = predict_prepare(m, normtype, norm_a, norm_b, want, houts, m->stream);
+  if (rc) return rc;
+  // super-chunks alternate between two streams so that the H2D copy of chunk i+1 and the
+  // D2H copy of chunk i-1 overlap the kernels of chunk i (pinned host memory required
+  // for true overlap; pageable memory still works, staged by the driver).
+  const long ct = chunk_tiles_for(m) * TB;
+  long sc = std::max<long>(ct, (1L << 19) / ct * ct);
+  for (long p0 = 0, it = 0; p0 < npred; p0 += sc, ++it) {
+    PredSlot& sl = m->slot[it & 1];
+    cudaStream_t st = sl.stream;
+    const long np = std::min<long>(sc, npred - p0);
+    CK(sl.x.reserve((size_t)std::min<long>(sc, npred) * m->d * 8));
+    CK(cudaMemcpyAsync(sl.x.p, x + (size_t)p0 * m->d, (size_t)np * m->d * 8, cudaMemcpyHostToDevice, st));
+    double* outs[7];
+    for (int i = 0; i < 7; ++i) {
+      outs[i] = nullptr;
+      if ((want >> i) & 1u) {
+        CK(sl.out[i].reserve((size_t)std::min<long>(sc, npred) * 8));
+        outs[i] = sl.out[i].d();
+      }
+    }
+    rc = predict_core(m, sl, sl.x.d(), np, normtype, want, ymin, limit, limit_ge, outs, st);
+    if (rc) return rc;
+    for (int i = 0; i < 7; ++i)
+      if (outs[i]) CK(cudaMemcpyAsync(houts[i] + p0, outs[i], (size_t)np * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(m->slot[0].stream));
+  CK(cudaStreamSynchronize(m->slot[1].stream));
+  if (stats) CK(cudaMemcpy(stats, m->stats.p, 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1046 @@
+// kadal_b200 — sm_100a kernels for the Kriging hot path.
+//
+//   corr_tile_kernel     K1  correlation tiles: Psi assembly (likelihood) / psi(X,x*) (predict)
+//   chol_diag_kernel     K2  left-looking step j, diagonal tile: DMMA SYRK update, in-smem
+//                            POTF2 + inverse, fused forward substitution of [y F], log-det
+//   chol_panel_kernel    K3  left-looking step j, tile (i,j): DMMA GEMM update, TRSM as a DMMA
+//                            GEMM with the inverted diagonal block.  Prediction points are
+//                            "extra rows" of the factorisation and reuse this kernel.
+//   lik_finalize_kernel  K4  GLS beta, sigma^2, concentrated / trainvar ln-likelihood
+//   backsolve_kernel         alpha = L^-T r, w = L^-T b (predictor state, once per fit)
+//   predict_epilogue_kernel  mean / SSqr / s / EI / PoI / PoF / U-function
+//   import / export kernels  row-major U, Psi  <->  tile layout
+//
+// Reference call sites replaced: likelihood_func.py:93-102,168-213; kernelfunc.py:4-94;
+// prediction.py:159-171,208-314.  See DESIGN.md for the data layout and rooflines.
+#include <cstdio>
+#include <cmath>
+#include "kb200_corr.cuh"
+#include "kb200_kernels.h"
+
+namespace kb200 {
+
+// ============================================================================ K1
+// One CTA = one 128x128 tile (assembly) or one 128-point row tile x all sample tiles
+// (prediction).  256 threads; lane -> (row = lane/4, 32-byte chunk = lane%4), so a warp
+// writes 8 consecutive 128-byte lines of a slab (1 KiB contiguous).
+constexpr int CORR_THREADS = 256;
+
+__device__ __forceinline__ double standardize1(double x, int normtype, double a, double b) {
+  if (normtype == 1) {  // 'default': ((x-lb)/(ub-lb) - 0.5) * 2   samplingplan.py:77-83
+    double v = __ddiv_rn(__dsub_rn(x, a), __dsub_rn(b, a));
+    return __dmul_rn(__dsub_rn(v, 0.5), 2.0);
+  }
+  if (normtype == 2) return __ddiv_rn(__dsub_rn(x, a), b);  // (x-mean)/std  prediction.py:164
+  return x;
+}
+
+__global__ void __launch_bounds__(CORR_THREADS)
+corr_tile_kernel(CorrArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int d = A.spec.d;
+  const int lda = d | 1;
+  double* As = reinterpret_cast<double*>(smem_raw);          // [128][lda]
+  double* Bt = As + ((TB * lda + 1) & ~1);                   // [d][128]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, ch = lane & 3;
+
+  int ti, tj0, tj1;
+  long m;  // candidate (assembly) — prediction uses candidate 0
+  if (A.mode == CORR_ASSEMBLE) {
+    // blockIdx.x -> lower-triangular tile (ti,tj)
+    int t = blockIdx.x;
+    ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    tj0 = t - ti * (ti + 1) / 2;
+    tj1 = tj0 + 1;
+    m = blockIdx.y;
+  } else {
+    ti = blockIdx.x;  // point tile
+    tj0 = 0;
+    tj1 = A.nt;
+    m = 0;
+  }
+  const double* cand = A.cand + m * A.cand_stride;
+
+  // ---- row coordinates -> As
+  if (A.mode == CORR_ASSEMBLE) {
+    for (int idx = tid; idx < TB * d; idx += CORR_THREADS) {
+      int r = idx / d, k = idx - r * d;
+      int gr = ti * TB + r;
+      As[r * lda + k] = (gr < A.n) ? A.X[(size_t)gr * d + k] : 0.0;
+    }
+  } else {
+    for (int idx = tid; idx < TB * d; idx += CORR_THREADS) {
+      int r = idx / d, k = idx - r * d;
+      long gp = (long)ti * TB + r;
+      double v = 0.0;
+      if (gp < A.npts) {
+        v = A.xpts[(size_t)gp * d + k];
+        v = standardize1(v, A.normtype, A.norm_a ? A.norm_a[k] : 0.0, A.norm_b ? A.norm_b[k] : 1.0);
+      }
+      As[r * lda + k] = v;
+    }
+  }
+
+  double facc0 = 0.0, facc1 = 0.0, uacc0 = 0.0, uacc1 = 0.0;
+  const double eps = cand[4 * A.spec.ntheta + A.spec.nkernel];
+
+  for (int tj = tj0; tj < tj1; ++tj) {
+    __syncthreads();  // As ready / previous Bt consumed
+    for (int idx = tid; idx < TB * d; idx += CORR_THREADS) {
+      int c = idx / d, k = idx - c * d;
+      int gc = tj * TB + c;
+      Bt[k * TB + c] = (gc < A.n) ? A.X[(size_t)gc * d + k] : 0.0;
+    }
+    __syncthreads();
+    double* tile;
+    if (A.mode == CORR_ASSEMBLE)
+      tile = A.out + ((size_t)m * A.tiles_per_mat + tri_index(ti, tj)) * TILE_ELEMS;
+    else
+      tile = A.out ? A.out + ((size_t)ti * A.nt + tj) * TILE_ELEMS : nullptr;
+
+#pragma unroll 1
+    for (int rgi = 0; rgi < 2; ++rgi) {
+      const int row = 8 * (warp + 8 * rgi) + g;
+      const long grow = (long)ti * TB + row;
+#pragma unroll 1
+      for (int s = 0; s < NSLAB; ++s) {
+        const int c0 = s * KS + 4 * ch;
+        const int gc0 = tj * TB + c0;
+        Quad q;
+        bool need = true;
+        if (A.mode == CORR_ASSEMBLE) {
+          // skip the strictly-upper part of diagonal tiles and fully padded quads
+          if ((ti == tj && c0 > row) || grow >= A.n || gc0 >= A.n) need = false;
+        } else {
+          if (gc0 >= A.n) need = false;
+        }
+        if (need) q = corr_quad(A.spec, cand, As + row * lda, Bt + c0, TB);
+        else q = quad_set(0.0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int gc = gc0 + e;
+          if (A.mode == CORR_ASSEMBLE) {
+            if (grow >= A.n || gc >= A.n) q.v[e] = (grow == gc) ? 1.0 : 0.0;   // identity padding
+            else if (grow == gc && A.add_eps) q.v[e] = __dadd_rn(q.v[e], eps); // Psi + eye*eps
+            else if (ti == tj && gc > grow) q.v[e] = 0.0;
+          } else {
+            if (gc >= A.n) q.v[e] = 0.0;
+          }
+        }
+        if (tile) {
+          double2* dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row * KS + ((ch ^ (row & 3)) << 2));
+          dst[0] = make_double2(q.v[0], q.v[1]);
+          dst[1] = make_double2(q.v[2], q.v[3]);
+        }
+        if (A.mode == CORR_PREDICT) {
+          double fa = 0.0, ua = 0.0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            int gc = gc0 + e;   // alpha / w are zero padded to nt*TB
+            fa = fma(q.v[e], A.alpha[gc], fa);
+            if (A.wvec) ua = fma(q.v[e], A.wvec[gc], ua);
+          }
+          if (rgi == 0) { facc0 += fa; uacc0 += ua; } else { facc1 += fa; uacc1 += ua; }
+        }
+      }
+    }
+  }
+  if (A.mode == CORR_PREDICT) {
+#pragma unroll
+    for (int rgi = 0; rgi < 2; ++rgi) {
+      double f = rgi ? facc1 : facc0, u = rgi ? uacc1 : uacc0;
+      f += __shfl_xor_sync(0xffffffffu, f, 1);
+      f += __shfl_xor_sync(0xffffffffu, f, 2);
+      u += __shfl_xor_sync(0xffffffffu, u, 1);
+      u += __shfl_xor_sync(0xffffffffu, u, 2);
+      const int row = 8 * (warp + 8 * rgi) + g;
+      const long gp = (long)ti * TB + row;
+      if (ch == 0 && gp < A.npts) {
+        A.fdot[gp] = f;
+        if (A.udot) A.udot[gp] = u;
+      }
+    }
+  }
+}
+
+// ==================================================================== DMMA GEMM core
+constexpr int CH_THREADS = 512;     // 16 warps: 4 (M) x 4 (N), warp tile 32x32
+constexpr int NSTAGE = 5;           // stage = A slab + B slab = 32 KiB
+constexpr int STAGE_ELEMS = 2 * SLAB_ELEMS;
+constexpr int LDP = TB + 1;         // POTF2 scratch leading dimension (odd -> conflict free)
+
+struct WarpPos {
+  int wm, wn, g, t;
+};
+
+__device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+}
+
+// one 16-wide k slab: acc += As(128x16) * Bs(128x16)^T on the warp's 32x32 sub-tile
+__device__ __forceinline__ void mma_slab(double (&acc)[4][4][2], const double* As, const double* Bs,
+                                         const WarpPos& w) {
+#pragma unroll
+  for (int kq = 0; kq < 4; ++kq) {
+    const int sw = ((kq ^ (w.g & 3)) << 2) + w.t;
+    double a[4], b[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) a[mt] = As[(32 * w.wm + 8 * mt + w.g) * KS + sw];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[(32 * w.wn + 8 * nt + w.g) * KS + sw];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+
+// acc += A(128 x 16*nslab) * B(128 x 16*nslab)^T, both operands streamed slab by slab from
+// HBM/L2 with cp.async.bulk into an NSTAGE-deep mbarrier pipeline.  `it` is the running
+// slab counter (identical in all threads) that defines stage and parity.
+template <bool SAME, bool SKIP_UPPER, typename OnSlab>
+__device__ __forceinline__ void gemm_stream(double (&acc)[4][4][2], const double* __restrict__ gA,
+                                            const double* __restrict__ gB, int nslab,
+                                            double* stages, uint64_t* full, uint32_t& it,
+                                            const WarpPos& w, OnSlab on_slab) {
+  const int tid = threadIdx.x;
+  auto issue = [&](int q, uint32_t cur) {
+    const int st = cur % NSTAGE;
+    double* dst = stages + (size_t)st * STAGE_ELEMS;
+    mbar_expect_tx(&full[st], SAME ? SLAB_BYTES : 2 * SLAB_BYTES);
+    bulk_g2s(dst, gA + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
+    if (!SAME) bulk_g2s(dst + SLAB_ELEMS, gB + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
+  };
+  if (tid == 0) {
+    const int pro = nslab < NSTAGE - 1 ? nslab : NSTAGE - 1;
+    for (int q = 0; q < pro; ++q) issue(q, it + q);
+  }
+  for (int q = 0; q < nslab; ++q) {
+    const uint32_t cur = it + q;
+    const int st = cur % NSTAGE;
+    if (tid == 0 && q + NSTAGE - 1 < nslab) issue(q + NSTAGE - 1, cur + NSTAGE - 1);
+    mbar_wait(&full[st], (cur / NSTAGE) & 1);
+    const double* As = stages + (size_t)st * STAGE_ELEMS;
+    const double* Bs = SAME ? As : As + SLAB_ELEMS;
+    if (!SKIP_UPPER || w.wm >= w.wn) mma_slab(acc, As, Bs, w);
+    on_slab(Bs, q);
+    __syncthreads();
+  }
+  it += nslab;
+}
+
+struct NoSlabOp {
+  __device__ __forceinline__ void operator()(const double*, int) const {}
+};
+
+__device__ __forceinline__ void init_barriers(uint64_t* bars, int nbar) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nbar; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+}
+
+// naive (debug) GEMM: same contract as gemm_stream, plain global loads + DFMA
+__device__ __forceinline__ void gemm_naive(double (&acc)[4][4][2], const double* gA, const double* gB, int nslab,
+                           const WarpPos& w) {
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t + e;
+        double s = 0.0;
+        for (int q = 0; q < nslab; ++q)
+          for (int k = 0; k < KS; ++k)
+            s = fma(gA[(size_t)q * SLAB_ELEMS + slab_off(r, k)], gB[(size_t)q * SLAB_ELEMS + slab_off(c, k)], s);
+        acc[mt][nt][e] += s;
+      }
+}
+
+// ---------------------------------------------------------- in-smem POTF2 + inverse
+// S (LDP-strided): lower triangle holds the SPD block on entry, L on exit; the strictly
+// upper part holds W = L^-1 transposed-shifted: W[r][c] (c <= r) lives at S[c*LDP + r + 1].
+// FACTOR=false: L is given (imported factor), only the inverse is computed.
+// Returns (to all threads) the first non-positive pivot index + 1, or 0.
+template <bool FACTOR>
+__device__ int potf2_inverse(double* S, int nthreads) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthreads >> 5;
+  int bad = 0;
+  // W = I
+  for (int idx = tid; idx < TB * TB; idx += nthreads) {
+    int c = idx / TB, r = idx - c * TB;
+    if (c <= r) S[c * LDP + r + 1] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < TB; ++k) {
+    double piv = S[k * LDP + k];
+    double dk;
+    if (FACTOR) {
+      if (!(piv > 0.0)) {
+        if (!bad) bad = k + 1;
+        piv = 1.0;
+      }
+      dk = sqrt(piv);
+    } else {
+      dk = (piv != 0.0) ? piv : 1.0;
+    }
+    const double inv = 1.0 / dk;
+    __syncthreads();  // everyone has read the pivot before it is overwritten
+    // scale column k of L (rows > k) and row k of W (cols <= k)
+    const int mrows = TB - 1 - k;
+    for (int idx = tid; idx < mrows + k + 1; idx += nthreads) {
+      if (idx < mrows) {
+        if (FACTOR) S[(k + 1 + idx) * LDP + k] *= inv;
+      } else {
+        int c = idx - mrows;
+        S[c * LDP + k + 1] *= inv;
+      }
+    }
+    if (FACTOR && tid == 0) S[k * LDP + k] = dk;
+    __syncthreads();
+    // (a) trailing update of S (lower part), (b) eliminate column k from W
+    if (FACTOR) {
+      for (int c = k + 1 + warp; c < TB; c += nwarp) {
+        const double lc = S[c * LDP + k];
+        for (int r = c + lane; r < TB; r += 32) S[r * LDP + c] = fma(-S[r * LDP + k], lc, S[r * LDP + c]);
+      }
+    }
+    for (int c = warp; c <= k; c += nwarp) {
+      const double wkc = S[c * LDP + k + 1];
+      for (int r = k + 1 + lane; r < TB; r += 32)
+        S[c * LDP + r + 1] = fma(-S[r * LDP + k], wkc, S[c * LDP + r + 1]);
+    }
+    __syncthreads();
+  }
+  return bad;
+}
+
+// write L (lower incl. diagonal, zeros above) and W from the POTF2 scratch to tile layout
+__device__ void store_LW(const double* S, double* Ltile, double* Wtile, int nthreads) {
+  for (int idx = threadIdx.x; idx < TILE_ELEMS / 4; idx += nthreads) {
+    // idx -> (slab, row, chunk)
+    const int ch = idx & 3, row = (idx >> 2) & (TB - 1), s = idx >> 9;
+    const int c0 = s * KS + 4 * ch;
+    double l[4], wv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int c = c0 + e;
+      l[e] = (c <= row) ? S[row * LDP + c] : 0.0;
+      wv[e] = (c <= row) ? S[c * LDP + row + 1] : 0.0;
+    }
+    const int off = s * SLAB_ELEMS + row * KS + ((ch ^ (row & 3)) << 2);
+    if (Ltile) {
+      double2* dl = reinterpret_cast<double2*>(Ltile + off);
+      dl[0] = make_double2(l[0], l[1]);
+      dl[1] = make_double2(l[2], l[3]);
+    }
+    double2* dw = reinterpret_cast<double2*>(Wtile + off);
+    dw[0] = make_double2(wv[0], wv[1]);
+    dw[1] = make_double2(wv[2], wv[3]);
+  }
+}
+
+// ============================================================================ K2
+template <bool NAIVE>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chol_diag_kernel(CholArgs A, int j) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);                 // NSTAGE*32 KiB, aliased by S
+  double* tvec = stages + (size_t)NSTAGE * STAGE_ELEMS;                 // [128][MAXQ]
+  uint64_t* full = reinterpret_cast<uint64_t*>(tvec + TB * MAXQ);
+  __shared__ double s_red[CH_THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpPos w{warp & 3, warp >> 2, lane >> 2, lane & 3};
+  const long m = blockIdx.x;
+  double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+  const double* rowj = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
+  double* Cjj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
+  const int nq = A.nq;
+  const double* zb = A.Z + (size_t)m * A.nq * A.npad;
+  init_barriers(full, NSTAGE);
+
+  double acc[4][4][2];
+  zero_acc(acc);
+  double tacc[MAXQ];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) tacc[q] = 0.0;
+  const int rr = tid >> 2, hh = tid & 3;
+
+  uint32_t it = 0;
+  const int nslab = NSLAB * j;
+  if (NAIVE) {
+    gemm_naive(acc, rowj, rowj, nslab, w);
+    for (int q = 0; q < nslab; ++q)
+      for (int e = 0; e < 4; ++e) {
+        double lv = rowj[(size_t)q * SLAB_ELEMS + slab_off(rr, 4 * hh + e)];
+#pragma unroll
+        for (int qq = 0; qq < MAXQ; ++qq)
+          if (qq < nq) tacc[qq] = fma(lv, zb[(size_t)qq * A.npad + q * KS + 4 * hh + e], tacc[qq]);
+      }
+  } else {
+    gemm_stream<true, true>(acc, rowj, rowj, nslab, stages, full, it, w,
+      [&](const double* Bs, int q) {
+        // fused forward substitution: t[r] -= L_jk[r][c] * Z_k[c]   (likelihood_func.py:183-193)
+        const double2* lp = reinterpret_cast<const double2*>(Bs + rr * KS + ((hh ^ (rr & 3)) << 2));
+        double2 l01 = lp[0], l23 = lp[1];
+        const int col = q * KS + 4 * hh;
+#pragma unroll
+        for (int qq = 0; qq < MAXQ; ++qq) {
+          if (qq < nq) {
+            const double* z = zb + (size_t)qq * A.npad + col;
+            double s = tacc[qq];
+            s = fma(l01.x, z[0], s); s = fma(l01.y, z[1], s);
+            s = fma(l23.x, z[2], s); s = fma(l23.y, z[3], s);
+            tacc[qq] = s;
+          }
+        }
+      });
+  }
+  // ---- S = Psi_jj - acc (lower warp tiles only), into the POTF2 scratch (aliases stages)
+  double* S = stages;
+  __syncthreads();
+  if (w.wm >= w.wn) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
+        const double2 p = *reinterpret_cast<const double2*>(Cjj + tile_off(r, c));
+        if (c <= r) S[r * LDP + c] = p.x - acc[mt][nt][0];
+        if (c + 1 <= r) S[r * LDP + c + 1] = p.y - acc[mt][nt][1];
+      }
+  }
+  // RHS: t = R_j - sum_k L_jk Z_k
+#pragma unroll
+  for (int qq = 0; qq < MAXQ; ++qq) {
+    if (qq < nq) {
+      double s = tacc[qq];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (hh == 0) tvec[rr * MAXQ + qq] = A.R[(size_t)qq * A.npad + j * TB + rr] - s;
+    }
+  }
+  __syncthreads();
+  const int bad = potf2_inverse<true>(S, CH_THREADS);
+  if (tid == 0 && bad && A.info[m] == 0) A.info[m] = j * TB + bad;
+  // ---- outputs
+  store_LW(S, Cjj, A.W + ((size_t)m * A.nt + j) * TILE_ELEMS, CH_THREADS);
+  // Z_j = W_jj t
+  {
+    const int r = tid >> 2;
+    for (int qq = tid & 3; qq < nq; qq += 4) {
+      double s = 0.0;
+      for (int c = 0; c <= r; ++c) s = fma(S[c * LDP + r + 1], tvec[c * MAXQ + qq], s);
+      A.Z[((size_t)m * A.nq + qq) * A.npad + j * TB + r] = s;
+    }
+  }
+  // log-det partial: sum ln L_rr (padded rows are exactly 1)
+  {
+    double v = (tid < TB) ? log(fabs(S[tid * LDP + tid])) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int i = 0; i < 4; ++i) s += s_red[i];
+      A.logdet[m] = (j == 0 ? 0.0 : A.logdet[m]) + s;
+    }
+  }
+}
+
+// inverse of an imported diagonal block (predictor_load path): W_jj = inv(L_jj)
+__global__ void __launch_bounds__(CH_THREADS, 1)
+diag_inverse_kernel(CholArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* S = reinterpret_cast<double*>(smem_raw);
+  const int j = blockIdx.x;
+  const long m = blockIdx.y;
+  double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+  const double* Ljj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
+  for (int idx = threadIdx.x; idx < TILE_ELEMS; idx += CH_THREADS) {
+    int r = idx >> 7, c = idx & (TB - 1);
+    if (c <= r) S[r * LDP + c] = Ljj[tile_off(r, c)];
+  }
+  __syncthreads();
+  potf2_inverse<false>(S, CH_THREADS);
+  store_LW(S, nullptr, A.W + ((size_t)m * A.nt + j) * TILE_ELEMS, CH_THREADS);
+}
+
+// ============================================================================ K3
+// tile (i,j) of the factor (MODE_CHOL) or tile (pt,j) of a prediction chunk (MODE_PRED):
+//   X = (C - A_row * B_row^T) * W_jj^T
+template <bool NAIVE>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chol_panel_kernel(CholArgs A, int j) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);          // 5 x 32 KiB
+  double* Cs = stages;                                           // 128 KiB (aliases stages 0..3)
+  double* Ws = stages + 4 * STAGE_ELEMS;                         // 2 x 16 KiB (aliases stage 4)
+  double* rowred = stages + (size_t)NSTAGE * STAGE_ELEMS;        // [128][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(rowred + TB * 4);
+  uint64_t* wfull = full + NSTAGE;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpPos w{warp & 3, warp >> 2, lane >> 2, lane & 3};
+  const double *rowA, *rowB, *Wj;
+  double* Cij;
+  long ssq_base = 0;
+  if (A.pred_mode) {
+    const long pt = blockIdx.x;
+    double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
+    rowA = base;
+    Cij = base + (size_t)j * TILE_ELEMS;
+    rowB = A.L + (size_t)tri_index(j, 0) * TILE_ELEMS;
+    Wj = A.W + (size_t)j * TILE_ELEMS;
+    ssq_base = pt * TB;
+  } else {
+    const int i = j + 1 + blockIdx.x;
+    const long m = blockIdx.y;
+    double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+    rowA = tiles + (size_t)tri_index(i, 0) * TILE_ELEMS;
+    rowB = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
+    Cij = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;
+    Wj = A.W + ((size_t)m * A.nt + j) * TILE_ELEMS;
+  }
+  init_barriers(full, NSTAGE + 2);
+
+  double acc[4][4][2];
+  zero_acc(acc);
+  uint32_t it = 0;
+  if (NAIVE) gemm_naive(acc, rowA, rowB, NSLAB * j, w);
+  else gemm_stream<false, false>(acc, rowA, rowB, NSLAB * j, stages, full, it, w, NoSlabOp());
+
+  // ---- C = Psi_ij - acc  -> Cs (tile layout, A operand of the TRSM-GEMM)
+  __syncthreads();
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
+      const int off = tile_off(r, c);
+      const double2 p = *reinterpret_cast<const double2*>(Cij + off);
+      *reinterpret_cast<double2*>(Cs + off) = make_double2(p.x - acc[mt][nt][0], p.y - acc[mt][nt][1]);
+    }
+  fence_proxy_async();   // Ws region was last written by the async proxy; order generic accesses
+  __syncthreads();
+
+  // ---- X[r][c] = sum_{k<=c} C[r][k] * W[c][k]   (W lower triangular)
+  zero_acc(acc);
+  if (NAIVE) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t + e;
+          double s = 0.0;
+          for (int k = 0; k <= c; ++k) s = fma(Cs[tile_off(r, k)], Wj[tile_off(c, k)], s);
+          acc[mt][nt][e] = s;
+        }
+  } else {
+    if (tid == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_expect_tx(&wfull[s], SLAB_BYTES);
+        bulk_g2s(Ws + (size_t)s * SLAB_ELEMS, Wj + (size_t)s * SLAB_ELEMS, SLAB_BYTES, &wfull[s]);
+      }
+    }
+    for (int s = 0; s < NSLAB; ++s) {
+      const int st = s & 1;
+      mbar_wait(&wfull[st], (s >> 1) & 1);
+      if (s <= 2 * w.wn + 1) mma_slab(acc, Cs + (size_t)s * SLAB_ELEMS, Ws + (size_t)st * SLAB_ELEMS, w);
+      __syncthreads();
+      if (tid == 0 && s + 2 < NSLAB) {
+        mbar_expect_tx(&wfull[st], SLAB_BYTES);
+        bulk_g2s(Ws + (size_t)st * SLAB_ELEMS, Wj + (size_t)(s + 2) * SLAB_ELEMS, SLAB_BYTES, &wfull[st]);
+      }
+    }
+  }
+  // ---- store X (tile layout) and, for prediction, accumulate ||x_row||^2
+  double rs[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
+      *reinterpret_cast<double2*>(Cij + tile_off(r, c)) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      rs[mt] = fma(acc[mt][nt][0], acc[mt][nt][0], rs[mt]);
+      rs[mt] = fma(acc[mt][nt][1], acc[mt][nt][1], rs[mt]);
+    }
+  if (A.pred_mode) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      double v = rs[mt];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (w.t == 0) rowred[(32 * w.wm + 8 * mt + w.g) * 4 + w.wn] = v;
+    }
+    __syncthreads();
+    if (tid < TB) {
+      double v = ((rowred[tid * 4 + 0] + rowred[tid * 4 + 1]) + rowred[tid * 4 + 2]) + rowred[tid * 4 + 3];
+      double* dst = A.ssq + ssq_base + tid;
+      *dst = (j == 0 ? 0.0 : *dst) + v;
+    }
+  }
+}
+
+// ============================================================================ K4
+// beta = (B^T B)^-1 B^T a, r = a - B beta, q = r^T r, with a = L^-1 y, B = L^-1 F
+// (Z rows).  Equivalent to likelihood_func.py:180-204 (<=1e-13 rel).
+__device__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int i = 0; i < nw; ++i) s += red[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(256)
+lik_finalize_kernel(FinArgs A) {
+  __shared__ double red[8];
+  __shared__ double G[(MAXQ - 1) * (MAXQ - 1)], gv[MAXQ - 1], beta[MAXQ - 1];
+  const long m = blockIdx.x;
+  const int p = A.nq - 1, npad = A.npad;
+  const double* a = A.Z + (size_t)m * A.nq * npad;
+  const double* B = a + npad;
+  // G = B^T B, g = B^T a
+  for (int i = 0; i < p; ++i) {
+    for (int k = 0; k <= i; ++k) {
+      double v = 0.0;
+      for (int r = threadIdx.x; r < npad; r += blockDim.x) v = fma(B[(size_t)i * npad + r], B[(size_t)k * npad + r], v);
+      v = block_sum(v, red);
+      if (threadIdx.x == 0) G[i * p + k] = G[k * p + i] = v;
+    }
+    double v = 0.0;
+    for (int r = threadIdx.x; r < npad; r += blockDim.x) v = fma(B[(size_t)i * npad + r], a[r], v);
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) gv[i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // p x p SPD solve (Cholesky), p <= 7
+    double Lg[(MAXQ - 1) * (MAXQ - 1)];
+    for (int i = 0; i < p; ++i)
+      for (int k = 0; k <= i; ++k) {
+        double s = G[i * p + k];
+        for (int t = 0; t < k; ++t) s -= Lg[i * p + t] * Lg[k * p + t];
+        Lg[i * p + k] = (i == k) ? sqrt(s) : s / Lg[k * p + k];
+      }
+    double yv[MAXQ - 1];
+    for (int i = 0; i < p; ++i) {
+      double s = gv[i];
+      for (int t = 0; t < i; ++t) s -= Lg[i * p + t] * yv[t];
+      yv[i] = s / Lg[i * p + i];
+    }
+    for (int i = p - 1; i >= 0; --i) {
+      double s = yv[i];
+      for (int t = i + 1; t < p; ++t) s -= Lg[t * p + i] * beta[t];
+      beta[i] = s / Lg[i * p + i];
+    }
+  }
+  __syncthreads();
+  double v = 0.0;
+  for (int r = threadIdx.x; r < npad; r += blockDim.x) {
+    double res = a[r];
+    for (int i = 0; i < p; ++i) res = fma(-B[(size_t)i * npad + r], beta[i], res);
+    if (A.resid) A.resid[(size_t)m * npad + r] = res;
+    v = fma(res, res, v);
+  }
+  const double q = block_sum(v, red);
+  if (threadIdx.x == 0) {
+    const double* cand = A.cand + m * A.cand_stride;
+    const double sig_tv = cand[A.cand_stride - 1];
+    const double half_logdet = A.logdet[m];   // sum ln L_ii = 0.5 * LnDetPsi
+    double nll, sig2;
+    if (A.trainvar) {
+      sig2 = sig_tv;
+      nll = half_logdet + 0.5 * A.nsamp * log(2.0 * 3.141592653589793) + 0.5 * A.nsamp * log(sig2) + q / (2.0 * sig2);
+    } else {
+      sig2 = q / (double)A.n;
+      nll = 0.5 * (double)A.n * log(sig2) + half_logdet;
+    }
+    if (A.info[m] != 0 || !(nll == nll)) nll = INFINITY;
+    A.nll[m] = nll;
+    if (A.sigma2) A.sigma2[m] = sig2;
+    if (A.beta) for (int i = 0; i < p; ++i) A.beta[m * p + i] = beta[i];
+    if (A.btb) A.btb[m] = G[0];
+  }
+}
+
+// ================================================================== backsolve (fit)
+// X_j = W_jj^T (RHS_j - sum_{k>j} L_kj^T X_k), j = nt-1 .. 0, nq columns; one CTA.
+__global__ void __launch_bounds__(CH_THREADS, 1)
+backsolve_kernel(BackArgs A) {
+  __shared__ double xs[TB * MAXQ];       // X_k block (broadcast reads); reused as t
+  __shared__ double part[4][TB][MAXQ];
+  double* tv = xs;
+  const int tid = threadIdx.x, r = tid & (TB - 1), part_id = tid >> 7;
+  const int nq = A.nq, npad = A.npad, nt = A.nt;
+  for (int j = nt - 1; j >= 0; --j) {
+    double acc[MAXQ];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) acc[q] = 0.0;
+    for (int k = j + 1; k < nt; ++k) {
+      __syncthreads();
+      for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
+        int c = idx / nq, q = idx - c * nq;
+        xs[c * MAXQ + q] = A.out[(size_t)q * npad + k * TB + c];
+      }
+      __syncthreads();
+      const double* T = A.L + (size_t)tri_index(k, j) * TILE_ELEMS;
+      for (int c = 32 * part_id; c < 32 * part_id + 32; ++c) {
+        const double l = T[tile_off(c, r)];
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q)
+          if (q < nq) acc[q] = fma(l, xs[c * MAXQ + q], acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q)
+      if (q < nq) part[part_id][r][q] = acc[q];
+    __syncthreads();
+    if (tid < TB) {
+      for (int q = 0; q < nq; ++q) {
+        double s = ((part[0][r][q] + part[1][r][q]) + part[2][r][q]) + part[3][r][q];
+        tv[r * MAXQ + q] = A.rhs[(size_t)q * npad + j * TB + r] - s;
+      }
+    }
+    __syncthreads();
+    // x_j[r] = sum_{c >= r} W_jj[c][r] t[c]
+    const double* Wj = A.W + (size_t)j * TILE_ELEMS;
+    for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
+      int rr = idx % TB, q = idx / TB;
+      double s = 0.0;
+      for (int c = rr; c < TB; ++c) s = fma(Wj[tile_off(c, rr)], tv[c * MAXQ + q], s);
+      A.out[(size_t)q * npad + j * TB + rr] = s;
+    }
+    __syncthreads();
+    __threadfence_block();
+  }
+}
+
+// ================================================================ forward solve (load)
+// X_j = W_jj (RHS_j - sum_{k<j} L_jk X_k), j = 0 .. nt-1, nq columns; one CTA.
+// Used when a factor is imported from KrigInfo['U'] (prediction.py:233-235, 245-246).
+__global__ void __launch_bounds__(CH_THREADS, 1)
+forwardsolve_kernel(BackArgs A) {
+  __shared__ double xs[TB * MAXQ];
+  __shared__ double part[4][TB][MAXQ];
+  double* tv = xs;
+  const int tid = threadIdx.x, r = tid & (TB - 1), part_id = tid >> 7;
+  const int nq = A.nq, npad = A.npad, nt = A.nt;
+  for (int j = 0; j < nt; ++j) {
+    double acc[MAXQ];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) acc[q] = 0.0;
+    for (int k = 0; k < j; ++k) {
+      __syncthreads();
+      for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
+        int c = idx / nq, q = idx - c * nq;
+        xs[c * MAXQ + q] = A.out[(size_t)q * npad + k * TB + c];
+      }
+      __syncthreads();
+      const double* T = A.L + (size_t)tri_index(j, k) * TILE_ELEMS;
+      for (int c = 32 * part_id; c < 32 * part_id + 32; ++c) {
+        const double l = T[tile_off(r, c)];
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q)
+          if (q < nq) acc[q] = fma(l, xs[c * MAXQ + q], acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q)
+      if (q < nq) part[part_id][r][q] = acc[q];
+    __syncthreads();
+    if (tid < TB) {
+      for (int q = 0; q < nq; ++q) {
+        double s = ((part[0][r][q] + part[1][r][q]) + part[2][r][q]) + part[3][r][q];
+        tv[r * MAXQ + q] = A.rhs[(size_t)q * npad + j * TB + r] - s;
+      }
+    }
+    __syncthreads();
+    // x_j[r] = sum_{c <= r} W_jj[r][c] t[c]
+    const double* Wj = A.W + (size_t)j * TILE_ELEMS;
+    for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
+      int rr = idx % TB, q = idx / TB;
+      double s = 0.0;
+      for (int c = 0; c <= rr; ++c) s = fma(Wj[tile_off(rr, c)], tv[c * MAXQ + q], s);
+      A.out[(size_t)q * npad + j * TB + rr] = s;
+    }
+    __syncthreads();
+    __threadfence_block();
+  }
+}
+
+// ========================================================================= decode
+// x -> per-candidate parameter rows.  Mirrors likelihood_func.py:57-79 and nuggetset
+// (:121-165): layout [log10 theta | log10 sigma2 (trainvar) | log10 nugget (tuned) |
+// kernel weights (nkernel>1)] decided by nbhyp.
+__global__ void decode_kernel(DecodeArgs A) {
+  const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= A.P) return;
+  const double* x = A.x + m * A.nbhyp;
+  double* c = A.cand + m * A.cand_stride;
+  const int nt = A.ntheta, nk = A.nkernel;
+  for (int k = 0; k < nt; ++k) {
+    const double xk = A.iso ? x[0] : x[k];
+    const double th = A.theta_is_linear ? xk : pow(10.0, xk);
+    const double th2 = __dmul_rn(th, th);
+    c[k] = th;
+    c[nt + k] = __drcp_rn(th);
+    c[2 * nt + k] = th2;
+    c[3 * nt + k] = __drcp_rn(th2);
+  }
+  const int off = (A.iso ? 1 : nt) + (A.trainvar ? 1 : 0);
+  double eps = A.eps_fixed;
+  if (A.layout & 1) eps = pow(10.0, x[off]);             // tuned nugget
+  const int woff = off + ((A.layout & 1) ? 1 : 0);
+  if (A.layout & 2) {                                    // composite weights / sum
+    double s = 0.0;
+    for (int k = 0; k < nk; ++k) s = __dadd_rn(s, x[woff + k]);
+    for (int k = 0; k < nk; ++k) c[4 * nt + k] = __ddiv_rn(x[woff + k], s);
+  } else if (A.wgkf_given) {
+    for (int k = 0; k < nk; ++k) c[4 * nt + k] = A.wgkf_given[k];
+  } else {
+    for (int k = 0; k < nk; ++k) c[4 * nt + k] = 1.0;
+  }
+  c[4 * nt + nk] = eps;
+  c[4 * nt + nk + 1] = A.trainvar ? pow(10.0, x[A.iso ? 1 : nt]) : 0.0;
+}
+
+// ============================================================ import / export (fit)
+__global__ void import_U_kernel(const double* __restrict__ U, int n, int nt, double* __restrict__ tiles) {
+  // tile layout L from row-major upper U (= L^T); identity padding
+  const int t = blockIdx.x;
+  int ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  while (ti * (ti + 1) / 2 > t) --ti;
+  const int tj = t - ti * (ti + 1) / 2;
+  double* T = tiles + (size_t)t * TILE_ELEMS;
+  for (int idx = threadIdx.x; idx < TILE_ELEMS; idx += blockDim.x) {
+    int c = idx >> 7, r = idx & (TB - 1);   // r fastest: U[gc][gr] contiguous in gr
+    int gr = ti * TB + r, gc = tj * TB + c;
+    double v;
+    if (gr < n && gc < n) v = (gc <= gr) ? U[(size_t)gc * n + gr] : 0.0;
+    else v = (gr == gc) ? 1.0 : 0.0;
+    T[tile_off(r, c)] = v;
+  }
+}
+
+__global__ void export_kernel(const double* __restrict__ tiles, int n, double* __restrict__ out, int what) {
+  // what = 0: U row-major upper (U[r][c] = L[c][r], zeros below the diagonal)
+  // what = 1: full symmetric Psi
+  const size_t total = (size_t)n * n;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(idx / n), c = (int)(idx - (size_t)r * n);
+    double v;
+    if (what == 0) {
+      v = (c >= r) ? tiles[(size_t)tri_index(c / TB, r / TB) * TILE_ELEMS + tile_off(c % TB, r % TB)] : 0.0;
+    } else {
+      int hi = r >= c ? r : c, lo = r >= c ? c : r;
+      v = tiles[(size_t)tri_index(hi / TB, lo / TB) * TILE_ELEMS + tile_off(hi % TB, lo % TB)];
+    }
+    out[idx] = v;
+  }
+}
+
+__global__ void add_diag_kernel(double* tiles, int n, const double* eps_ptr) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double eps = *eps_ptr;
+    double* p = tiles + (size_t)tri_index(i / TB, i / TB) * TILE_ELEMS + tile_off(i % TB, i % TB);
+    *p = __dadd_rn(*p, eps);
+  }
+}
+
+// ======================================================================= epilogue
+// prediction.py:233-235 (mean), :245-251 (SSqr, s), :258-310 (acquisition values),
+// akmcs.py:281-285 (U-function)
+__global__ void predict_epilogue_kernel(EpiArgs A) {
+  const double tiny = 2.2250738585072014e-308;
+  const double RSQ2 = 0.7071067811865475;        // 1/np.sqrt(2)
+  const double SQ2PI = 2.5066282746310002;       // np.sqrt(2*np.pi)
+  long zero_ss = 0;
+  int any = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.npts; i += (long)gridDim.x * blockDim.x) {
+    const double f = A.beta + A.fdot[i];
+    if (A.pred) A.pred[i] = f;
+    if (!A.need_var) continue;
+    const double u = A.udot[i] - 1.0;
+    const double term1 = 1.0 - A.ssq[i];
+    const double term2 = u * (u / A.btb);
+    const double ssqr = A.sigma2 * (term1 + term2);
+    const double s = sqrt(fabs(ssqr));
+    if (A.ssqr) A.ssqr[i] = ssqr;
+    if (A.s) A.s[i] = s;
+    if (ssqr == 0.0) ++zero_ss;
+    if (A.ei) {
+      const double dlt = A.ymin - f;
+      const double t1 = dlt * (0.5 + 0.5 * erf(RSQ2 * dlt / s));
+      const double t2 = s / SQ2PI * exp(-0.5 * (dlt * dlt) / ssqr);
+      if (t1 != 0.0 || t2 != 0.0) any = 1;
+      A.ei[i] = -(t1 + t2 + tiny);
+    }
+    if (A.poi) A.poi[i] = -(0.5 + 0.5 * erf(RSQ2 * (A.ymin - f) / s));
+    if (A.pof) {
+      const double z = A.limit_ge ? (f - A.limit) / s : (A.limit - f) / s;
+      A.pof[i] = 0.5 + 0.5 * erf(RSQ2 * z);
+    }
+    if (A.ufun) A.ufun[i] = fabs(f) / s;
+  }
+  if (A.stats) {
+    if (zero_ss) atomicAdd(reinterpret_cast<unsigned long long*>(A.stats), (unsigned long long)zero_ss);
+    if (any) atomicOr(reinterpret_cast<unsigned long long*>(A.stats + 1), 1ull);
+  }
+}
+
+// ====================================================================== launchers
+static inline size_t corr_smem_bytes(int d) {
+  const int lda = d | 1;
+  return (size_t)(((TB * lda + 1) & ~1) + d * TB) * sizeof(double);
+}
+
+#define KB_LAUNCH_CHECK()                          \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return e__;            \
+  } while (0)
+
+// dynamic-smem opt-in is per device (context): remember what was set for each device
+static size_t g_corr_attr[64] = {0};
+static bool g_chol_attr[64] = {false};
+static inline int cur_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 63;
+}
+constexpr size_t DIAG_SMEM = (size_t)NSTAGE * STAGE_ELEMS * 8 + TB * MAXQ * 8 + NSTAGE * 8;
+constexpr size_t PANEL_SMEM = (size_t)NSTAGE * STAGE_ELEMS * 8 + TB * 4 * 8 + (NSTAGE + 2) * 8;
+constexpr size_t DINV_SMEM = (size_t)TB * LDP * 8 + 16;
+static_assert((size_t)TB * LDP * 8 + 16 <= (size_t)NSTAGE * STAGE_ELEMS * 8, "POTF2 scratch must fit in the stage buffers");
+
+cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st) {
+  const size_t sm = corr_smem_bytes(a.spec.d);
+  if (sm > 227 * 1024) return cudaErrorInvalidValue;
+  const int dev = cur_dev();
+  if (sm > g_corr_attr[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(corr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm > 48 * 1024 ? sm : 48 * 1024));
+    if (e != cudaSuccess) return e;
+    g_corr_attr[dev] = sm;
+  }
+  corr_tile_kernel<<<dim3(grid_x, grid_y), CORR_THREADS, sm, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+static cudaError_t chol_attrs() {
+  const int dev = cur_dev();
+  if (g_chol_attr[dev]) return cudaSuccess;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(chol_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(chol_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(chol_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(chol_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DINV_SMEM);
+  if (e != cudaSuccess) return e;
+  g_chol_attr[dev] = true;
+  return cudaSuccess;
+}
+
+cudaError_t launch_chol_diag(const CholArgs& a, int j, int nmat, cudaStream_t st) {
+  cudaError_t e = chol_attrs();
+  if (e != cudaSuccess) return e;
+  if (a.naive) chol_diag_kernel<true><<<nmat, CH_THREADS, DIAG_SMEM, st>>>(a, j);
+  else chol_diag_kernel<false><<<nmat, CH_THREADS, DIAG_SMEM, st>>>(a, j);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st) {
+  cudaError_t e = chol_attrs();
+  if (e != cudaSuccess) return e;
+  if (grid_x <= 0 || grid_y <= 0) return cudaSuccess;
+  if (a.naive) chol_panel_kernel<true><<<dim3(grid_x, grid_y), CH_THREADS, PANEL_SMEM, st>>>(a, j);
+  else chol_panel_kernel<false><<<dim3(grid_x, grid_y), CH_THREADS, PANEL_SMEM, st>>>(a, j);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_diag_inverse(const CholArgs& a, int nmat, cudaStream_t st) {
+  cudaError_t e = chol_attrs();
+  if (e != cudaSuccess) return e;
+  diag_inverse_kernel<<<dim3(a.nt, nmat), CH_THREADS, DINV_SMEM, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_finalize(const FinArgs& a, int nmat, cudaStream_t st) {
+  lik_finalize_kernel<<<nmat, 256, 0, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_backsolve(const BackArgs& a, cudaStream_t st) {
+  backsolve_kernel<<<1, CH_THREADS, 0, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_forwardsolve(const BackArgs& a, cudaStream_t st) {
+  forwardsolve_kernel<<<1, CH_THREADS, 0, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t st) {
+  decode_kernel<<<(int)((a.P + 127) / 128), 128, 0, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_import_U(const double* U, int n, int nt, double* tiles, cudaStream_t st) {
+  import_U_kernel<<<nt * (nt + 1) / 2, 256, 0, st>>>(U, n, nt, tiles);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_export(const double* tiles, int n, double* out, int what, cudaStream_t st) {
+  export_kernel<<<148 * 4, 256, 0, st>>>(tiles, n, out, what);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_add_diag(double* tiles, int n, const double* eps_ptr, cudaStream_t st) {
+  add_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(tiles, n, eps_ptr);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_epilogue(const EpiArgs& a, cudaStream_t st) {
+  long blocks = (a.npts + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  predict_epilogue_kernel<<<(int)blocks, 256, 0, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+}  // namespace kb200

@@ -1,0 +1,114 @@
+// kadal_b200 — kernel argument blocks and launchers (internal; the public ABI is include/kb200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include "kb200_corr.cuh"
+
+namespace kb200 {
+
+enum { CORR_ASSEMBLE = 0, CORR_PREDICT = 1 };
+
+struct CorrArgs {
+  CorrSpec spec;
+  int mode;
+  int n;                 // training samples
+  int nt;                // tiles per dimension (ceil(n / 128))
+  const double* X;       // [n][d] training inputs (already normalised)
+  const double* cand;    // [P][cand_stride]
+  int cand_stride;
+  // assembly
+  double* out;           // tile storage (assembly: [P][tiles_per_mat] tiles; predict: chunk [pt][nt] or null)
+  long tiles_per_mat;
+  int add_eps;
+  // prediction
+  const double* xpts;    // [npts][d] raw points
+  long npts;
+  int normtype;          // 0 none, 1 'default' (lb,ub), 2 'std' (mean,std)
+  const double* norm_a;
+  const double* norm_b;
+  const double* alpha;   // [nt*128] zero padded
+  const double* wvec;    // [nt*128] zero padded, or null
+  double* fdot;          // [npts]  psi^T alpha
+  double* udot;          // [npts]  psi^T w
+};
+
+struct CholArgs {
+  double* L;             // tile storage of the matrices being factorised (in place)
+  double* W;             // [P][nt] inverse diagonal blocks
+  long tiles_per_mat;
+  int nt, npad, n;
+  // fused forward substitution
+  int nq;                // RHS columns (1 + p)
+  const double* R;       // [nq][npad] shared RHS ([y F]^T, zero padded)
+  double* Z;             // [P][nq][npad]
+  double* logdet;        // [P]  sum ln L_ii
+  int* info;             // [P]
+  int naive;             // debug: plain-FMA GEMM instead of the DMMA pipeline
+  // prediction-as-extra-rows
+  int pred_mode;
+  double* chunk;         // [npt_tiles][nt] tiles (psi in, L^-1 psi out)
+  double* ssq;           // [npt_tiles*128]
+};
+
+struct FinArgs {
+  const double* Z;
+  const double* logdet;
+  const int* info;
+  const double* cand;
+  int cand_stride;
+  int nq, npad, n;
+  int trainvar;
+  double nsamp;
+  double* nll;           // [P]
+  double* sigma2;        // [P] or null
+  double* beta;          // [P][p] or null
+  double* btb;           // [P] or null  (B^T B = F^T Psi^-1 F, p = 1)
+  double* resid;         // [P][npad] or null  (a - B beta)
+};
+
+struct BackArgs {
+  const double* L;       // tiles of one matrix
+  const double* W;       // [nt] tiles
+  int nt, npad, nq;
+  const double* rhs;     // [nq][npad]
+  double* out;           // [nq][npad]
+};
+
+struct DecodeArgs {
+  const double* x;       // [P][nbhyp]
+  long P;
+  int nbhyp, ntheta, nkernel;
+  int iso;               // iso_gaussian: one theta replicated
+  int theta_is_linear;   // x already holds theta (not log10) — unused by the public API
+  int trainvar;
+  int layout;            // bit0: tuned nugget in x, bit1: kernel weights in x
+  double eps_fixed;      // 10**KrigInfo['nugget'] when the nugget is fixed
+  const double* wgkf_given;  // device [nkernel] or null
+  double* cand;
+  int cand_stride;
+};
+
+struct EpiArgs {
+  long npts;
+  double beta, sigma2, btb, ymin, limit;
+  int limit_ge, need_var;
+  const double* fdot;
+  const double* udot;
+  const double* ssq;
+  double *pred, *ssqr, *s, *ei, *poi, *pof, *ufun;
+  unsigned long long* stats;   // [0] = #(SSqr == 0), [1] = any nonzero EI term
+};
+
+cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st);
+cudaError_t launch_chol_diag(const CholArgs& a, int j, int nmat, cudaStream_t st);
+cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);
+cudaError_t launch_diag_inverse(const CholArgs& a, int nmat, cudaStream_t st);
+cudaError_t launch_finalize(const FinArgs& a, int nmat, cudaStream_t st);
+cudaError_t launch_backsolve(const BackArgs& a, cudaStream_t st);
+cudaError_t launch_import_U(const double* U, int n, int nt, double* tiles, cudaStream_t st);
+cudaError_t launch_export(const double* tiles, int n, double* out, int what, cudaStream_t st);
+cudaError_t launch_add_diag(double* tiles, int n, const double* eps_ptr, cudaStream_t st);
+cudaError_t launch_forwardsolve(const BackArgs& a, cudaStream_t st);
+cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t st);
+cudaError_t launch_epilogue(const EpiArgs& a, cudaStream_t st);
+
+}  // namespace kb200

@@ -1,0 +1,220 @@
+"""Device-resident view of a KrigInfo dict.
+
+The KrigInfo dict stays the single source of truth and stays picklable: device handles live
+in a side cache keyed by the identity (+ cheap checksum) of the arrays the reference reads
+(``likelihood_func.py:38-68``, ``prediction.py:122-157``), never inside the dict.
+"""
+import ctypes
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _capi
+from ._capi import c_void_p, ptr, as_f64, check
+
+
+def select_xy(KrigInfo):
+    """Same selection as likelihood_func.py:44-53 / prediction.py:138-146."""
+    if KrigInfo["standardization"] is False:
+        return KrigInfo["X"], KrigInfo["y"]
+    X = KrigInfo["X_norm"]
+    if "y_norm" in KrigInfo and np.any(np.asarray(KrigInfo["y_norm"]).ravel()[0] != 0):
+        return X, KrigInfo["y_norm"]
+    return X, KrigInfo["y"]
+
+
+def kernel_ids(KrigInfo):
+    kern = KrigInfo["kernel"]
+    if not isinstance(kern, (list, tuple)):
+        kern = [kern]
+    ids = []
+    for k in kern:
+        try:
+            ids.append(_capi.KERNEL_IDS[k.lower()])
+        except KeyError:
+            raise ValueError("Kernel option not available!")  # kernelfunc.py:31
+    return ids, list(kern) == ["iso_gaussian"]
+
+
+class GpuModel:
+    """Owns one ``kb200_model`` handle (training data + workspaces + predictor state)."""
+
+    def __init__(self, X, y, F, kernels, pls=None, nsamp=None, iso=False, device=None, naive=None):
+        lib = _capi.require_gpu()
+        self.lib = lib
+        X = as_f64(X)
+        y = as_f64(np.asarray(y).reshape(-1))
+        F = as_f64(F)
+        if F.ndim == 1:
+            F = F.reshape(-1, 1)
+        self.n, self.d = X.shape
+        self.p = F.shape[1]
+        if y.shape[0] != self.n or F.shape[0] != self.n:
+            raise ValueError("X, y, F row counts differ")
+        self.h = 0
+        if pls is not None:
+            pls = as_f64(pls)
+            self.h = pls.shape[1]
+        self.ntheta = self.h if self.h else self.d
+        self.nkernel = len(kernels)
+        self.iso = bool(iso)
+        if device is None:
+            device = int(os.environ.get("KADAL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            device = device % max(1, lib.kb200_device_count())
+        if naive is None:
+            naive = os.environ.get("KB200_NAIVE", "0") == "1"
+        flags = (_capi.FLAG_ISO if iso else 0) | (_capi.FLAG_NAIVE if naive else 0)
+        kid = (ctypes.c_int * self.nkernel)(*kernels)
+        h = c_void_p()
+        check(lib.kb200_model_create(ctypes.byref(h), device, self.n, self.d, self.p, self.h, ptr(X), ptr(y),
+                                     ptr(F), ptr(pls), kid, self.nkernel,
+                                     float(self.n if nsamp is None else nsamp), flags))
+        self.handle = h
+        self.device = device
+        self.ymin = float(np.min(y))
+        self.pred_token = None
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.kb200_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ likelihood
+    def lik_batch(self, Xpop, trainvar, nugget_log10):
+        Xpop = as_f64(np.atleast_2d(Xpop))
+        P, nb = Xpop.shape
+        nll = np.empty(P)
+        info = np.empty(P, dtype=np.int32)
+        check(self.lib.kb200_lik_batch(self.handle, ptr(Xpop), P, nb, int(bool(trainvar)),
+                                       float(nugget_log10), ptr(nll), ptr(info)))
+        return nll, info
+
+    def lik_batch_dev(self, x_ptr, P, nbhyp, trainvar, nugget_log10, nll_ptr, info_ptr, stream=0):
+        check(self.lib.kb200_lik_batch_dev(self.handle, c_void_p(x_ptr), P, nbhyp, int(bool(trainvar)),
+                                           float(nugget_log10), c_void_p(nll_ptr), c_void_p(info_ptr),
+                                           c_void_p(stream)))
+
+    def fit_state(self, x, trainvar, nugget_log10, want_U=True, want_Psi=True):
+        x = as_f64(np.asarray(x).reshape(-1))
+        n = self.n
+        U = np.empty((n, n)) if want_U else None
+        Psi = np.empty((n, n)) if want_Psi else None
+        BE = np.empty(self.p)
+        theta = np.empty(self.ntheta)
+        wgkf = np.empty(self.nkernel)
+        s2, nll, nug = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        info = ctypes.c_int()
+        check(self.lib.kb200_fit_state(self.handle, ptr(x), x.shape[0], int(bool(trainvar)), float(nugget_log10),
+                                       ptr(U), ptr(Psi), ptr(BE), ctypes.byref(s2), ctypes.byref(nll),
+                                       ctypes.byref(info), ptr(theta), ctypes.byref(nug), ptr(wgkf)))
+        return dict(U=U, Psi=Psi, BE=BE, sigma2=s2.value, nll=nll.value, info=info.value, theta=theta,
+                    nugget=nug.value, wgkf=wgkf)
+
+    def debug_psi(self, x, trainvar, nugget_log10, add_eps=False):
+        x = as_f64(np.asarray(x).reshape(-1))
+        Psi = np.empty((self.n, self.n))
+        check(self.lib.kb200_debug_psi(self.handle, ptr(x), x.shape[0], int(bool(trainvar)), float(nugget_log10),
+                                       int(add_eps), ptr(Psi)))
+        return Psi
+
+    # ------------------------------------------------------------------ prediction
+    def predictor_load(self, theta_log10, wgkf, U, BE, sigma2):
+        theta_log10 = as_f64(np.asarray(theta_log10).reshape(-1))
+        wgkf = as_f64(np.asarray(wgkf, dtype=float).reshape(-1))
+        U = as_f64(U)
+        BE = as_f64(np.asarray(BE).reshape(-1))
+        check(self.lib.kb200_predictor_load(self.handle, ptr(theta_log10), ptr(wgkf), ptr(U), ptr(BE),
+                                            float(sigma2)))
+
+    def predict(self, x, want, normtype=0, norm_a=None, norm_b=None, ymin=None, limit=0.0, limit_ge=True,
+                out=None):
+        """Host-pointer predict: returns dict name -> (npred,) array plus 'stats'."""
+        x = as_f64(np.atleast_2d(x))
+        npred = x.shape[0]
+        if x.shape[1] != self.d:
+            raise ValueError("prediction sites have %d columns, model has %d" % (x.shape[1], self.d))
+        names = ["pred", "ssqr", "s", "ei", "poi", "pof", "ufun"]
+        outs = {}
+        ptrs = []
+        for i, nm in enumerate(names):
+            if want & (1 << i):
+                arr = out[nm] if out is not None and nm in out else np.empty(npred)
+                outs[nm] = arr
+                ptrs.append(ptr(arr))
+            else:
+                ptrs.append(None)
+        stats = (ctypes.c_ulonglong * 2)()
+        na = as_f64(norm_a) if norm_a is not None else None
+        nb = as_f64(norm_b) if norm_b is not None else None
+        check(self.lib.kb200_predict(self.handle, ptr(x), npred, int(normtype), ptr(na), ptr(nb), int(want),
+                                     float(self.ymin if ymin is None else ymin), float(limit), int(bool(limit_ge)),
+                                     *ptrs, stats))
+        outs["stats"] = (int(stats[0]), int(stats[1]))
+        return outs
+
+    def predict_dev(self, x_ptr, npred, want, out_ptrs, normtype=0, norm_a=None, norm_b=None, ymin=None,
+                    limit=0.0, limit_ge=True, stream=0, want_stats=False):
+        """Device-pointer predict (x_ptr and out_ptrs are raw device addresses, e.g. torch
+        ``tensor.data_ptr()``); no host<->device traffic except the tiny normalisation vectors."""
+        na = as_f64(norm_a) if norm_a is not None else None
+        nb = as_f64(norm_b) if norm_b is not None else None
+        ptrs = [c_void_p(p) if p else None for p in out_ptrs]
+        stats = (ctypes.c_ulonglong * 2)() if want_stats else None
+        check(self.lib.kb200_predict_dev(self.handle, c_void_p(x_ptr), int(npred), int(normtype), ptr(na), ptr(nb),
+                                         int(want), float(self.ymin if ymin is None else ymin), float(limit),
+                                         int(bool(limit_ge)), *ptrs, stats, c_void_p(stream)))
+        return (int(stats[0]), int(stats[1])) if want_stats else None
+
+    def launch_count(self):
+        return int(self.lib.kb200_launch_count(self.handle))
+
+
+# ------------------------------------------------------------------------- cache
+_CACHE = OrderedDict()
+_CACHE_MAX = int(os.environ.get("KADAL_B200_CACHE", "8"))
+
+
+def _fingerprint(a):
+    a = np.asarray(a)
+    return (id(a), a.shape, float(a.sum()) if a.size else 0.0)
+
+
+def model_for(KrigInfo):
+    """GpuModel for this KrigInfo (created on first use, re-created when the training data
+    the reference would read has changed, e.g. after SOBO/AK-MCS append a sample)."""
+    X, y = select_xy(KrigInfo)
+    F = KrigInfo["F"]
+    kids, iso = kernel_ids(KrigInfo)
+    kpls = str(KrigInfo["type"]).lower() == "kpls"
+    pls = KrigInfo["plscoeff"] if kpls else None
+    if not kpls and str(KrigInfo["type"]).lower() != "kriging":
+        raise ValueError("Kriging model dictionary 'type' value: '%s' is not recognised." % KrigInfo["type"])
+    key = (_fingerprint(X), _fingerprint(y), _fingerprint(F), tuple(kids), iso,
+           _fingerprint(pls) if pls is not None else None, KrigInfo["nsamp"])
+    m = _CACHE.get(key)
+    if m is not None:
+        _CACHE.move_to_end(key)
+        return m
+    if kpls and KrigInfo["n_princomp"] is not False and int(KrigInfo["n_princomp"]) != np.shape(pls)[1]:
+        raise ValueError("plscoeff has %d components, n_princomp=%s" % (np.shape(pls)[1], KrigInfo["n_princomp"]))
+    m = GpuModel(X, y, F, kids, pls=pls, nsamp=KrigInfo["nsamp"], iso=iso)
+    m._keep = (X, y, F, pls)   # keep the arrays alive so ids stay unique
+    _CACHE[key] = m
+    while len(_CACHE) > _CACHE_MAX:
+        _, old = _CACHE.popitem(last=False)
+        old.close()
+    return m
+
+
+def clear_cache():
+    while _CACHE:
+        _, m = _CACHE.popitem()
+        m.close()
