@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the KADAL Kriging hot path on B200.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # our arm (CUDA, C ABI)
+    python bench.py --impl reference --steps 3 --warmup 1     # reference CPU arm (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): likelihood evals/sec at n=1000, d=10 (configs[1]: CMA-ES population
+of 512 theta candidates per GPU); a "step" is one pass of the batched likelihood over one
+population.  Weak scaling: every rank evaluates its own 512-candidate population (restarts /
+populations are independent) and the NLL vectors are all-gathered with NCCL.
+The same JSON line carries the predicted-points/sec figures of configs[2] (n=200, d=6,
+pred + s over Monte-Carlo points) under "predict".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_PER_GPU = 512
+N_C2, D_C2 = 1000, 10
+
+
+# ------------------------------------------------------------------ workload (synthetic)
+def c2_data():
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (N_C2, D_C2))
+    y = np.sin(X.sum(1))[:, None] + 0.1 * rng.standard_normal((N_C2, 1))
+    rng.uniform(-1, 1, D_C2)            # known-answer candidate (keeps the stream aligned with SURVEY §8d)
+    rng.uniform(-5, 5, (512, D_C2))     # population A (reference search box)
+    popB = rng.uniform(-0.5, 1.5, (512, D_C2))   # population B (informative region)
+    return X, y, popB
+
+
+def population(rank):
+    X, y, popB = c2_data()
+    if rank == 0:
+        return X, y, popB
+    return X, y, np.random.default_rng(1000 + rank).uniform(-0.5, 1.5, (P_PER_GPU, D_C2))
+
+
+def c3_data():
+    rng = np.random.default_rng(1)
+    X = rng.uniform(-1, 1, (200, 6))
+    y = (np.sin(X.sum(1)) + 0.3 * X[:, 0] ** 2)[:, None] + 3.0
+    return X, y, np.full(6, 0.2)
+
+
+# ------------------------------------------------------------------ algorithmic work
+def chol_panel_flops(n, P):
+    """Algorithmic flops of all chol_panel_kernel launches of one likelihood pass: for tile
+    (i,j), i>j: GEMM update 2*r_i*c_j*(128 j) + triangular solve r_i*c_j^2 (true, unpadded
+    row/column counts)."""
+    nt = (n + 127) // 128
+    size = lambda t: min(128, n - 128 * t)
+    fl = 0.0
+    for j in range(nt):
+        for i in range(j + 1, nt):
+            fl += 2.0 * size(i) * size(j) * (128 * j) + size(i) * size(j) ** 2
+    return fl * P
+
+
+def lik_flops_per_eval(n, d, p=1, c_exp=20):
+    """n^3/3 + n^2 (1.5 d + p + 1) + (n^2/2) c_exp."""
+    return n ** 3 / 3 + n ** 2 * (1.5 * d + p + 1) + (n ** 2 / 2) * c_exp
+
+
+def predict_flops_per_point(n, d, var=True, c_exp=20):
+    f = n * (3 * d + c_exp) + 2 * n
+    return f + (n * n + 2 * n if var else 0)
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path, timed on this box's host cores.
+    KADAL is pure Python (numpy/scipy) and /root/reference does not travel to the GPU box, so
+    the timed code is oracle/kriging_oracle.py — the operation-by-operation restatement that
+    tests/test_oracle.py pins bit-for-bit to the live reference (kind = "port")."""
+    if rank != 0:
+        return
+    from oracle import kriging_oracle as ko
+    X, y, pop = c2_data()
+    info = ko.make_kriginfo(X, y)
+    per_step = 2
+    k = 0
+    for _ in range(max(args.warmup, 1)):
+        ko.likelihood(pop[k % 512].copy(), info, "default", False)
+        k += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            ko.likelihood(pop[k % 512].copy(), info, "default", False)
+            k += 1
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step / dt
+    cores = os.cpu_count()
+    sample = "%d of the 512 popB candidates per step, sequential calls as cma/scipy issue them, eigvals check on, BLAS threads = all cores" % per_step
+    line = {
+        "impl": "reference", "metric": "likelihood_evals_per_sec", "value": val, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 batched likelihood sweep: n=1000, d=10, population 512 (bounded sample)",
+                   "n": N_C2, "d": D_C2, "population_per_gpu": P_PER_GPU, "kernel": "gaussian", "nugget": -6},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(budget_s=14.0):
+    from oracle import kriging_oracle as ko
+    X, y, pop = c2_data()
+    info = ko.make_kriginfo(X, y)
+    ko.likelihood(pop[0].copy(), info, "default", False)   # warm BLAS
+    t0, k = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s * 0.6 and k < 16:
+        ko.likelihood(pop[k].copy(), info, "default", False)
+        k += 1
+    asis = k / (time.perf_counter() - t0)
+    t1, k2 = time.perf_counter(), 0
+    while time.perf_counter() - t1 < budget_s * 0.4 and k2 < 16:
+        ko.likelihood(pop[k2].copy(), info, "default", False, check_pd=False)
+        k2 += 1
+    fair = k2 / (time.perf_counter() - t1)
+    return {"value": asis, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "first %d of the 512 popB candidates, sequential oracle.likelihood calls (as cma/scipy call the "
+                      "reference), eigvals check on; with the result-neutral eigvals check off: %.2f evals/s (%d evals)"
+                      % (k, fair, k2)}
+
+
+# ------------------------------------------------------------------ our arm (GPU)
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from kadal_b200 import _capi
+    from kadal_b200.model import GpuModel, fp64_probe
+
+    _capi.require_gpu()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    X, y, pop = population(rank)
+    model = GpuModel(X, y, np.ones((N_C2, 1)), [0], device=local_rank)
+    P, nb = pop.shape
+    x_dev = torch.from_numpy(pop).to(dev)
+    nll_dev = torch.empty(P, dtype=torch.float64, device=dev)
+    info_dev = torch.empty(P, dtype=torch.int32, device=dev)
+    gathered = torch.empty(world * P, dtype=torch.float64, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        model.lik_batch_dev(x_dev.data_ptr(), P, nb, False, -6.0, nll_dev.data_ptr(), info_dev.data_ptr(), stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, nll_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = model.launch_count()
+    model.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    model.profile(False)
+    prof = model.profile_get()
+    launches = model.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    value = world * P * args.steps / (ms * 1e-3)
+    nll_host = nll_dev.cpu().numpy()
+    assert np.all(np.isfinite(nll_host)) and int((info_dev != 0).sum().item()) == 0
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers, H2D + D2H inside)
+    xh = _capi.pinned_empty((P, nb))
+    xh[:] = pop
+    nll_h = _capi.pinned_empty((P,))
+    info_h = _capi.pinned_empty((P,), dtype=np.int32)
+    lib = model.lib
+
+    def e2e_step():
+        _capi.check(lib.kb200_lik_batch(model.handle, _capi.ptr(xh), P, nb, 0, -6.0, _capi.ptr(nll_h), _capi.ptr(info_h)))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * P * args.steps / e2e_s
+    assert np.array_equal(nll_h, nll_host)
+
+    # ---- prediction throughput (configs[2]: n=200, d=6, pred + s), device resident + e2e
+    pred = predict_bench(args, rank, local_rank, world, torch, dist, barrier)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    dmma_tf, dfma_tf = fp64_probe(local_rank)
+    peaks = measured_peaks()
+    pan_ms, pan_cnt = prof["chol_panel"]
+    pan_flops = chol_panel_flops(N_C2, P) * args.steps
+    pan_tf = pan_flops / (pan_ms * 1e-3) / 1e12 if pan_ms > 0 else None
+    kernel_ms = {k: round(v[0], 4) for k, v in prof.items() if v[1]}
+    step_tf = lik_flops_per_eval(N_C2, D_C2) * P * args.steps / (sum(v[0] for v in prof.values()) * 1e-3) / 1e12
+    hbm = peaks["hbm_gbs"] if peaks else 6650.0
+    line = {
+        "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 batched likelihood sweep: n=1000, d=10, CMA-ES population 512 theta candidates per GPU",
+                   "n": N_C2, "d": D_C2, "population_per_gpu": P, "kernel": "gaussian", "nugget": -6,
+                   "candidates": "popB: log10(theta) ~ U(-0.5, 1.5) (informative region, cond up to ~7e8)",
+                   "l2": "working set %.1f GB of factor tiles per step >> 126 MB L2 (inputs larger than L2)" % (P * 36 * 131072 / 1e9),
+                   "parallelism": "dp%d (candidates sharded per GPU, NCCL all-gather of NLL)" % world},
+        "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": world * P * nb * 8,
+                "d2h_bytes_per_step": world * P * 12},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "chol_panel_kernel (fp64 DMMA GEMM + TRSM-by-inverse)",
+                     "achieved": pan_tf, "peak": dmma_tf, "unit": "TFLOP/s", "frac": (pan_tf / dmma_tf) if pan_tf else None,
+                     "traffic": None,
+                     "peak_source": "kb200_fp64_probe: register-resident mma.sync.m8n8k4.f64 loop measured in this run "
+                                    "(MEASURED_PEAKS.json has no FP64 figure; DFMA probe: %.1f TFLOP/s)" % dfma_tf,
+                     "launches": pan_cnt, "avg_launch_ms": pan_ms / pan_cnt if pan_cnt else None,
+                     "share_of_step": pan_ms / sum(v[0] for v in prof.values()),
+                     "whole_step_tflops": step_tf, "whole_step_frac": step_tf / dmma_tf,
+                     "hbm_view": {"achieved": P * args.steps * 36 * 131072 * 3 / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "note": "factor tiles written once by assembly, read+written once by the factorisation "
+                                          "(compulsory traffic); not the binding roof (AI >> 6 flop/B)"}},
+        "kernel_ms": kernel_ms,
+        "predict": pred,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def predict_bench(args, rank, local_rank, world, torch, dist, barrier):
+    from kadal_b200 import _capi
+    from kadal_b200.model import GpuModel
+    dev = torch.device("cuda", local_rank)
+    X, y, th = c3_data()
+    n, d = X.shape
+    m = GpuModel(X, y, np.ones((n, 1)), [0], device=local_rank)
+    st = m.fit_state(th, False, -6.0, want_U=False, want_Psi=False)
+    assert st["info"] == 0
+    npts = int(args.predict_points)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2 + rank)
+    xs = (torch.randn(npts, d, generator=g, device=dev, dtype=torch.float64) * 0.5).clamp_(-1, 1)
+    o_pred = torch.empty(npts, dtype=torch.float64, device=dev)
+    o_s = torch.empty(npts, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    lb, ub = -np.ones(d), np.ones(d)
+    want = _capi.OUT_PRED | _capi.OUT_S
+
+    def step():
+        m.predict_dev(xs.data_ptr(), npts, want, [o_pred.data_ptr(), 0, o_s.data_ptr(), 0, 0, 0, 0],
+                      normtype=_capi.NORM_DEFAULT, norm_a=lb, norm_b=ub, stream=stream)
+
+    steps = max(2, min(args.steps, 5))
+    for _ in range(3):
+        step()
+    barrier()
+    m.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    m.profile(False)
+    prof = m.profile_get()
+    # e2e: pinned host points in, pinned host results out
+    xh = _capi.pinned_empty((npts, d))
+    xh[:] = xs.cpu().numpy()
+    out = {"pred": _capi.pinned_empty((npts,)), "s": _capi.pinned_empty((npts,))}
+    m.predict(xh, want, _capi.NORM_DEFAULT, lb, ub, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        m.predict(xh, want, _capi.NORM_DEFAULT, lb, ub, out=out)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / 2
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0].item()), float(t[1].item())
+    assert np.allclose(out["pred"], o_pred.cpu().numpy(), rtol=0, atol=0)
+    pts = world * npts * steps / (ms * 1e-3)
+    fl = predict_flops_per_point(n, d, True)
+    return {"metric": "predicted_points_per_sec", "value": pts, "unit": "pts/s", "e2e_value": world * npts / e2e_s,
+            "config": {"workload": "C3 AK-MCS: n=200, d=6, pred + s over %d Monte-Carlo points per GPU" % npts},
+            "ms_per_step": ms / steps, "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+            "fp64_tflops_algorithmic": pts * fl / 1e12,
+            "hbm_gbs_algorithmic": pts * (8 * d + 16) / 1e9,
+            "h2d_bytes_per_step": world * npts * d * 8, "d2h_bytes_per_step": world * npts * 16}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--predict-points", type=float, default=4e6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

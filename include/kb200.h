@@ -113,6 +113,25 @@ unsigned long long kb200_launch_count(const kb200_model* m);
 int kb200_debug_psi(kb200_model* m, const double* x, int nbhyp, int trainvar,
                     double nugget_log10, int add_eps, double* Psi);
 
+
+/* Per-kernel-class device timing with CUDA events on the launching stream (bench.py's
+ * roofline): enable, run, then read accumulated milliseconds and launch counts. */
+#define KB200_PROF_ASSEMBLE 0   /* corr_tile_kernel, Psi assembly            */
+#define KB200_PROF_DIAG 1       /* chol_diag_kernel                          */
+#define KB200_PROF_PANEL 2      /* chol_panel_kernel (factorisation)         */
+#define KB200_PROF_FINALIZE 3   /* lik_finalize_kernel                       */
+#define KB200_PROF_PSI 4        /* corr_tile_kernel, psi(X, x*) + mean       */
+#define KB200_PROF_PREDSOLVE 5  /* chol_panel_kernel (prediction variance)   */
+#define KB200_PROF_EPILOGUE 6   /* predict_epilogue_kernel                   */
+#define KB200_PROF_OTHER 7
+#define KB200_PROF_NCLASS 8
+int kb200_profile_enable(kb200_model* m, int on);
+int kb200_profile_get(kb200_model* m, double* ms, unsigned long long* counts, int reset);
+
+/* Empirical FP64 roof of the device: register-resident DMMA (mode 0) or DFMA (mode 1)
+ * loops, best of 5, in TFLOP/s. */
+int kb200_fp64_probe(int device, int mode, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

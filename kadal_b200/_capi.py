@@ -19,6 +19,7 @@ KERNEL_IDS = {"gaussian": 0, "iso_gaussian": 0, "exponential": 1, "matern32": 2,
 FLAG_ISO, FLAG_NAIVE = 1, 2
 OUT_PRED, OUT_SSQR, OUT_S, OUT_EI, OUT_POI, OUT_POF, OUT_UFUN = 1, 2, 4, 8, 16, 32, 64
 NORM_NONE, NORM_DEFAULT, NORM_STD = 0, 1, 2
+PROF_CLASSES = ["assemble", "chol_diag", "chol_panel", "finalize", "psi", "pred_solve", "epilogue", "other"]
 
 # every symbol include/kb200.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -49,6 +50,9 @@ SIGNATURES = {
                                          c_u64_p, c_void_p]),
     "kb200_model_dims": (ctypes.c_int, [c_void_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "kb200_launch_count": (ctypes.c_ulonglong, [c_void_p]),
+    "kb200_profile_enable": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "kb200_profile_get": (ctypes.c_int, [c_void_p, c_double_p, c_u64_p, ctypes.c_int]),
+    "kb200_fp64_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_double_p]),
     "kb200_debug_psi": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        ctypes.c_int, c_void_p]),
 }

@@ -80,6 +80,30 @@ struct kb200_model {
   DevBuf norm_a, norm_b, stats;
   unsigned long long launches = 0;
   size_t ws_cap_bytes = 0;
+  // optional per-kernel-class event timing (kb200_profile_*)
+  bool prof_on = false;
+  struct ProfRec { cudaEvent_t a, b; int cls; };
+  std::vector<ProfRec> prof;
+  double prof_ms[KB200_PROF_NCLASS] = {0};
+  unsigned long long prof_cnt[KB200_PROF_NCLASS] = {0};
+};
+
+// RAII: time one launch on stream `st` when profiling is on, and count it
+struct Timed {
+  kb200_model* m;
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  Timed(kb200_model* m_, int cls, cudaStream_t st_) : m(m_), st(st_) {
+    m->launches++;
+    if (!m->prof_on) return;
+    cudaEvent_t a;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { b = nullptr; return; }
+    cudaEventRecord(a, st);
+    m->prof.push_back({a, b, cls});
+  }
+  ~Timed() {
+    if (b) cudaEventRecord(b, st);
+  }
 };
 
 static CorrSpec make_spec(const kb200_model* m) {
@@ -263,8 +287,10 @@ static int decode(kb200_model* m, const double* d_x, long P, int nbhyp, int trai
   a.wgkf_given = nullptr;
   a.cand = d_cand;
   a.cand_stride = m->cstride;
-  CK(launch_decode(a, st));
-  m->launches++;
+  {
+    Timed t(m, KB200_PROF_OTHER, st);
+    CK(launch_decode(a, st));
+  }
   return 0;
 }
 
@@ -288,8 +314,10 @@ static int assemble(kb200_model* m, const double* d_cand, int Pb, double* tiles,
   c.n = m->n; c.nt = m->nt; c.X = m->X.d();
   c.cand = d_cand; c.cand_stride = m->cstride;
   c.out = tiles; c.tiles_per_mat = m->tiles_per_mat; c.add_eps = add_eps;
-  CK(launch_corr(c, (int)m->tiles_per_mat, Pb, st));
-  m->launches++;
+  {
+    Timed t(m, KB200_PROF_ASSEMBLE, st);
+    CK(launch_corr(c, (int)m->tiles_per_mat, Pb, st));
+  }
   return 0;
 }
 
@@ -297,11 +325,13 @@ static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z
                      int* info, cudaStream_t st) {
   CholArgs a = chol_args(m, tiles, W, Z, logdet, info);
   for (int j = 0; j < m->nt; ++j) {
-    CK(launch_chol_diag(a, j, Pb, st));
-    m->launches++;
+    {
+      Timed t(m, KB200_PROF_DIAG, st);
+      CK(launch_chol_diag(a, j, Pb, st));
+    }
     if (j + 1 < m->nt) {
+      Timed t(m, KB200_PROF_PANEL, st);
       CK(launch_chol_panel(a, j, m->nt - 1 - j, Pb, st));
-      m->launches++;
     }
   }
   return 0;
@@ -349,8 +379,10 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
     f.nq = m->nq; f.npad = m->npad; f.n = m->n;
     f.trainvar = trainvar; f.nsamp = m->nsamp;
     f.nll = d_nll + p0;
-    CK(launch_finalize(f, pb, st));
-    m->launches++;
+    {
+      Timed t(m, KB200_PROF_FINALIZE, st);
+      CK(launch_finalize(f, pb, st));
+    }
   }
   return 0;
 }
@@ -608,12 +640,16 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
       cc.xpts = d_x + (size_t)t0 * TB * m->d;
       cc.npts = std::min<long>(npts - t0 * TB, tn * TB);
       cc.fdot = sl.fdot.d() + t0 * TB;
-      CK(launch_corr(cc, (int)tn, 1, st));
-      m->launches++;
+      {
+        Timed t(m, KB200_PROF_PSI, st);
+        CK(launch_corr(cc, (int)tn, 1, st));
+      }
     }
     e.npts = npts; e.fdot = sl.fdot.d(); e.pred = outs[0];
-    CK(launch_epilogue(e, st));
-    m->launches++;
+    {
+      Timed t(m, KB200_PROF_EPILOGUE, st);
+      CK(launch_epilogue(e, st));
+    }
     return 0;
   }
   const long ct = chunk_tiles_for(m);
@@ -631,11 +667,13 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     CorrArgs cc = c;
     cc.xpts = d_x + (size_t)p0 * m->d; cc.npts = np; cc.out = sl.chunk.d();
     cc.wvec = m->pw.d(); cc.fdot = sl.fdot.d() + p0; cc.udot = sl.udot.d() + p0;
-    CK(launch_corr(cc, tiles, 1, st));
-    m->launches++;
+    {
+      Timed t(m, KB200_PROF_PSI, st);
+      CK(launch_corr(cc, tiles, 1, st));
+    }
     for (int j = 0; j < m->nt; ++j) {
+      Timed t(m, KB200_PROF_PREDSOLVE, st);
       CK(launch_chol_panel(pa, j, tiles, 1, st));
-      m->launches++;
     }
     EpiArgs ee = e;
     ee.npts = np; ee.fdot = sl.fdot.d() + p0; ee.udot = sl.udot.d() + p0; ee.ssq = sl.ssq.d();
@@ -646,8 +684,10 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     ee.poi = outs[4] ? outs[4] + p0 : nullptr;
     ee.pof = outs[5] ? outs[5] + p0 : nullptr;
     ee.ufun = outs[6] ? outs[6] + p0 : nullptr;
-    CK(launch_epilogue(ee, st));
-    m->launches++;
+    {
+      Timed t(m, KB200_PROF_EPILOGUE, st);
+      CK(launch_epilogue(ee, st));
+    }
   }
   return 0;
 }
@@ -733,6 +773,74 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
   CK(cudaStreamSynchronize(m->slot[0].stream));
   CK(cudaStreamSynchronize(m->slot[1].stream));
   if (stats) CK(cudaMemcpy(stats, m->stats.p, 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int kb200_profile_enable(kb200_model* m, int on) {
+  if (!m) return fail_arg("null model");
+  m->prof_on = on != 0;
+  return 0;
+}
+
+static int prof_collect(kb200_model* m) {
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  for (auto& r : m->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      m->prof_ms[r.cls] += ms;
+      m->prof_cnt[r.cls]++;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  m->prof.clear();
+  return 0;
+}
+
+int kb200_profile_get(kb200_model* m, double* ms, unsigned long long* counts, int reset) {
+  if (!m) return fail_arg("null model");
+  int rc = prof_collect(m);
+  if (rc) return rc;
+  for (int i = 0; i < KB200_PROF_NCLASS; ++i) {
+    if (ms) ms[i] = m->prof_ms[i];
+    if (counts) counts[i] = m->prof_cnt[i];
+    if (reset) { m->prof_ms[i] = 0; m->prof_cnt[i] = 0; }
+  }
+  return 0;
+}
+
+int kb200_fp64_probe(int device, int mode, double* tflops) {
+  if (!tflops) return fail_arg("null argument");
+  CK(cudaSetDevice(device));
+  double* sink = nullptr;
+  CK(cudaMalloc(&sink, 8));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int blocks = 148 * 4, iters = 4096;
+  CK(launch_fp64_probe(blocks, 64, mode, sink, 0));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(a, 0));
+    CK(launch_fp64_probe(blocks, iters, mode, sink, 0));
+    CK(cudaEventRecord(b, 0));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    // per thread and iteration: DMMA 16 x (8*8*4*2)/32 flops, DFMA 32 x 2 flops
+    const double per_thread = mode == 0 ? 16.0 * 512.0 / 32.0 : 64.0;
+    const double fl = per_thread * iters * 512.0 * blocks;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  *tflops = best;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(sink);
   return 0;
 }
 

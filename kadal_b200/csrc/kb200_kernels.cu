@@ -1043,4 +1043,37 @@ cudaError_t launch_epilogue(const EpiArgs& a, cudaStream_t st) {
   return cudaSuccess;
 }
 
+// ===================================================================== FP64 probes
+// Register-resident DMMA / DFMA loops: the empirical FP64 roof of this chip (there is no
+// FP64 figure in MEASURED_PEAKS.json).  16 independent accumulator tiles per warp, like the
+// GEMM core, so the number is the ceiling of that instruction mix.
+__global__ void __launch_bounds__(CH_THREADS, 1) fp64_probe_kernel(int iters, int mode, double* sink) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        acc[i][0] = fma(a, b, acc[i][0]);
+        acc[i][1] = fma(b, a, acc[i][1]);
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t launch_fp64_probe(int blocks, int iters, int mode, double* sink, cudaStream_t st) {
+  fp64_probe_kernel<<<blocks, CH_THREADS, 0, st>>>(iters, mode, sink);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
 }  // namespace kb200

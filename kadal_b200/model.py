@@ -173,6 +173,15 @@ class GpuModel:
                                          int(bool(limit_ge)), *ptrs, stats, c_void_p(stream)))
         return (int(stats[0]), int(stats[1])) if want_stats else None
 
+    def profile(self, on):
+        check(self.lib.kb200_profile_enable(self.handle, int(bool(on))))
+
+    def profile_get(self, reset=True):
+        ms = (ctypes.c_double * 8)()
+        cnt = (ctypes.c_ulonglong * 8)()
+        check(self.lib.kb200_profile_get(self.handle, ms, cnt, int(reset)))
+        return {nm: (ms[i], int(cnt[i])) for i, nm in enumerate(_capi.PROF_CLASSES)}
+
     def launch_count(self):
         return int(self.lib.kb200_launch_count(self.handle))
 
@@ -218,3 +227,14 @@ def clear_cache():
     while _CACHE:
         _, m = _CACHE.popitem()
         m.close()
+
+
+def fp64_probe(device=0):
+    """(DMMA TFLOP/s, DFMA TFLOP/s) measured with register-resident loops."""
+    lib = _capi.require_gpu()
+    out = []
+    for mode in (0, 1):
+        v = ctypes.c_double()
+        check(lib.kb200_fp64_probe(device, mode, ctypes.byref(v)))
+        out.append(v.value)
+    return tuple(out)

@@ -1,0 +1,276 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle, the golden vectors of the live
+reference, and size-independent properties at BASELINE.json's full sizes.
+
+Tolerances are the north star's: ln-likelihood 1e-9 relative, mean 1e-8, variance 1e-7
+(denominators floored as in SURVEY.md Appendix E: max(|ref|, 1) for NLL / mean,
+max(|ref|, 1e-6*sigma^2) for SSqr), arg-min candidate index exact.  For candidates with
+cond(Psi) > 1e8 the reference's own reordering noise exceeds 1e-9 (Appendix E: 6-8e-10 at
+cond 2e8); there the bound is scaled with the condition number and says so.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+import cases
+from oracle import kriging_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+TOL_NLL, TOL_MEAN, TOL_VAR = 1e-9, 1e-8, 1e-7
+
+
+@pytest.fixture(scope="module")
+def kb():
+    import kadal_b200
+    from kadal_b200 import _capi
+    _capi.require_gpu()   # loud failure if the CUDA extension / device is missing
+    return kadal_b200
+
+
+def nll_tol(cond):
+    return max(TOL_NLL, 10 * cond * 2.0 ** -53)
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", cases.APPENDIX_C_CASES)
+def test_appendix_c_against_reference_golden(kb, golden_c, name):
+    g = golden_c
+    info, x, tv = cases.appendix_c_info(g, name)
+    v = kb.likelihood(x.copy(), copy.deepcopy(info), "default", tv)
+    assert relerr(v, g[name + "_nll"]) < TOL_NLL
+    out = kb.likelihood(x.copy(), info, "all", tv)
+    assert out is info
+    s2 = float(g[name + "_s2"][0])
+    assert relerr(info["NegLnLike"], g[name + "_nll"]) < TOL_NLL
+    assert relerr(info["BE"], g[name + "_BE"]) < TOL_MEAN
+    assert relerr(np.asarray(info["SigmaSqr"]).ravel(), g[name + "_s2"], 1e-300) < TOL_MEAN
+    assert relerr(info["U"], g[name + "_U"]) < TOL_MEAN
+    assert relerr(info["Psi"], g[name + "_Psi"], 1e-300) < 1e-13
+    assert info["BE"].shape == (1, 1)
+    assert np.shape(info["SigmaSqr"]) == (() if tv else (1, 1))
+    p = kb.prediction(g["xp"], info, cases.PT)
+    assert relerr(p[0].ravel(), g[name + "_pred"]) < TOL_MEAN
+    assert relerr(p[1].ravel(), g[name + "_SSqr"], 1e-6 * s2) < TOL_VAR
+    assert relerr(p[2].ravel(), g[name + "_s"], 1e-3 * np.sqrt(s2)) < TOL_VAR
+    assert relerr(p[4].ravel(), g[name + "_PoI"], 1e-12) < 1e-6
+    ei_ref = g[name + "_EI"]
+    big = np.abs(ei_ref) > 1e-200
+    assert relerr(p[3].ravel()[big], ei_ref[big], 1e-300) < 1e-4
+    for a in p:
+        assert a.shape == (3, 1)
+
+
+def test_c3_population_and_bulk_predict_against_golden(kb, golden_c3):
+    g = golden_c3
+    info, xp = cases.c3_info(g)
+    nll, inf = kb.likelihood_batch(g["pop"], info, False)
+    assert np.all(inf == 0)
+    assert relerr(nll, g["pop_nll"]) < nll_tol(3e8)
+    assert relerr(nll[:32], g["pop_nll"][:32]) < TOL_NLL          # theta in [-5,5] / [-1,1]: cond <= 1e8
+    assert int(np.argmin(nll)) == int(np.argmin(g["pop_nll"]))
+    kb.likelihood(g["fit_x"].copy(), info, "all", False)
+    s2 = float(g["fit_s2"][0])
+    p = kb.prediction(xp, info, cases.PT + ["PoF"])
+    assert relerr(p[0].ravel(), g["pred"]) < TOL_MEAN
+    assert relerr(p[1].ravel(), g["SSqr"], 1e-6 * s2) < TOL_VAR
+    assert relerr(p[2].ravel(), g["s"], 1e-3 * np.sqrt(s2)) < TOL_VAR
+    assert relerr(p[4].ravel(), g["PoI"], 1e-9) < 1e-5
+    assert relerr(p[5].ravel(), g["PoF"], 1e-9) < 1e-5
+    # same model, predictor imported from the *reference's* factor (KrigInfo['U'] route)
+    ref = copy.deepcopy(cases.c3_info(g)[0])
+    ko.likelihood(g["fit_x"].copy(), ref, "all", False, check_pd=False)
+    q = kb.prediction(xp, ref, ["pred", "SSqr"])
+    assert relerr(q[0].ravel(), g["pred"]) < TOL_MEAN
+    assert relerr(q[1].ravel(), g["SSqr"], 1e-6 * s2) < TOL_VAR
+
+
+def test_std_normalisation_against_golden(kb, golden_std):
+    g = golden_std
+    info = cases.std_info(g)
+    kb.likelihood(g["x"].copy(), info, "all", False)
+    s2 = float(g["s2"][0])
+    assert relerr(info["NegLnLike"], g["nll"]) < TOL_NLL
+    p = kb.prediction(g["xp"], info, ["pred", "SSqr", "s"])
+    assert relerr(p[0].ravel(), g["pred"]) < TOL_MEAN
+    assert relerr(p[1].ravel(), g["SSqr"], 1e-6 * s2) < TOL_VAR
+
+
+# ------------------------------------------------------------------ BASELINE config 2
+@pytest.fixture(scope="module")
+def c2():
+    w = ko.workload("C2")
+    return w, ko.make_kriginfo(w["X"], w["y"])
+
+
+def test_c2_known_answer_and_anchors(kb, c2, golden_c2):
+    w, info = c2
+    v = kb.likelihood(w["kat_x"], copy.deepcopy(info), "default", False)
+    assert abs(v - (-345.9939996418981)) < TOL_NLL * 346
+    nA, infA = kb.likelihood_batch(w["popA"], info, False)
+    nB, infB = kb.likelihood_batch(w["popB"], info, False)
+    assert np.all(infA == 0) and np.all(infB == 0)
+    assert relerr(nA[golden_c2["idxA"]], golden_c2["nllA"]) < TOL_NLL
+    # popB reaches cond ~ 7e8: reference reordering noise ~ cond * ulp
+    assert relerr(nB[golden_c2["idxB"]], golden_c2["nllB"]) < nll_tol(1e9)
+
+
+def test_c2_full_population_properties(kb, c2):
+    w, info = c2
+    pop = w["popB"]
+    nll, inf = kb.likelihood_batch(pop, info, False)
+    assert nll.shape == (512,) and np.all(np.isfinite(nll))
+    # independence of the batch composition: any sub-batch / permutation is bit-identical
+    perm = np.random.default_rng(3).permutation(512)
+    nll_p, _ = kb.likelihood_batch(pop[perm], info, False)
+    assert np.array_equal(nll_p, nll[perm])
+    one, _ = kb.likelihood_batch(pop[17:18], info, False)
+    assert one[0] == nll[17]
+    # arg-min must match the oracle on the contenders (best 12 by GPU value + 12 random)
+    rng = np.random.default_rng(5)
+    idx = np.unique(np.r_[np.argsort(nll)[:12], rng.choice(512, 12, replace=False)])
+    ref = ko.likelihood_population(pop[idx], copy.deepcopy(info), False, check_pd=False)
+    assert idx[int(np.argmin(ref))] == int(np.argmin(nll))
+    assert relerr(nll[idx], ref) < nll_tol(1e9)
+    order_ref, order_gpu = np.argsort(ref), np.argsort(nll[idx])
+    assert np.array_equal(order_ref[:6], order_gpu[:6])
+
+
+def test_c2_factor_round_trip(kb, c2):
+    w, info = c2
+    info = copy.deepcopy(info)
+    x = w["popB"][3]
+    kb.likelihood(x.copy(), info, "all", False)
+    U, Psi = info["U"], info["Psi"]
+    assert np.allclose(np.tril(U, -1), 0.0)
+    A = Psi + np.eye(1000) * 1e-6
+    assert np.linalg.norm(U.T @ U - A) / np.linalg.norm(A) < 1e-14
+    assert np.array_equal(Psi, Psi.T) and np.all(np.diag(Psi) == 1.0)
+    # Kriging interpolates the samples up to the nugget; variance there is ~ nugget-sized
+    p, ss = kb.prediction(info["X"][:300], info, ["pred", "SSqr"])
+    s2 = float(info["SigmaSqr"][0, 0])
+    assert np.max(np.abs(p - info["y"][:300])) < 1e-3 * np.ptp(info["y"])
+    assert np.max(np.abs(ss)) < 1e-4 * s2
+
+
+# ------------------------------------------------------------------ shapes and edges
+@pytest.mark.parametrize("n", [1, 2, 5, 127, 128, 129, 257, 300])
+def test_tile_boundaries_likelihood_and_predict(kb, n):
+    rng = np.random.default_rng(n)
+    d = 3
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(X.sum(1, keepdims=True)) + 3.0
+    info = ko.make_kriginfo(X, y)
+    x = np.array([0.0, 0.2, -0.1])
+    A, B = copy.deepcopy(info), copy.deepcopy(info)
+    ko.likelihood(x.copy(), A, "all", False, check_pd=False)
+    kb.likelihood(x.copy(), B, "all", False)
+    if n > 1:   # n = 1: sigma^2 = 0 exactly in exact arithmetic, ln(0) on both sides
+        assert relerr(B["NegLnLike"], A["NegLnLike"]) < TOL_NLL
+    assert relerr(B["U"], A["U"]) < TOL_MEAN
+    for npred in (1, 127, 129):
+        xp = rng.uniform(-1, 1, (npred, d))
+        pa = ko.prediction(xp, A, ["pred", "SSqr"])
+        pb = kb.prediction(xp, B, ["pred", "SSqr"])
+        s2 = float(np.asarray(A["SigmaSqr"]).ravel()[0])
+        assert relerr(pb[0], pa[0]) < TOL_MEAN
+        if n > 1:
+            assert relerr(pb[1], pa[1], max(1e-6 * s2, 1e-300)) < TOL_VAR
+
+
+def test_predict_crosses_chunk_boundary(kb, golden_c3):
+    """npred larger than one variance chunk (296 tiles x 128 points at n=200) and not a
+    multiple of the tile size; mean-only and mean+variance paths must agree on the mean."""
+    g = golden_c3
+    info, _ = cases.c3_info(g)
+    kb.likelihood(g["fit_x"].copy(), info, "all", False)
+    npred = 2 * 296 * 128 + 77
+    xp = (ko.mc_points(npred, 6, seed=9) / 2 + 0.5) * (g["ub"] - g["lb"]) + g["lb"]
+    f_only = kb.prediction(xp, info, ["pred"])
+    f, s = kb.prediction(xp, info, ["pred", "s"])
+    assert f_only.shape == (npred, 1) and np.array_equal(f_only, f)
+    sel = np.r_[0:300, 296 * 128 - 150:296 * 128 + 150, npred - 300:npred]
+    ra = ko.prediction(xp[sel], info, ["pred", "s"])
+    s2 = float(info["SigmaSqr"][0, 0])
+    assert relerr(f[sel], ra[0]) < TOL_MEAN
+    assert relerr(s[sel], ra[1], 1e-3 * np.sqrt(s2)) < TOL_VAR
+
+
+def test_return_types_and_errors(kb, golden_c):
+    info, x, tv = cases.appendix_c_info(golden_c, "gaussian")
+    kb.likelihood(x.copy(), info, "all", tv)
+    xp = golden_c["xp"]
+    assert isinstance(kb.prediction(xp[0], info, "pred"), float)          # prediction.py:317-321
+    assert kb.prediction(xp, info, "SSqr").shape == (3, 1)
+    assert kb.prediction(xp, info, "ebe").shape == (1, 3)                 # prediction.py:270
+    assert isinstance(kb.prediction(xp, info, ["pred", "s"]), list)
+    assert relerr(kb.prediction(xp, info, "FPC"), np.full((3, 1), info["BE"][0, 0])) < 1e-15
+    with pytest.raises(NotImplementedError):
+        kb.prediction(xp, info, "bogus")
+    with pytest.raises(TypeError):
+        kb.likelihood(x.copy(), info, "bogus", tv)
+    bad = copy.deepcopy(info)
+    bad["kernel"] = ["cubic"]
+    with pytest.raises(ValueError):
+        kb.likelihood(x.copy(), bad, "default", tv)
+    with pytest.raises(NotImplementedError):
+        kb.prediction(xp, info, "pred", num=0)
+    with pytest.raises(ValueError):
+        kb.likelihood(np.zeros(9), info, "default", tv)                   # nuggetset: no such layout
+
+
+def test_not_positive_definite_is_reported_per_candidate(kb):
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (40, 2))
+    X[7] = X[3]                               # duplicated sample, vanishing nugget -> singular
+    info = ko.make_kriginfo(X, np.ones((40, 1)) + X[:, :1], nugget=-300)
+    pop = np.array([[0.0, 0.0], [-2.0, -2.0], [0.5, 0.5]])
+    nll, inf = kb.likelihood_batch(pop, info, False)
+    assert np.all(inf != 0) and np.all(np.isinf(nll))
+    with pytest.raises(np.linalg.LinAlgError):
+        kb.likelihood(pop[0], info, "default", False)
+    with pytest.raises(np.linalg.LinAlgError):
+        ko.likelihood(pop[0], copy.deepcopy(info), "default", False, check_pd=False)
+    # a healthy candidate in the same batch is unaffected by its neighbours
+    Xg = np.delete(X, 7, axis=0)
+    good = ko.make_kriginfo(Xg, np.ones((39, 1)) + Xg[:, :1])
+    n1, i1 = kb.likelihood_batch(pop, good, False)
+    assert np.all(i1 == 0) and np.all(np.isfinite(n1))
+
+
+def test_debug_naive_kernels_agree_with_dmma(kb):
+    from kadal_b200.model import GpuModel
+    w = ko.workload("C2", scale=0.3)
+    X, y = w["X"], w["y"]
+    a = GpuModel(X, y, np.ones((len(X), 1)), [0])
+    b = GpuModel(X, y, np.ones((len(X), 1)), [0], naive=True)
+    pop = w["popB"][:8]
+    na, _ = a.lik_batch(pop, False, -6.0)
+    nb, _ = b.lik_batch(pop, False, -6.0)
+    assert relerr(na, nb) < 1e-12
+    a.close()
+    b.close()
+
+
+def test_kpls_and_composite_population(kb):
+    rng = np.random.default_rng(8)
+    n, d, h = 180, 12, 3
+    X = rng.uniform(-1, 1, (n, d))
+    y = (X[:, :4].sum(1) ** 2)[:, None] + 3
+    pls = rng.standard_normal((d, h)) / 3
+    info = ko.make_kriginfo(X, y, pls=pls, n_princomp=h)
+    pop = rng.uniform(-1, 1, (12, h))
+    ref = ko.likelihood_population(pop, copy.deepcopy(info), False, check_pd=False)
+    nll, inf = kb.likelihood_batch(pop, info, False)
+    assert relerr(nll, ref) < TOL_NLL and int(np.argmin(nll)) == int(np.argmin(ref))
+    info2 = ko.make_kriginfo(X, y, kernel=("gaussian", "matern52"))
+    info2["nugget"] = [-8, -2]
+    pop2 = np.hstack([rng.uniform(-0.5, 1, (10, d)), rng.uniform(-6, -3, (10, 1)), rng.uniform(0.1, 1, (10, 2))])
+    ref2 = ko.likelihood_population(pop2, copy.deepcopy(info2), False, check_pd=False)
+    nll2, _ = kb.likelihood_batch(pop2, info2, False)
+    assert relerr(nll2, ref2) < TOL_NLL
+    popv = np.hstack([pop2[:, :d], rng.uniform(-1, 1, (10, 1)), pop2[:, d:]])
+    ref3 = ko.likelihood_population(popv, copy.deepcopy(info2), True, check_pd=False)
+    nll3, _ = kb.likelihood_batch(popv, info2, True)
+    assert relerr(nll3, ref3) < TOL_NLL
