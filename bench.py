@@ -69,6 +69,24 @@ def chol_panel_flops(n, P):
     return fl * P
 
 
+def chol_diag_flops(n, P, nq=2):
+    """Algorithmic flops of the diagonal-tile kernel: SYRK update c_j^2*(128 j), POTF2
+    c_j^3/3, fused forward substitution of [y F] 2*nq*c_j*(128 j) + nq*c_j^2.  The block
+    inverse the kernel also forms is an implementation choice, not algorithmic work."""
+    nt = (n + 127) // 128
+    size = lambda t: min(128, n - 128 * t)
+    fl = 0.0
+    for j in range(nt):
+        c = size(j)
+        fl += c * c * (128.0 * j) + c ** 3 / 3.0 + 2.0 * nq * c * (128.0 * j) + nq * c * c
+    return fl * P
+
+
+def assemble_flops(n, d, P, c_exp=20):
+    """Lower triangle incl. diagonal: per entry d*(sub, mul, div, add) + exp."""
+    return P * (n * (n + 1) / 2.0) * (4.0 * d + c_exp)
+
+
 def lik_flops_per_eval(n, d, p=1, c_exp=20):
     """n^3/3 + n^2 (1.5 d + p + 1) + (n^2/2) c_exp."""
     return n ** 3 / 3 + n ** 2 * (1.5 * d + p + 1) + (n ** 2 / 2) * c_exp
@@ -210,7 +228,12 @@ def run_ours(args, rank, local_rank, world):
     nll_dev = torch.empty(P, dtype=torch.float64, device=dev)
     info_dev = torch.empty(P, dtype=torch.int32, device=dev)
     gathered = torch.empty(world * P, dtype=torch.float64, device=dev) if world > 1 else None
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: the library launches on the handle it is given, and
+    # torch.cuda.Event only sees work of torch's *current* stream -> make them the same one
+    tstream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         model.lik_batch_dev(x_dev.data_ptr(), P, nb, False, -6.0, nll_dev.data_ptr(), info_dev.data_ptr(), stream)
@@ -288,12 +311,29 @@ def run_ours(args, rank, local_rank, world):
         return
     dmma_tf, dfma_tf = fp64_probe(local_rank)
     peaks = measured_peaks()
-    pan_ms, pan_cnt = prof["chol_panel"]
-    pan_flops = chol_panel_flops(N_C2, P) * args.steps
-    pan_tf = pan_flops / (pan_ms * 1e-3) / 1e12 if pan_ms > 0 else None
     kernel_ms = {k: round(v[0], 4) for k, v in prof.items() if v[1]}
-    step_tf = lik_flops_per_eval(N_C2, D_C2) * P * args.steps / (sum(v[0] for v in prof.values()) * 1e-3) / 1e12
+    tot_ms = sum(v[0] for v in prof.values())
+    step_tf = lik_flops_per_eval(N_C2, D_C2) * P * args.steps / (tot_ms * 1e-3) / 1e12
     hbm = peaks["hbm_gbs"] if peaks else 6650.0
+    # algorithmic flops per launch class -> achieved TFLOP/s of each kernel
+    cls_flops = {"assemble": assemble_flops(N_C2, D_C2, P), "chol_diag": chol_diag_flops(N_C2, P),
+                 "chol_panel": chol_panel_flops(N_C2, P)}
+    cls_name = {"assemble": "corr_tile_kernel (Psi assembly, fp64 FMA pipe + exp)",
+                "chol_diag": "chol_diag_kernel (fp64 DMMA SYRK + in-smem POTF2/inverse + fused forward substitution)",
+                "chol_panel": "chol_panel_kernel (fp64 DMMA GEMM + TRSM-by-inverse)"}
+    per_kernel = {}
+    for k, fl in cls_flops.items():
+        ms_k, cnt_k = prof[k]
+        if cnt_k:
+            tf = fl * args.steps / (ms_k * 1e-3) / 1e12
+            per_kernel[k] = {"tflops": tf, "frac_of_dmma_peak": tf / dmma_tf, "share_of_step": ms_k / tot_ms,
+                             "launches": cnt_k, "avg_launch_ms": ms_k / cnt_k}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["share_of_step"])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
     line = {
         "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -307,13 +347,14 @@ def run_ours(args, rank, local_rank, world):
                 "d2h_bytes_per_step": world * P * 12},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "chol_panel_kernel (fp64 DMMA GEMM + TRSM-by-inverse)",
-                     "achieved": pan_tf, "peak": dmma_tf, "unit": "TFLOP/s", "frac": (pan_tf / dmma_tf) if pan_tf else None,
-                     "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": cls_name[dom],
+                     "achieved": per_kernel[dom]["tflops"], "peak": dmma_tf, "unit": "TFLOP/s",
+                     "frac": per_kernel[dom]["frac_of_dmma_peak"], "traffic": traffic,
                      "peak_source": "kb200_fp64_probe: register-resident mma.sync.m8n8k4.f64 loop measured in this run "
                                     "(MEASURED_PEAKS.json has no FP64 figure; DFMA probe: %.1f TFLOP/s)" % dfma_tf,
-                     "launches": pan_cnt, "avg_launch_ms": pan_ms / pan_cnt if pan_cnt else None,
-                     "share_of_step": pan_ms / sum(v[0] for v in prof.values()),
+                     "launches": per_kernel[dom]["launches"], "avg_launch_ms": per_kernel[dom]["avg_launch_ms"],
+                     "share_of_step": per_kernel[dom]["share_of_step"],
+                     "per_kernel": per_kernel,
                      "whole_step_tflops": step_tf, "whole_step_frac": step_tf / dmma_tf,
                      "hbm_view": {"achieved": P * args.steps * 36 * 131072 * 3 / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                   "note": "factor tiles written once by assembly, read+written once by the factorisation "
@@ -343,7 +384,8 @@ def predict_bench(args, rank, local_rank, world, torch, dist, barrier):
     xs = (torch.randn(npts, d, generator=g, device=dev, dtype=torch.float64) * 0.5).clamp_(-1, 1)
     o_pred = torch.empty(npts, dtype=torch.float64, device=dev)
     o_s = torch.empty(npts, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.current_stream().cuda_stream   # run_ours installed a non-default stream
+    assert stream != 0
     lb, ub = -np.ones(d), np.ones(d)
     want = _capi.OUT_PRED | _capi.OUT_S
 
