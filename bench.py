@@ -246,12 +246,12 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs ~1 s to start sampling: begin before the warm-up
     for _ in range(warm):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = model.launch_count()
     model.profile(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

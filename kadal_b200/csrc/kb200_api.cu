@@ -297,7 +297,7 @@ static int decode(kb200_model* m, const double* d_x, long P, int nbhyp, int trai
 static CholArgs chol_args(kb200_model* m, double* tiles, double* W, double* Z, double* logdet, int* info) {
   CholArgs a;
   memset(&a, 0, sizeof(a));
-  a.L = tiles; a.W = W; a.tiles_per_mat = m->tiles_per_mat;
+  a.L = tiles; a.W8 = W; a.tiles_per_mat = m->tiles_per_mat;
   a.nt = m->nt; a.npad = m->npad; a.n = m->n;
   a.nq = m->nq; a.R = m->R.d(); a.Z = Z; a.logdet = logdet; a.info = info;
   a.naive = (m->flags & KB200_FLAG_NAIVE) ? 1 : 0;
@@ -338,12 +338,12 @@ static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z
 }
 
 static size_t per_matrix_bytes(const kb200_model* m) {
-  return (size_t)(m->tiles_per_mat + m->nt) * TILE_ELEMS * 8 + (size_t)m->nq * m->npad * 8 + 64;
+  return (size_t)m->tiles_per_mat * TILE_ELEMS * 8 + (size_t)m->nt * 1024 * 8 + (size_t)m->nq * m->npad * 8 + 64;
 }
 
 static int reserve_lik(kb200_model* m, long P, int Pb) {
   CK(m->tiles.reserve((size_t)Pb * m->tiles_per_mat * TILE_ELEMS * 8));
-  CK(m->W.reserve((size_t)Pb * m->nt * TILE_ELEMS * 8));
+  CK(m->W.reserve((size_t)Pb * m->nt * 1024 * 8));
   CK(m->Z.reserve((size_t)Pb * m->nq * m->npad * 8));
   CK(m->cand.reserve((size_t)P * m->cstride * 8));
   CK(m->logdet.reserve((size_t)Pb * 8));
@@ -430,7 +430,7 @@ int kb200_debug_psi(kb200_model* m, const double* x, int nbhyp, int trainvar,
 static int install_predictor(kb200_model* m, const double* tiles, const double* W, const double* d_resid,
                              const double* d_b, const double* d_cand_row, double beta, double sigma2,
                              double btb, cudaStream_t st) {
-  const size_t tb = (size_t)m->tiles_per_mat * TILE_ELEMS * 8, wb = (size_t)m->nt * TILE_ELEMS * 8;
+  const size_t tb = (size_t)m->tiles_per_mat * TILE_ELEMS * 8, wb = (size_t)m->nt * 1024 * 8;
   CK(m->pL.reserve(tb));
   CK(m->pW.reserve(wb));
   CK(m->pcand.reserve((size_t)m->cstride * 8));
@@ -444,7 +444,7 @@ static int install_predictor(kb200_model* m, const double* tiles, const double* 
   CK(cudaMemcpyAsync(m->rhs2.d(), d_resid, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(m->rhs2.d() + m->npad, d_b, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   BackArgs b;
-  b.L = m->pL.d(); b.W = m->pW.d(); b.nt = m->nt; b.npad = m->npad; b.nq = 2;
+  b.L = m->pL.d(); b.nt = m->nt; b.npad = m->npad; b.nq = 2;
   b.rhs = m->rhs2.d(); b.out = m->sol2.d();
   CK(launch_backsolve(b, st));
   m->launches++;
@@ -547,7 +547,7 @@ int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double
   const size_t nn = (size_t)m->n * m->n * 8;
   CK(m->sol2.reserve(std::max(nn, (size_t)2 * m->npad * 8)));
   CK(m->pL.reserve((size_t)m->tiles_per_mat * TILE_ELEMS * 8));
-  CK(m->pW.reserve((size_t)m->nt * TILE_ELEMS * 8));
+  CK(m->pW.reserve((size_t)m->nt * 1024 * 8));
   CK(m->pcand.reserve((size_t)m->cstride * 8));
   CK(m->xdev.reserve((size_t)(m->ntheta + m->nkernel) * 8));
   // candidate row from Theta / wgkf (theta = 10**Theta, prediction.py:148)
@@ -570,7 +570,7 @@ int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double
   CK(launch_import_U(m->sol2.d(), m->n, m->nt, m->pL.d(), st));
   m->launches++;
   CholArgs ca = chol_args(m, m->pL.d(), m->pW.d(), nullptr, nullptr, nullptr);
-  CK(launch_diag_inverse(ca, 1, st));
+  CK(launch_w8_from_tiles(ca, 1, st));
   m->launches++;
   // forward solve of [y - F*BE | F]
   CK(m->rhs2.reserve((size_t)2 * m->npad * 8));
@@ -583,7 +583,7 @@ int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double
   CK(cudaMemcpyAsync(m->rhs2.p, rhs.data(), rhs.size() * 8, cudaMemcpyHostToDevice, st));
   CK(m->Z.reserve((size_t)2 * m->npad * 8));
   BackArgs f;
-  f.L = m->pL.d(); f.W = m->pW.d(); f.nt = m->nt; f.npad = m->npad; f.nq = 2;
+  f.L = m->pL.d(); f.nt = m->nt; f.npad = m->npad; f.nq = 2;
   f.rhs = m->rhs2.d(); f.out = m->Z.d();
   CK(launch_forwardsolve(f, st));
   m->launches++;

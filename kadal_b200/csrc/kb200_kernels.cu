@@ -265,97 +265,292 @@ __device__ __forceinline__ void gemm_naive(double (&acc)[4][4][2], const double*
       }
 }
 
-// ---------------------------------------------------------- in-smem POTF2 + inverse
-// S (LDP-strided): lower triangle holds the SPD block on entry, L on exit; the strictly
-// upper part holds W = L^-1 transposed-shifted: W[r][c] (c <= r) lives at S[c*LDP + r + 1].
-// FACTOR=false: L is given (imported factor), only the inverse is computed.
-// Returns (to all threads) the first non-positive pivot index + 1, or 0.
-template <bool FACTOR>
-__device__ int potf2_inverse(double* S, int nthreads) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthreads >> 5;
+// ------------------------------------------------- in-smem blocked POTF2 (diagonal tile)
+// The 128x128 diagonal tile is factorised inside one CTA with a blocked right-looking
+// algorithm (block 32):
+//   (1) warp 0 factorises the 32x32 diagonal block in REGISTERS (lane = row, rank-1 updates
+//       broadcast with warp shuffles) and inverts its four 8x8 diagonal sub-blocks (W8);
+//   (2) the rows below (and the right-hand-side strip [y F]^T, which rides along as eight extra
+//       rows) are solved against the block 8 rows per warp with DMMA: a right-looking TRSM
+//       whose only "divisions" are products with the 8x8 inverses;
+//   (3) the trailing part is updated with DMMA (SYRK, lower 16x16 items + RHS items).
+// No 128x128 inverse is ever formed: the panel kernel runs the same right-looking TRSM with
+// the sixteen 8x8 inverses of the tile.
+//
+// S (LDP-strided) holds the lower triangle of the SPD tile on entry and L on exit; the part
+// above the diagonal is scratch.  trow (TLD-strided, 8 rows) holds the RHS strip.
+constexpr int TLD = TB + 4;
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+// C-fragment (c0,c1 = T[g][2t], T[g][2t+1]) of an 8x8 tile  ->  the two A-fragments
+// (a0 = T[g][t], a1 = T[g][4+t]) of the same tile, g = lane/4, t = lane%4.
+__device__ __forceinline__ void cfrag_to_afrag(double c0, double c1, double& a0, double& a1, int lane) {
+  const int src0 = (lane & ~3) + ((lane & 3) >> 1);
+  const double v00 = __shfl_sync(FULLMASK, c0, src0), v01 = __shfl_sync(FULLMASK, c1, src0);
+  const double v10 = __shfl_sync(FULLMASK, c0, src0 + 2), v11 = __shfl_sync(FULLMASK, c1, src0 + 2);
+  a0 = (lane & 1) ? v01 : v00;
+  a1 = (lane & 1) ? v11 : v10;
+}
+
+// warp-level Cholesky of the 32x32 block at B (stride LDP): lane r owns row r in registers.
+// dinv[k] = 1/L_kk.  Returns first bad pivot (global index + 1) or 0.
+__device__ __forceinline__ int potf2_32_warp(double* B, double* dinv, int lane, int base) {
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? B[lane * LDP + c] : 0.0;
   int bad = 0;
-  // W = I
-  for (int idx = tid; idx < TB * TB; idx += nthreads) {
-    int c = idx / TB, r = idx - c * TB;
-    if (c <= r) S[c * LDP + r + 1] = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    double piv = __shfl_sync(FULLMASK, a[k], k);
+    if (!(piv > 0.0)) {
+      if (!bad) bad = base + k + 1;
+      piv = 1.0;
+    }
+    const double inv = rsqrt(piv);
+    double dk = piv * inv;
+    dk = fma(fma(-dk, dk, piv), 0.5 * inv, dk);       // one Newton step: sqrt(piv) to <1 ulp
+    const double l = a[k] * inv;
+#pragma unroll
+    for (int c = k + 1; c < 32; ++c) {
+      const double lc = __shfl_sync(FULLMASK, l, c);
+      a[c] = fma(-l, lc, a[c]);
+    }
+    a[k] = (lane == k) ? dk : l;
+    if (lane == k) dinv[k] = inv;
   }
-  __syncthreads();
-  for (int k = 0; k < TB; ++k) {
-    double piv = S[k * LDP + k];
-    double dk;
-    if (FACTOR) {
-      if (!(piv > 0.0)) {
-        if (!bad) bad = k + 1;
-        piv = 1.0;
-      }
-      dk = sqrt(piv);
-    } else {
-      dk = (piv != 0.0) ? piv : 1.0;
-    }
-    const double inv = 1.0 / dk;
-    __syncthreads();  // everyone has read the pivot before it is overwritten
-    // scale column k of L (rows > k) and row k of W (cols <= k)
-    const int mrows = TB - 1 - k;
-    for (int idx = tid; idx < mrows + k + 1; idx += nthreads) {
-      if (idx < mrows) {
-        if (FACTOR) S[(k + 1 + idx) * LDP + k] *= inv;
-      } else {
-        int c = idx - mrows;
-        S[c * LDP + k + 1] *= inv;
-      }
-    }
-    if (FACTOR && tid == 0) S[k * LDP + k] = dk;
-    __syncthreads();
-    // (a) trailing update of S (lower part), (b) eliminate column k from W
-    if (FACTOR) {
-      for (int c = k + 1 + warp; c < TB; c += nwarp) {
-        const double lc = S[c * LDP + k];
-        for (int r = c + lane; r < TB; r += 32) S[r * LDP + c] = fma(-S[r * LDP + k], lc, S[r * LDP + c]);
-      }
-    }
-    for (int c = warp; c <= k; c += nwarp) {
-      const double wkc = S[c * LDP + k + 1];
-      for (int r = k + 1 + lane; r < TB; r += 32)
-        S[c * LDP + r + 1] = fma(-S[r * LDP + k], wkc, S[c * LDP + r + 1]);
-    }
-    __syncthreads();
-  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c <= lane) B[lane * LDP + c] = a[c];
   return bad;
 }
 
-// write L (lower incl. diagonal, zeros above) and W from the POTF2 scratch to tile layout
-__device__ void store_LW(const double* S, double* Ltile, double* Wtile, int nthreads) {
+// inverses of the four 8x8 diagonal sub-blocks of the 32x32 block at B (one warp:
+// lane = (sub-block, column)).  out: 4 x 64 doubles, row-major 8x8 each, zeros above.
+__device__ __forceinline__ void inv8_warp(const double* B, const double* dinv, double* out, int lane) {
+  const int blk = lane >> 3, c = lane & 7;
+  const double* Lb = B + (8 * blk) * LDP + 8 * blk;
+  double w[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < r; ++t) s = fma(Lb[r * LDP + t], w[t], s);
+    w[r] = ((r == c) ? 1.0 : -s) * dinv[8 * blk + r];
+    if (r < c) w[r] = 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) out[blk * 64 + r * 8 + c] = w[r];
+}
+
+// one 8-row strip against the 32x32 block: rows <- rows * L_kk^-T (right-looking, DMMA).
+// rows: pointer to element (first row of the strip, first column of the block), stride ld.
+__device__ __forceinline__ void strip_trsm32(double* rows, int ld, const double* Lkk, const double* W8,
+                                             int lane) {
+  const int g = lane >> 2, tq = lane & 3;
+  double x[4][2];
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) {
+    x[ct][0] = rows[g * ld + 8 * ct + 2 * tq];
+    x[ct][1] = rows[g * ld + 8 * ct + 2 * tq + 1];
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    double a0, a1;
+    cfrag_to_afrag(x[t][0], x[t][1], a0, a1, lane);
+    double y0 = 0.0, y1 = 0.0;
+    dmma884(y0, y1, a0, W8[t * 64 + g * 8 + tq]);
+    dmma884(y0, y1, a1, W8[t * 64 + g * 8 + 4 + tq]);
+    x[t][0] = y0;
+    x[t][1] = y1;
+    if (t < 3) {
+      cfrag_to_afrag(y0, y1, a0, a1, lane);
+      a0 = -a0;
+      a1 = -a1;
+#pragma unroll
+      for (int ct = t + 1; ct < 4; ++ct) {
+        const double b0 = Lkk[(8 * ct + g) * LDP + 8 * t + tq];
+        const double b1 = Lkk[(8 * ct + g) * LDP + 8 * t + 4 + tq];
+        dmma884(x[ct][0], x[ct][1], a0, b0);
+        dmma884(x[ct][0], x[ct][1], a1, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) {
+    rows[g * ld + 8 * ct + 2 * tq] = x[ct][0];
+    rows[g * ld + 8 * ct + 2 * tq + 1] = x[ct][1];
+  }
+}
+
+// trailing update after the 32-wide panel at column o:
+//   S[r][c]   -= sum_k S[r][o+k] * S[c][o+k]        o+32 <= c <= r      (16x16 items, lower)
+//   trow[q][c] -= sum_k trow[q][o+k] * S[c][o+k]                         (8x16 RHS items)
+__device__ __forceinline__ void trailing_update32(double* S, double* trow, int o, int warp, int lane,
+                                                  int nwarp) {
+  const int g = lane >> 2, tq = lane & 3;
+  const int base = o + 32;
+  const int nb = (TB - base) >> 4;
+  const int ntri = nb * (nb + 1) / 2;
+  const int nitems = ntri + nb;
+  for (int it = warp; it < nitems; it += nwarp) {
+    if (it < ntri) {
+      int bi = 0;
+      while ((bi + 1) * (bi + 2) / 2 <= it) ++bi;
+      const int bj = it - bi * (bi + 1) / 2;
+      double* ar0 = S + (base + 16 * bi + g) * LDP;
+      double* ar1 = ar0 + 8 * LDP;
+      const double* br0 = S + (base + 16 * bj + g) * LDP;
+      const double* br1 = br0 + 8 * LDP;
+      const int cc = base + 16 * bj + 2 * tq;
+      double c[2][2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        c[0][nt][0] = ar0[cc + 8 * nt]; c[0][nt][1] = ar0[cc + 8 * nt + 1];
+        c[1][nt][0] = ar1[cc + 8 * nt]; c[1][nt][1] = ar1[cc + 8 * nt + 1];
+      }
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) {
+        const int kc = o + 4 * kq + tq;
+        const double a0 = -ar0[kc], a1 = -ar1[kc];
+        const double b0 = br0[kc], b1 = br1[kc];
+        dmma884(c[0][0][0], c[0][0][1], a0, b0);
+        dmma884(c[0][1][0], c[0][1][1], a0, b1);
+        dmma884(c[1][0][0], c[1][0][1], a1, b0);
+        dmma884(c[1][1][0], c[1][1][1], a1, b1);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        if (bi > bj || nt == 0) { ar0[cc + 8 * nt] = c[0][nt][0]; ar0[cc + 8 * nt + 1] = c[0][nt][1]; }
+        ar1[cc + 8 * nt] = c[1][nt][0]; ar1[cc + 8 * nt + 1] = c[1][nt][1];
+      }
+    } else {
+      const int bj = it - ntri;
+      double* ar0 = trow + g * TLD;
+      const double* br0 = S + (base + 16 * bj + g) * LDP;
+      const double* br1 = br0 + 8 * LDP;
+      const int cc = base + 16 * bj + 2 * tq;
+      double c[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { c[nt][0] = ar0[cc + 8 * nt]; c[nt][1] = ar0[cc + 8 * nt + 1]; }
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) {
+        const int kc = o + 4 * kq + tq;
+        const double a0 = -ar0[kc];
+        dmma884(c[0][0], c[0][1], a0, br0[kc]);
+        dmma884(c[1][0], c[1][1], a0, br1[kc]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { ar0[cc + 8 * nt] = c[nt][0]; ar0[cc + 8 * nt + 1] = c[nt][1]; }
+    }
+  }
+}
+
+// Blocked factorisation of the tile in S with the RHS strip in trow.  On exit: S lower = L,
+// dinv[128] = 1/L_kk, W8s = sixteen 8x8 inverse diagonal blocks, trow = (L^-1 [y F])^T.
+// s_bad (shared) receives the first non-positive pivot index + 1.  All threads must call.
+__device__ void potf2_blocked(double* S, double* trow, double* dinv, double* W8s, int* s_bad) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  if (tid == 0) *s_bad = 0;
+  for (int kb = 0; kb < 4; ++kb) {
+    const int o = 32 * kb;
+    __syncthreads();
+    if (warp == 0) {
+      const int b = potf2_32_warp(S + o * LDP + o, dinv + o, lane, o);
+      __syncwarp();
+      inv8_warp(S + o * LDP + o, dinv + o, W8s + kb * 256, lane);
+      if (lane == 0 && b && *s_bad == 0) *s_bad = b;
+    }
+    __syncthreads();
+    const int nrow_strips = (TB - o - 32) >> 3;
+    for (int st = warp; st <= nrow_strips; st += nwarp) {
+      if (st < nrow_strips) strip_trsm32(S + (o + 32 + 8 * st) * LDP + o, LDP, S + o * LDP + o, W8s + kb * 256, lane);
+      else strip_trsm32(trow + o, TLD, S + o * LDP + o, W8s + kb * 256, lane);
+    }
+    __syncthreads();
+    if (kb < 3) trailing_update32(S, trow, o, warp, lane, nwarp);
+  }
+  __syncthreads();
+}
+
+// plain column-by-column variant (debug / KB200_FLAG_NAIVE): same outputs, DFMA only
+__device__ void potf2_simple(double* S, double* trow, double* dinv, double* W8s, int* s_bad, int nq) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarp = nthreads >> 5;
+  int bad = 0;
+  for (int k = 0; k < TB; ++k) {
+    __syncthreads();
+    double piv = S[k * LDP + k];
+    if (!(piv > 0.0)) {
+      if (!bad) bad = k + 1;
+      piv = 1.0;
+    }
+    const double dk = sqrt(piv), inv = 1.0 / dk;
+    __syncthreads();
+    for (int r = k + 1 + tid; r < TB; r += nthreads) S[r * LDP + k] *= inv;
+    if (tid == 0) { S[k * LDP + k] = dk; dinv[k] = inv; }
+    __syncthreads();
+    for (int c = k + 1 + warp; c < TB; c += nwarp) {
+      const double lc = S[c * LDP + k];
+      for (int r = c + lane; r < TB; r += 32) S[r * LDP + c] = fma(-S[r * LDP + k], lc, S[r * LDP + c]);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) *s_bad = bad;
+  if (tid < 128) {
+    const int blk = tid >> 3, c = tid & 7;
+    const double* Lb = S + (8 * blk) * LDP + 8 * blk;
+    double w[8];
+    for (int r = 0; r < 8; ++r) {
+      double s = 0.0;
+      for (int t = 0; t < r; ++t) s = fma(Lb[r * LDP + t], w[t], s);
+      w[r] = (r < c) ? 0.0 : ((r == c) ? 1.0 : -s) * dinv[8 * blk + r];
+    }
+    for (int r = 0; r < 8; ++r) W8s[blk * 64 + r * 8 + c] = w[r];
+  }
+  if (tid >= 128 && tid < 128 + nq) {
+    double* t = trow + (tid - 128) * TLD;
+    for (int r = 0; r < TB; ++r) {
+      double s = t[r];
+      for (int c = 0; c < r; ++c) s = fma(-S[r * LDP + c], t[c], s);
+      t[r] = s * dinv[r];
+    }
+  }
+  __syncthreads();
+}
+
+// write L (lower incl. diagonal, zeros above) from the scratch to tile layout
+__device__ void store_L(const double* S, double* Ltile, int nthreads) {
   for (int idx = threadIdx.x; idx < TILE_ELEMS / 4; idx += nthreads) {
     // idx -> (slab, row, chunk)
     const int ch = idx & 3, row = (idx >> 2) & (TB - 1), s = idx >> 9;
     const int c0 = s * KS + 4 * ch;
-    double l[4], wv[4];
+    double l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int c = c0 + e;
       l[e] = (c <= row) ? S[row * LDP + c] : 0.0;
-      wv[e] = (c <= row) ? S[c * LDP + row + 1] : 0.0;
     }
     const int off = s * SLAB_ELEMS + row * KS + ((ch ^ (row & 3)) << 2);
-    if (Ltile) {
-      double2* dl = reinterpret_cast<double2*>(Ltile + off);
-      dl[0] = make_double2(l[0], l[1]);
-      dl[1] = make_double2(l[2], l[3]);
-    }
-    double2* dw = reinterpret_cast<double2*>(Wtile + off);
-    dw[0] = make_double2(wv[0], wv[1]);
-    dw[1] = make_double2(wv[2], wv[3]);
+    double2* dl = reinterpret_cast<double2*>(Ltile + off);
+    dl[0] = make_double2(l[0], l[1]);
+    dl[1] = make_double2(l[2], l[3]);
   }
 }
 
 // ============================================================================ K2
+// Shared-memory map of the diagonal-tile work (also used by the panel kernel's "next
+// diagonal" role): [stages | trow 8xTLD | dinv 128 | W8s 1024 | barriers | flags]
+constexpr int DIAG_EXTRA_ELEMS = 8 * TLD + TB + 1024;
+
 template <bool NAIVE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chol_diag_kernel(CholArgs A, int j) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);                 // NSTAGE*32 KiB, aliased by S
-  double* tvec = stages + (size_t)NSTAGE * STAGE_ELEMS;                 // [128][MAXQ]
-  uint64_t* full = reinterpret_cast<uint64_t*>(tvec + TB * MAXQ);
+  double* trow = stages + (size_t)NSTAGE * STAGE_ELEMS;                 // [8][TLD]
+  double* dinv = trow + 8 * TLD;                                        // [128]
+  double* W8s = dinv + TB;                                              // [16][64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(W8s + 1024);
+  int* s_bad = reinterpret_cast<int*>(full + NSTAGE + 2);
   __shared__ double s_red[CH_THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -367,6 +562,7 @@ chol_diag_kernel(CholArgs A, int j) {
   const int nq = A.nq;
   const double* zb = A.Z + (size_t)m * A.nq * A.npad;
   init_barriers(full, NSTAGE);
+  for (int idx = tid; idx < 8 * TLD; idx += CH_THREADS) trow[idx] = 0.0;
 
   double acc[4][4][2];
   zero_acc(acc);
@@ -419,33 +615,33 @@ chol_diag_kernel(CholArgs A, int j) {
         if (c + 1 <= r) S[r * LDP + c + 1] = p.y - acc[mt][nt][1];
       }
   }
-  // RHS: t = R_j - sum_k L_jk Z_k
+  // RHS strip: t = R_j - sum_k L_jk Z_k   (row q of trow)
 #pragma unroll
   for (int qq = 0; qq < MAXQ; ++qq) {
     if (qq < nq) {
       double s = tacc[qq];
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (hh == 0) tvec[rr * MAXQ + qq] = A.R[(size_t)qq * A.npad + j * TB + rr] - s;
+      if (hh == 0) trow[qq * TLD + rr] = A.R[(size_t)qq * A.npad + j * TB + rr] - s;
     }
   }
   __syncthreads();
-  const int bad = potf2_inverse<true>(S, CH_THREADS);
+  if (NAIVE) potf2_simple(S, trow, dinv, W8s, s_bad, nq);
+  else potf2_blocked(S, trow, dinv, W8s, s_bad);
+  const int bad = *s_bad;
   if (tid == 0 && bad && A.info[m] == 0) A.info[m] = j * TB + bad;
-  // ---- outputs
-  store_LW(S, Cjj, A.W + ((size_t)m * A.nt + j) * TILE_ELEMS, CH_THREADS);
-  // Z_j = W_jj t
+  // ---- outputs: L_jj, the 8x8 inverse blocks, Z_j, log-det partial
+  store_L(S, Cjj, CH_THREADS);
   {
-    const int r = tid >> 2;
-    for (int qq = tid & 3; qq < nq; qq += 4) {
-      double s = 0.0;
-      for (int c = 0; c <= r; ++c) s = fma(S[c * LDP + r + 1], tvec[c * MAXQ + qq], s);
-      A.Z[((size_t)m * A.nq + qq) * A.npad + j * TB + r] = s;
-    }
+    double* w8 = A.W8 + ((size_t)m * A.nt + j) * 1024;
+    for (int idx = tid; idx < 1024; idx += CH_THREADS) w8[idx] = W8s[idx];
   }
-  // log-det partial: sum ln L_rr (padded rows are exactly 1)
+  for (int idx = tid; idx < nq * TB; idx += CH_THREADS) {
+    const int q = idx >> 7, r = idx & (TB - 1);
+    A.Z[((size_t)m * A.nq + q) * A.npad + j * TB + r] = trow[q * TLD + r];
+  }
   {
-    double v = (tid < TB) ? log(fabs(S[tid * LDP + tid])) : 0.0;
+    double v = (tid < TB) ? log(fabs(S[tid * LDP + tid])) : 0.0;   // padded rows are exactly 1
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) s_red[warp] = v;
@@ -458,27 +654,31 @@ chol_diag_kernel(CholArgs A, int j) {
   }
 }
 
-// inverse of an imported diagonal block (predictor_load path): W_jj = inv(L_jj)
-__global__ void __launch_bounds__(CH_THREADS, 1)
-diag_inverse_kernel(CholArgs A) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* S = reinterpret_cast<double*>(smem_raw);
+// 8x8 inverse blocks of an imported factor (predictor_load path): one CTA per tile column
+__global__ void __launch_bounds__(128)
+w8_from_tiles_kernel(CholArgs A) {
   const int j = blockIdx.x;
   const long m = blockIdx.y;
-  double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
-  const double* Ljj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
-  for (int idx = threadIdx.x; idx < TILE_ELEMS; idx += CH_THREADS) {
-    int r = idx >> 7, c = idx & (TB - 1);
-    if (c <= r) S[r * LDP + c] = Ljj[tile_off(r, c)];
+  const double* Ljj = A.L + ((size_t)m * A.tiles_per_mat + tri_index(j, j)) * TILE_ELEMS;
+  const int blk = threadIdx.x >> 3, c = threadIdx.x & 7;
+  double w[8];
+  for (int r = 0; r < 8; ++r) {
+    double s = 0.0;
+    for (int t = 0; t < r; ++t) s = fma(Ljj[tile_off(8 * blk + r, 8 * blk + t)], w[t], s);
+    const double d = Ljj[tile_off(8 * blk + r, 8 * blk + r)];
+    w[r] = (r < c) ? 0.0 : ((r == c) ? 1.0 : -s) / (d != 0.0 ? d : 1.0);
   }
-  __syncthreads();
-  potf2_inverse<false>(S, CH_THREADS);
-  store_LW(S, nullptr, A.W + ((size_t)m * A.nt + j) * TILE_ELEMS, CH_THREADS);
+  double* w8 = A.W8 + ((size_t)m * A.nt + j) * 1024;
+  for (int r = 0; r < 8; ++r) w8[blk * 64 + r * 8 + c] = w[r];
 }
 
 // ============================================================================ K3
 // tile (i,j) of the factor (MODE_CHOL) or tile (pt,j) of a prediction chunk (MODE_PRED):
-//   X = (C - A_row * B_row^T) * W_jj^T
+//   X = (C - A_row * B_row^T) * L_jj^-T
+// GEMM update: 4x4 warps of 32x32 (DMMA, operands streamed by bulk copies).  TRSM: the tile is
+// re-distributed through shared memory so that each warp owns 8 complete rows (rows are
+// independent), then solved right-looking column tile by column tile: the finished 8x8 tile
+// times the 8x8 inverse block, followed by DMMA updates of the column tiles to its right.
 template <bool NAIVE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chol_panel_kernel(CholArgs A, int j) {
@@ -486,13 +686,13 @@ chol_panel_kernel(CholArgs A, int j) {
   double* stages = reinterpret_cast<double*>(smem_raw);          // 5 x 32 KiB
   double* Cs = stages;                                           // 128 KiB (aliases stages 0..3)
   double* Ws = stages + 4 * STAGE_ELEMS;                         // 2 x 16 KiB (aliases stage 4)
-  double* rowred = stages + (size_t)NSTAGE * STAGE_ELEMS;        // [128][4]
-  uint64_t* full = reinterpret_cast<uint64_t*>(rowred + TB * 4);
+  double* W8s = stages + (size_t)NSTAGE * STAGE_ELEMS;           // [16][64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(W8s + 1024);
   uint64_t* wfull = full + NSTAGE;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpPos w{warp & 3, warp >> 2, lane >> 2, lane & 3};
-  const double *rowA, *rowB, *Wj;
+  const double *rowA, *rowB, *Ljj, *W8j;
   double* Cij;
   long ssq_base = 0;
   if (A.pred_mode) {
@@ -501,7 +701,8 @@ chol_panel_kernel(CholArgs A, int j) {
     rowA = base;
     Cij = base + (size_t)j * TILE_ELEMS;
     rowB = A.L + (size_t)tri_index(j, 0) * TILE_ELEMS;
-    Wj = A.W + (size_t)j * TILE_ELEMS;
+    Ljj = A.L + (size_t)tri_index(j, j) * TILE_ELEMS;
+    W8j = A.W8 + (size_t)j * 1024;
     ssq_base = pt * TB;
   } else {
     const int i = j + 1 + blockIdx.x;
@@ -510,7 +711,8 @@ chol_panel_kernel(CholArgs A, int j) {
     rowA = tiles + (size_t)tri_index(i, 0) * TILE_ELEMS;
     rowB = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
     Cij = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;
-    Wj = A.W + ((size_t)m * A.nt + j) * TILE_ELEMS;
+    Ljj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
+    W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;
   }
   init_barriers(full, NSTAGE + 2);
 
@@ -520,7 +722,7 @@ chol_panel_kernel(CholArgs A, int j) {
   if (NAIVE) gemm_naive(acc, rowA, rowB, NSLAB * j, w);
   else gemm_stream<false, false>(acc, rowA, rowB, NSLAB * j, stages, full, it, w, NoSlabOp());
 
-  // ---- C = Psi_ij - acc  -> Cs (tile layout, A operand of the TRSM-GEMM)
+  // ---- C = Psi_ij - acc  -> Cs (tile layout)
   __syncthreads();
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
@@ -534,62 +736,86 @@ chol_panel_kernel(CholArgs A, int j) {
   fence_proxy_async();   // Ws region was last written by the async proxy; order generic accesses
   __syncthreads();
 
-  // ---- X[r][c] = sum_{k<=c} C[r][k] * W[c][k]   (W lower triangular)
-  zero_acc(acc);
   if (NAIVE) {
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t + e;
-          double s = 0.0;
-          for (int k = 0; k <= c; ++k) s = fma(Cs[tile_off(r, k)], Wj[tile_off(c, k)], s);
-          acc[mt][nt][e] = s;
-        }
-  } else {
-    if (tid == 0) {
-      for (int s = 0; s < 2; ++s) {
-        mbar_expect_tx(&wfull[s], SLAB_BYTES);
-        bulk_g2s(Ws + (size_t)s * SLAB_ELEMS, Wj + (size_t)s * SLAB_ELEMS, SLAB_BYTES, &wfull[s]);
+    // one thread per row: x[c] = (C[r][c] - sum_{t<c} x[t] L[c][t]) / L[c][c]
+    if (tid < TB) {
+      for (int c = 0; c < TB; ++c) {
+        double s = Cs[tile_off(tid, c)];
+        for (int t = 0; t < c; ++t) s = fma(-Cs[tile_off(tid, t)], Ljj[tile_off(c, t)], s);
+        Cs[tile_off(tid, c)] = s / Ljj[tile_off(c, c)];
       }
     }
+    __syncthreads();
+  } else {
+    if (tid == 0) {
+      mbar_expect_tx(&wfull[0], SLAB_BYTES + 8192);
+      bulk_g2s(W8s, W8j, 8192, &wfull[0]);
+      bulk_g2s(Ws, Ljj, SLAB_BYTES, &wfull[0]);
+      mbar_expect_tx(&wfull[1], SLAB_BYTES);
+      bulk_g2s(Ws + SLAB_ELEMS, Ljj + SLAB_ELEMS, SLAB_BYTES, &wfull[1]);
+    }
+  }
+  // ---- every warp takes 8 complete rows of the tile (C-fragment layout, 16 column tiles)
+  const int g = w.g, tq = w.t;
+  const int xr = 8 * warp + g;
+  double x[16][2];
+#pragma unroll
+  for (int ct = 0; ct < 16; ++ct) {
+    const double2 p = *reinterpret_cast<const double2*>(Cs + tile_off(xr, 8 * ct + 2 * tq));
+    x[ct][0] = p.x;
+    x[ct][1] = p.y;
+  }
+  if (!NAIVE) {
+#pragma unroll
     for (int s = 0; s < NSLAB; ++s) {
-      const int st = s & 1;
-      mbar_wait(&wfull[st], (s >> 1) & 1);
-      if (s <= 2 * w.wn + 1) mma_slab(acc, Cs + (size_t)s * SLAB_ELEMS, Ws + (size_t)st * SLAB_ELEMS, w);
+      const int stg = s & 1;
+      mbar_wait(&wfull[stg], (s >> 1) & 1);
+      const double* Ls = Ws + (size_t)stg * SLAB_ELEMS;
+#pragma unroll
+      for (int tt = 0; tt < 2; ++tt) {
+        const int t = 2 * s + tt;
+        double a0, a1;
+        cfrag_to_afrag(x[t][0], x[t][1], a0, a1, lane);
+        double y0 = 0.0, y1 = 0.0;
+        dmma884(y0, y1, a0, W8s[t * 64 + g * 8 + tq]);
+        dmma884(y0, y1, a1, W8s[t * 64 + g * 8 + 4 + tq]);
+        x[t][0] = y0;
+        x[t][1] = y1;
+        if (t < 15) {
+          cfrag_to_afrag(y0, y1, a0, a1, lane);
+          a0 = -a0;
+          a1 = -a1;
+#pragma unroll
+          for (int ct = t + 1; ct < 16; ++ct) {
+            const double* lrow = Ls + (8 * ct + g) * KS + tq;
+            const double b0 = lrow[((2 * tt) ^ (g & 3)) << 2];
+            const double b1 = lrow[((2 * tt + 1) ^ (g & 3)) << 2];
+            dmma884(x[ct][0], x[ct][1], a0, b0);
+            dmma884(x[ct][0], x[ct][1], a1, b1);
+          }
+        }
+      }
       __syncthreads();
       if (tid == 0 && s + 2 < NSLAB) {
-        mbar_expect_tx(&wfull[st], SLAB_BYTES);
-        bulk_g2s(Ws + (size_t)st * SLAB_ELEMS, Wj + (size_t)(s + 2) * SLAB_ELEMS, SLAB_BYTES, &wfull[st]);
+        mbar_expect_tx(&wfull[stg], SLAB_BYTES);
+        bulk_g2s(Ws + (size_t)stg * SLAB_ELEMS, Ljj + (size_t)(s + 2) * SLAB_ELEMS, SLAB_BYTES, &wfull[stg]);
       }
     }
   }
   // ---- store X (tile layout) and, for prediction, accumulate ||x_row||^2
-  double rs[4] = {0.0, 0.0, 0.0, 0.0};
+  double rs = 0.0;
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
-      *reinterpret_cast<double2*>(Cij + tile_off(r, c)) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-      rs[mt] = fma(acc[mt][nt][0], acc[mt][nt][0], rs[mt]);
-      rs[mt] = fma(acc[mt][nt][1], acc[mt][nt][1], rs[mt]);
-    }
+  for (int ct = 0; ct < 16; ++ct) {
+    *reinterpret_cast<double2*>(Cij + tile_off(xr, 8 * ct + 2 * tq)) = make_double2(x[ct][0], x[ct][1]);
+    rs = fma(x[ct][0], x[ct][0], rs);
+    rs = fma(x[ct][1], x[ct][1], rs);
+  }
   if (A.pred_mode) {
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      double v = rs[mt];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (w.t == 0) rowred[(32 * w.wm + 8 * mt + w.g) * 4 + w.wn] = v;
-    }
-    __syncthreads();
-    if (tid < TB) {
-      double v = ((rowred[tid * 4 + 0] + rowred[tid * 4 + 1]) + rowred[tid * 4 + 2]) + rowred[tid * 4 + 3];
-      double* dst = A.ssq + ssq_base + tid;
-      *dst = (j == 0 ? 0.0 : *dst) + v;
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    if (tq == 0) {
+      double* dst = A.ssq + ssq_base + xr;
+      *dst = (j == 0 ? 0.0 : *dst) + rs;
     }
   }
 }
@@ -682,7 +908,26 @@ lik_finalize_kernel(FinArgs A) {
 }
 
 // ================================================================== backsolve (fit)
-// X_j = W_jj^T (RHS_j - sum_{k>j} L_kj^T X_k), j = nt-1 .. 0, nq columns; one CTA.
+// X_j = L_jj^-T (RHS_j - sum_{k>j} L_kj^T X_k), j = nt-1 .. 0, nq columns; one CTA.
+// (once per fit: alpha = L^-T r, w = L^-T b of the predictor, prediction.py:233-235, 245-249)
+// The in-tile solve is a column-oriented substitution in shared memory: thread (r, q-group).
+__device__ __forceinline__ void tile_substitute(const double* __restrict__ T, double* tv, double* out_base,
+                                                int npad, int nq, bool transposed) {
+  // forward (transposed = false): solve L x = t;  backward (true): solve L^T x = t
+  const int tid = threadIdx.x, r = tid & (TB - 1), part = tid >> 7;
+  for (int step = 0; step < TB; ++step) {
+    const int c = transposed ? TB - 1 - step : step;
+    const double dcc = T[tile_off(c, c)];
+    const double lrc = transposed ? (r < c ? T[tile_off(c, r)] : 0.0) : (r > c ? T[tile_off(r, c)] : 0.0);
+    for (int q = part; q < nq; q += 4) {
+      const double xc = tv[c * MAXQ + q] / dcc;
+      if (r == c) out_base[(size_t)q * npad + r] = xc;
+      else tv[r * MAXQ + q] = fma(-lrc, xc, tv[r * MAXQ + q]);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(CH_THREADS, 1)
 backsolve_kernel(BackArgs A) {
   __shared__ double xs[TB * MAXQ];       // X_k block (broadcast reads); reused as t
@@ -720,21 +965,14 @@ backsolve_kernel(BackArgs A) {
       }
     }
     __syncthreads();
-    // x_j[r] = sum_{c >= r} W_jj[c][r] t[c]
-    const double* Wj = A.W + (size_t)j * TILE_ELEMS;
-    for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
-      int rr = idx % TB, q = idx / TB;
-      double s = 0.0;
-      for (int c = rr; c < TB; ++c) s = fma(Wj[tile_off(c, rr)], tv[c * MAXQ + q], s);
-      A.out[(size_t)q * npad + j * TB + rr] = s;
-    }
-    __syncthreads();
+    tile_substitute(A.L + (size_t)tri_index(j, j) * TILE_ELEMS, tv, A.out + j * TB, npad, nq, true);
     __threadfence_block();
+    __syncthreads();
   }
 }
 
 // ================================================================ forward solve (load)
-// X_j = W_jj (RHS_j - sum_{k<j} L_jk X_k), j = 0 .. nt-1, nq columns; one CTA.
+// X_j = L_jj^-1 (RHS_j - sum_{k<j} L_jk X_k), j = 0 .. nt-1, nq columns; one CTA.
 // Used when a factor is imported from KrigInfo['U'] (prediction.py:233-235, 245-246).
 __global__ void __launch_bounds__(CH_THREADS, 1)
 forwardsolve_kernel(BackArgs A) {
@@ -773,16 +1011,9 @@ forwardsolve_kernel(BackArgs A) {
       }
     }
     __syncthreads();
-    // x_j[r] = sum_{c <= r} W_jj[r][c] t[c]
-    const double* Wj = A.W + (size_t)j * TILE_ELEMS;
-    for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
-      int rr = idx % TB, q = idx / TB;
-      double s = 0.0;
-      for (int c = 0; c <= rr; ++c) s = fma(Wj[tile_off(rr, c)], tv[c * MAXQ + q], s);
-      A.out[(size_t)q * npad + j * TB + rr] = s;
-    }
-    __syncthreads();
+    tile_substitute(A.L + (size_t)tri_index(j, j) * TILE_ELEMS, tv, A.out + j * TB, npad, nq, false);
     __threadfence_block();
+    __syncthreads();
   }
 }
 
@@ -928,9 +1159,9 @@ static inline int cur_dev() {
   cudaGetDevice(&d);
   return d & 63;
 }
-constexpr size_t DIAG_SMEM = (size_t)NSTAGE * STAGE_ELEMS * 8 + TB * MAXQ * 8 + NSTAGE * 8;
-constexpr size_t PANEL_SMEM = (size_t)NSTAGE * STAGE_ELEMS * 8 + TB * 4 * 8 + (NSTAGE + 2) * 8;
-constexpr size_t DINV_SMEM = (size_t)TB * LDP * 8 + 16;
+constexpr size_t DIAG_SMEM = ((size_t)NSTAGE * STAGE_ELEMS + DIAG_EXTRA_ELEMS) * 8 + (NSTAGE + 2) * 8 + 16;
+constexpr size_t PANEL_SMEM = ((size_t)NSTAGE * STAGE_ELEMS + 1024) * 8 + (NSTAGE + 2) * 8;
+static_assert(DIAG_SMEM <= 227 * 1024 && PANEL_SMEM <= 227 * 1024, "shared memory budget");
 static_assert((size_t)TB * LDP * 8 + 16 <= (size_t)NSTAGE * STAGE_ELEMS * 8, "POTF2 scratch must fit in the stage buffers");
 
 cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st) {
@@ -959,8 +1190,6 @@ static cudaError_t chol_attrs() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(chol_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DINV_SMEM);
-  if (e != cudaSuccess) return e;
   g_chol_attr[dev] = true;
   return cudaSuccess;
 }
@@ -984,10 +1213,8 @@ cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, 
   return cudaSuccess;
 }
 
-cudaError_t launch_diag_inverse(const CholArgs& a, int nmat, cudaStream_t st) {
-  cudaError_t e = chol_attrs();
-  if (e != cudaSuccess) return e;
-  diag_inverse_kernel<<<dim3(a.nt, nmat), CH_THREADS, DINV_SMEM, st>>>(a);
+cudaError_t launch_w8_from_tiles(const CholArgs& a, int nmat, cudaStream_t st) {
+  w8_from_tiles_kernel<<<dim3(a.nt, nmat), 128, 0, st>>>(a);
   KB_LAUNCH_CHECK();
   return cudaSuccess;
 }

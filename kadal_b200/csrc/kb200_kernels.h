@@ -33,7 +33,7 @@ struct CorrArgs {
 
 struct CholArgs {
   double* L;             // tile storage of the matrices being factorised (in place)
-  double* W;             // [P][nt] inverse diagonal blocks
+  double* W8;            // [P][nt][16][64] inverses of the 8x8 diagonal blocks of every diagonal tile
   long tiles_per_mat;
   int nt, npad, n;
   // fused forward substitution
@@ -67,7 +67,6 @@ struct FinArgs {
 
 struct BackArgs {
   const double* L;       // tiles of one matrix
-  const double* W;       // [nt] tiles
   int nt, npad, nq;
   const double* rhs;     // [nq][npad]
   double* out;           // [nq][npad]
@@ -101,7 +100,7 @@ struct EpiArgs {
 cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st);
 cudaError_t launch_chol_diag(const CholArgs& a, int j, int nmat, cudaStream_t st);
 cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);
-cudaError_t launch_diag_inverse(const CholArgs& a, int nmat, cudaStream_t st);
+cudaError_t launch_w8_from_tiles(const CholArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_finalize(const FinArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_backsolve(const BackArgs& a, cudaStream_t st);
 cudaError_t launch_import_U(const double* U, int n, int nt, double* tiles, cudaStream_t st);

@@ -30,7 +30,21 @@ def kb():
 
 
 def nll_tol(cond):
-    return max(TOL_NLL, 10 * cond * 2.0 ** -53)
+    """1e-9, or half of cond * ulp where that is larger: SURVEY.md Appendix E measures the
+    reference's own reordering noise at 6-8e-10 for cond 2e8 (about 0.03 cond*ulp) and a
+    one-ulp change of the kernel entries at up to 0.07 cond*ulp."""
+    return max(TOL_NLL, 0.5 * cond * 2.0 ** -53)
+
+
+def conds_of(info, pop):
+    """cond(Psi + eps I) per candidate, from the oracle (the checker)."""
+    out = []
+    for x in pop:
+        A = copy.deepcopy(info)
+        ko.likelihood(np.array(x, dtype=float), A, "all", False, check_pd=False)
+        n = A["Psi"].shape[0]
+        out.append(np.linalg.cond(A["Psi"] + np.eye(n) * 10.0 ** float(A["nugget"])))
+    return np.array(out)
 
 
 # ------------------------------------------------------------------ golden vectors
@@ -67,8 +81,11 @@ def test_c3_population_and_bulk_predict_against_golden(kb, golden_c3):
     info, xp = cases.c3_info(g)
     nll, inf = kb.likelihood_batch(g["pop"], info, False)
     assert np.all(inf == 0)
-    assert relerr(nll, g["pop_nll"]) < nll_tol(3e8)
-    assert relerr(nll[:32], g["pop_nll"][:32]) < TOL_NLL          # theta in [-5,5] / [-1,1]: cond <= 1e8
+    conds = conds_of(info, g["pop"])
+    rel = np.abs(nll - g["pop_nll"]) / np.maximum(np.abs(g["pop_nll"]), 1.0)
+    tol = np.array([nll_tol(c) for c in conds])
+    assert np.all(rel < tol), (rel / tol).max()
+    assert np.all(rel[conds < 1e7] < TOL_NLL)                       # plain 1e-9 wherever cond*ulp allows it
     assert int(np.argmin(nll)) == int(np.argmin(g["pop_nll"]))
     kb.likelihood(g["fit_x"].copy(), info, "all", False)
     s2 = float(g["fit_s2"][0])
@@ -221,22 +238,30 @@ def test_return_types_and_errors(kb, golden_c):
 
 
 def test_not_positive_definite_is_reported_per_candidate(kb):
+    # KPLS-exponential with signed coefficients gives "distances" of either sign, hence
+    # correlations > 1: an indefinite Psi, robustly -- unlike an exactly
+    # singular matrix, whose last pivot is rounding noise of either sign.
     rng = np.random.default_rng(0)
-    X = rng.uniform(-1, 1, (40, 2))
-    X[7] = X[3]                               # duplicated sample, vanishing nugget -> singular
-    info = ko.make_kriginfo(X, np.ones((40, 1)) + X[:, :1], nugget=-300)
-    pop = np.array([[0.0, 0.0], [-2.0, -2.0], [0.5, 0.5]])
+    X = rng.uniform(-1, 1, (40, 4))
+    info = ko.make_kriginfo(X, np.ones((40, 1)) + X[:, :1], pls=rng.standard_normal((4, 2)),
+                            n_princomp=2, kernel=("exponential",))
+    pop = np.array([[0.0, 0.0], [-0.5, 0.3], [0.5, 0.5]])
     nll, inf = kb.likelihood_batch(pop, info, False)
     assert np.all(inf != 0) and np.all(np.isinf(nll))
     with pytest.raises(np.linalg.LinAlgError):
         kb.likelihood(pop[0], info, "default", False)
     with pytest.raises(np.linalg.LinAlgError):
         ko.likelihood(pop[0], copy.deepcopy(info), "default", False, check_pd=False)
-    # a healthy candidate in the same batch is unaffected by its neighbours
-    Xg = np.delete(X, 7, axis=0)
-    good = ko.make_kriginfo(Xg, np.ones((39, 1)) + Xg[:, :1])
-    n1, i1 = kb.likelihood_batch(pop, good, False)
+    # healthy candidates of another model are unaffected; a duplicated sample with a vanishing
+    # nugget (exactly singular) must give either a flagged candidate or a finite value, never a crash
+    good = ko.make_kriginfo(X, np.ones((40, 1)) + X[:, :1])
+    n1, i1 = kb.likelihood_batch(rng.uniform(-1, 1, (3, 4)), good, False)
     assert np.all(i1 == 0) and np.all(np.isfinite(n1))
+    Xd = X.copy()
+    Xd[7] = Xd[3]
+    sing = ko.make_kriginfo(Xd, np.ones((40, 1)) + Xd[:, :1], nugget=-300)
+    n2, i2 = kb.likelihood_batch(np.zeros((2, 4)), sing, False)
+    assert np.all((i2 != 0) == np.isinf(n2)) and not np.any(np.isnan(n2))
 
 
 def test_debug_naive_kernels_agree_with_dmma(kb):
@@ -248,7 +273,7 @@ def test_debug_naive_kernels_agree_with_dmma(kb):
     pop = w["popB"][:8]
     na, _ = a.lik_batch(pop, False, -6.0)
     nb, _ = b.lik_batch(pop, False, -6.0)
-    assert relerr(na, nb) < 1e-12
+    assert relerr(na, nb) < 1e-9    # two different factorisation orders (cond up to 5e8)
     a.close()
     b.close()
 
