@@ -324,8 +324,9 @@ static int assemble(kb200_model* m, const double* d_cand, int Pb, double* tiles,
 static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z, double* logdet,
                      int* info, cudaStream_t st) {
   CholArgs a = chol_args(m, tiles, W, Z, logdet, info);
+  a.fuse_diag = a.naive ? 0 : 1;
   for (int j = 0; j < m->nt; ++j) {
-    {
+    if (j == 0 || !a.fuse_diag) {
       Timed t(m, KB200_PROF_DIAG, st);
       CK(launch_chol_diag(a, j, Pb, st));
     }

@@ -183,11 +183,13 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 }
 
-// one 16-wide k slab: acc += As(128x16) * Bs(128x16)^T on the warp's 32x32 sub-tile
+// one 16-wide k slab (k quarters KQ0 <= kq < KQ1 of it): acc += As(128x16) * Bs(128x16)^T on the
+// warp's 32x32 sub-tile
+template <int KQ0 = 0, int KQ1 = 4>
 __device__ __forceinline__ void mma_slab(double (&acc)[4][4][2], const double* As, const double* Bs,
                                          const WarpPos& w) {
 #pragma unroll
-  for (int kq = 0; kq < 4; ++kq) {
+  for (int kq = KQ0; kq < KQ1; ++kq) {
     const int sw = ((kq ^ (w.g & 3)) << 2) + w.t;
     double a[4], b[4];
 #pragma unroll
@@ -201,21 +203,81 @@ __device__ __forceinline__ void mma_slab(double (&acc)[4][4][2], const double* A
   }
 }
 
-// acc += A(128 x 16*nslab) * B(128 x 16*nslab)^T, both operands streamed slab by slab from
-// HBM/L2 with cp.async.bulk into an NSTAGE-deep mbarrier pipeline.  `it` is the running
-// slab counter (identical in all threads) that defines stage and parity.
-template <bool SAME, bool SKIP_UPPER, typename OnSlab>
+// diagonal 32x32 block of a SYRK: only the 8x8 tiles on or below the block diagonal
+__device__ __forceinline__ void mma_slab_diag(double (&acc)[4][4][2], const double* As, const WarpPos& w) {
+#pragma unroll
+  for (int kq = 0; kq < 4; ++kq) {
+    const int sw = ((kq ^ (w.g & 3)) << 2) + w.t;
+    double a[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) a[mt] = As[(32 * w.wm + 8 * mt + w.g) * KS + sw];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt <= mt; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], a[nt]);
+  }
+}
+
+// one slab of the SYRK  C(lower) += A A^T  with the 16 warps balanced over the four SM
+// sub-partitions (a warp's sub-partition is warp%4 = wm) WITHIN every slab (the slab loop has
+// a CTA barrier per slab): the owner (wm > wn) of an off-diagonal block takes k quarters 0-1,
+// the otherwise idle mirror warp (wm < wn) takes k quarters 2-3 of the same block (split-K,
+// summed by syrk_reduce), and diagonal warps skip the tiles above the diagonal.  Work per
+// sub-partition and slab: 136 DMMA instead of 256.
+__device__ __forceinline__ void syrk_slab(double (&acc)[4][4][2], const double* As, const WarpPos& w) {
+  if (w.wm > w.wn) {
+    mma_slab<0, 2>(acc, As, As, w);
+  } else if (w.wm < w.wn) {
+    const WarpPos h{w.wn, w.wm, w.g, w.t};
+    mma_slab<2, 4>(acc, As, As, h);
+  } else {
+    mma_slab_diag(acc, As, w);
+  }
+}
+
+// helpers hand their partial block to the owners through shared memory (red: 6 x 1024 doubles)
+__device__ __forceinline__ void syrk_reduce(double (&acc)[4][4][2], double* red, const WarpPos& w, int lane) {
+  __syncthreads();
+  const int hi = w.wm > w.wn ? w.wm : w.wn, lo = w.wm > w.wn ? w.wn : w.wm;
+  double* buf = red + (hi * (hi - 1) / 2 + lo) * 1024 + lane;
+  if (w.wm < w.wn) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        buf[((mt * 4 + nt) * 2 + 0) * 32] = acc[mt][nt][0];
+        buf[((mt * 4 + nt) * 2 + 1) * 32] = acc[mt][nt][1];
+      }
+  }
+  __syncthreads();
+  if (w.wm > w.wn) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[mt][nt][0] += buf[((mt * 4 + nt) * 2 + 0) * 32];
+        acc[mt][nt][1] += buf[((mt * 4 + nt) * 2 + 1) * 32];
+      }
+  }
+  __syncthreads();
+}
+
+// acc += A(128 x 16*nslab) * B(128 x 16*nslab)^T (SYRK = false) or the lower blocks of A A^T
+// (SYRK = true, one operand), streamed slab by slab from HBM/L2 with cp.async.bulk into an
+// NSTAGE-deep mbarrier pipeline.  `it` is the running slab counter (identical in all
+// threads) that defines stage and parity; `stage_elems` is the stage stride in doubles.
+template <bool SYRK, typename OnSlab>
 __device__ __forceinline__ void gemm_stream(double (&acc)[4][4][2], const double* __restrict__ gA,
                                             const double* __restrict__ gB, int nslab,
-                                            double* stages, uint64_t* full, uint32_t& it,
+                                            double* stages, int stage_elems, uint64_t* full, uint32_t& it,
                                             const WarpPos& w, OnSlab on_slab) {
   const int tid = threadIdx.x;
   auto issue = [&](int q, uint32_t cur) {
     const int st = cur % NSTAGE;
-    double* dst = stages + (size_t)st * STAGE_ELEMS;
-    mbar_expect_tx(&full[st], SAME ? SLAB_BYTES : 2 * SLAB_BYTES);
+    double* dst = stages + (size_t)st * stage_elems;
+    mbar_expect_tx(&full[st], SYRK ? SLAB_BYTES : 2 * SLAB_BYTES);
     bulk_g2s(dst, gA + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
-    if (!SAME) bulk_g2s(dst + SLAB_ELEMS, gB + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
+    if (!SYRK) bulk_g2s(dst + SLAB_ELEMS, gB + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
   };
   if (tid == 0) {
     const int pro = nslab < NSTAGE - 1 ? nslab : NSTAGE - 1;
@@ -226,10 +288,10 @@ __device__ __forceinline__ void gemm_stream(double (&acc)[4][4][2], const double
     const int st = cur % NSTAGE;
     if (tid == 0 && q + NSTAGE - 1 < nslab) issue(q + NSTAGE - 1, cur + NSTAGE - 1);
     mbar_wait(&full[st], (cur / NSTAGE) & 1);
-    const double* As = stages + (size_t)st * STAGE_ELEMS;
-    const double* Bs = SAME ? As : As + SLAB_ELEMS;
-    if (!SKIP_UPPER || w.wm >= w.wn) mma_slab(acc, As, Bs, w);
-    on_slab(Bs, q);
+    const double* As = stages + (size_t)st * stage_elems;
+    if (SYRK) syrk_slab(acc, As, w);
+    else mma_slab(acc, As, As + SLAB_ELEMS, w);
+    on_slab(As, q);
     __syncthreads();
   }
   it += nslab;
@@ -292,31 +354,51 @@ __device__ __forceinline__ void cfrag_to_afrag(double c0, double c1, double& a0,
   a1 = (lane & 1) ? v11 : v10;
 }
 
+// sqrt(x) and 1/sqrt(x) of a positive normal double: MUFU.RSQ64H seed (>= 20 bits) and two
+// coupled Newton (Goldschmidt) steps, s refined once more -> both within ~1 ulp.  This is the
+// latency-critical operation of the factorisation (one per pivot, strictly sequential).
+__device__ __forceinline__ void sqrt_rsqrt(double x, double& s, double& twice_h) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double t = x * y, h = 0.5 * y;
+  double e = fma(-t, h, 0.5);
+  t = fma(t, e, t);
+  h = fma(h, e, h);
+  e = fma(-t, h, 0.5);
+  t = fma(t, e, t);
+  h = fma(h, e, h);
+  s = fma(fma(-t, t, x), h, t);
+  twice_h = h;            // caller multiplies by 2 (folded into its own operand)
+}
+
 // warp-level Cholesky of the 32x32 block at B (stride LDP): lane r owns row r in registers.
+// Column k of L is broadcast through shared memory (lbuf, 2 x 32 doubles, double buffered: one
+// STS + wide LDS per lane instead of 31 double shuffles); the only value on the critical path,
+// the next pivot a[k+1][k+1] - l[k+1]^2, is formed in its own lane and shuffled.
 // dinv[k] = 1/L_kk.  Returns first bad pivot (global index + 1) or 0.
-__device__ __forceinline__ int potf2_32_warp(double* B, double* dinv, int lane, int base) {
+__device__ __noinline__ int potf2_32_warp(double* B, double* dinv, double* lbuf, int lane, int base) {
   double a[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? B[lane * LDP + c] : 0.0;
   int bad = 0;
+  double piv = __shfl_sync(FULLMASK, a[0], 0);
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    double piv = __shfl_sync(FULLMASK, a[k], k);
-    if (!(piv > 0.0)) {
-      if (!bad) bad = base + k + 1;
-      piv = 1.0;
-    }
-    const double inv = rsqrt(piv);
-    double dk = piv * inv;
-    dk = fma(fma(-dk, dk, piv), 0.5 * inv, dk);       // one Newton step: sqrt(piv) to <1 ulp
-    const double l = a[k] * inv;
+    const bool ok = piv > 0.0;
+    bad = (!ok && bad == 0) ? base + k + 1 : bad;
+    piv = ok ? piv : 1.0;
+    const double a2 = a[k] + a[k];
+    double dk, h;
+    sqrt_rsqrt(piv, dk, h);
+    const double l = a2 * h;                           // a[k] / sqrt(piv)
+    if (k + 1 < 32) piv = __shfl_sync(FULLMASK, fma(-l, l, a[k + 1]), k + 1);   // next pivot
+    double* lb = lbuf + (k & 1) * 32;
+    lb[lane] = l;
+    __syncwarp();
 #pragma unroll
-    for (int c = k + 1; c < 32; ++c) {
-      const double lc = __shfl_sync(FULLMASK, l, c);
-      a[c] = fma(-l, lc, a[c]);
-    }
+    for (int c = k + 1; c < 32; ++c) a[c] = fma(-l, lb[c], a[c]);
     a[k] = (lane == k) ? dk : l;
-    if (lane == k) dinv[k] = inv;
+    if (lane == k) dinv[k] = h + h;
   }
 #pragma unroll
   for (int c = 0; c < 32; ++c)
@@ -382,17 +464,20 @@ __device__ __forceinline__ void strip_trsm32(double* rows, int ld, const double*
   }
 }
 
-// trailing update after the 32-wide panel at column o:
+// trailing update after the 32-wide panel at column o (items it0 <= it < it1 of the list
+// "lower 16x16 blocks in row-major triangular order, then the RHS 8x16 blocks"), done by
+// `nw` warps of which this one is number `widx`:
 //   S[r][c]   -= sum_k S[r][o+k] * S[c][o+k]        o+32 <= c <= r      (16x16 items, lower)
 //   trow[q][c] -= sum_k trow[q][o+k] * S[c][o+k]                         (8x16 RHS items)
-__device__ __forceinline__ void trailing_update32(double* S, double* trow, int o, int warp, int lane,
-                                                  int nwarp) {
+__device__ __forceinline__ void trailing_update32(double* S, double* trow, int o, int it0, int it1,
+                                                  int widx, int nw, int lane) {
   const int g = lane >> 2, tq = lane & 3;
   const int base = o + 32;
   const int nb = (TB - base) >> 4;
   const int ntri = nb * (nb + 1) / 2;
   const int nitems = ntri + nb;
-  for (int it = warp; it < nitems; it += nwarp) {
+  if (it1 > nitems) it1 = nitems;
+  for (int it = it0 + widx; it < it1; it += nw) {
     if (it < ntri) {
       int bi = 0;
       while ((bi + 1) * (bi + 2) / 2 <= it) ++bi;
@@ -448,17 +533,22 @@ __device__ __forceinline__ void trailing_update32(double* S, double* trow, int o
 // Blocked factorisation of the tile in S with the RHS strip in trow.  On exit: S lower = L,
 // dinv[128] = 1/L_kk, W8s = sixteen 8x8 inverse diagonal blocks, trow = (L^-1 [y F])^T.
 // s_bad (shared) receives the first non-positive pivot index + 1.  All threads must call.
-__device__ void potf2_blocked(double* S, double* trow, double* dinv, double* W8s, int* s_bad) {
+// Look-ahead: of the trailing update of panel kb only the three items that touch the next
+// diagonal block are done before warp 0 starts on it; the rest runs on warps 1..15 while
+// warp 0 is inside the (strictly sequential, latency-bound) 32x32 factorisation.
+__device__ void potf2_blocked(double* S, double* trow, double* dinv, double* W8s, double* lbuf, int* s_bad) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   if (tid == 0) *s_bad = 0;
+  __syncthreads();
   for (int kb = 0; kb < 4; ++kb) {
     const int o = 32 * kb;
-    __syncthreads();
     if (warp == 0) {
-      const int b = potf2_32_warp(S + o * LDP + o, dinv + o, lane, o);
+      const int b = potf2_32_warp(S + o * LDP + o, dinv + o, lbuf, lane, o);
       __syncwarp();
       inv8_warp(S + o * LDP + o, dinv + o, W8s + kb * 256, lane);
       if (lane == 0 && b && *s_bad == 0) *s_bad = b;
+    } else if (kb > 0) {
+      trailing_update32(S, trow, o - 32, 3, 1 << 20, warp - 1, nwarp - 1, lane);
     }
     __syncthreads();
     const int nrow_strips = (TB - o - 32) >> 3;
@@ -467,9 +557,11 @@ __device__ void potf2_blocked(double* S, double* trow, double* dinv, double* W8s
       else strip_trsm32(trow + o, TLD, S + o * LDP + o, W8s + kb * 256, lane);
     }
     __syncthreads();
-    if (kb < 3) trailing_update32(S, trow, o, warp, lane, nwarp);
+    if (kb < 3) {
+      trailing_update32(S, trow, o, 0, 3, warp, nwarp, lane);
+      __syncthreads();
+    }
   }
-  __syncthreads();
 }
 
 // plain column-by-column variant (debug / KB200_FLAG_NAIVE): same outputs, DFMA only
@@ -537,32 +629,179 @@ __device__ void store_L(const double* S, double* Ltile, int nthreads) {
 }
 
 // ============================================================================ K2
-// Shared-memory map of the diagonal-tile work (also used by the panel kernel's "next
-// diagonal" role): [stages | trow 8xTLD | dinv 128 | W8s 1024 | barriers | flags]
-constexpr int DIAG_EXTRA_ELEMS = 8 * TLD + TB + 1024;
+// Diagonal-tile work shared by chol_diag_kernel and the panel kernel's "next diagonal" role.
+// Shared-memory map: [0, 132 KiB) S scratch | ... | trow 8xTLD | dinv 128 | W8 out 1024.
+struct DiagSmem {
+  double* S;       // [128][LDP] POTF2 scratch
+  double* trow;    // [8][TLD]  RHS strip
+  double* dinv;    // [128]
+  double* W8s;     // [16][64]
+  double* lbuf;    // [2][32] column broadcast buffer of potf2_32_warp
+  int* s_bad;
+  double* s_red;   // [16]
+};
+
+// fused forward substitution hook: t[r] -= L_jk[r][c] * Z_k[c]   (likelihood_func.py:183-193)
+// thread -> (row rr = tid/4, column quarter hh = tid%4) of the slab
+struct RhsHook {
+  double (&tacc)[MAXQ];
+  const double* zb;     // Z of this matrix, [nq][npad]
+  int npad, nq, rr, hh, col0;
+  __device__ __forceinline__ void operator()(const double* As, int q) const {
+    const double2* lp = reinterpret_cast<const double2*>(As + rr * KS + ((hh ^ (rr & 3)) << 2));
+    const double2 l01 = lp[0], l23 = lp[1];
+    const int col = col0 + q * KS + 4 * hh;
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      if (qq < nq) {
+        const double* z = zb + (size_t)qq * npad + col;
+        double s = tacc[qq];
+        s = fma(l01.x, z[0], s); s = fma(l01.y, z[1], s);
+        s = fma(l23.x, z[2], s); s = fma(l23.y, z[3], s);
+        tacc[qq] = s;
+      }
+    }
+  }
+};
+
+// The same hook with Z staged in shared memory: a rolling two-tile buffer zs[2][nq][128].  The
+// per-slab global loads of the plain hook sit in front of the slab barrier with their full
+// L2 latency exposed (44 % of all stall samples of the panel kernel's diagonal role, profile
+// r1e); here tile t+1 is fetched into registers at the first slab of tile t and stored to the
+// other half of the buffer at its last slab (the slab barrier publishes it).
+struct RhsHookStaged {
+  double (&tacc)[MAXQ];
+  double (&zreg)[2];
+  const double* zg;     // Z of this matrix, [nq][npad] (global)
+  double* zs;           // shared, [2][nq][128]
+  int npad, nq, rr, hh, tile0, ntile;
+  __device__ __forceinline__ void preload(int tile) const {
+    for (int idx = threadIdx.x; idx < nq * TB; idx += CH_THREADS)
+      zs[((tile & 1) * nq) * TB + idx] = zg[(size_t)(idx >> 7) * npad + tile * TB + (idx & (TB - 1))];
+  }
+  __device__ __forceinline__ void operator()(const double* As, int q) const {
+    const int tile = tile0 + (q >> 3), sq = q & 7;
+    const bool more = tile + 1 < ntile;
+    if (sq == 0 && more) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int idx = threadIdx.x + e * CH_THREADS;
+        if (idx < nq * TB) zreg[e] = zg[(size_t)(idx >> 7) * npad + (tile + 1) * TB + (idx & (TB - 1))];
+      }
+    }
+    const double2* lp = reinterpret_cast<const double2*>(As + rr * KS + ((hh ^ (rr & 3)) << 2));
+    const double2 l01 = lp[0], l23 = lp[1];
+    const double* zt = zs + ((tile & 1) * nq) * TB + sq * KS + 4 * hh;
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      if (qq < nq) {
+        const double2 z01 = *reinterpret_cast<const double2*>(zt + qq * TB);
+        const double2 z23 = *reinterpret_cast<const double2*>(zt + qq * TB + 2);
+        double s = tacc[qq];
+        s = fma(l01.x, z01.x, s); s = fma(l01.y, z01.y, s);
+        s = fma(l23.x, z23.x, s); s = fma(l23.y, z23.y, s);
+        tacc[qq] = s;
+      }
+    }
+    if (sq == 7 && more) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int idx = threadIdx.x + e * CH_THREADS;
+        if (idx < nq * TB) zs[(((tile + 1) & 1) * nq) * TB + idx] = zreg[e];
+      }
+    }
+  }
+};
+
+// From the SYRK accumulators to the finished diagonal tile jd of matrix m:
+//   S = Psi_jd,jd - acc; t = R_jd - tacc; blocked POTF2; outputs L_jd,jd (in place), the 8x8
+//   inverse blocks, Z_jd and the log-det partial.  All threads of the CTA must call.
+template <bool NAIVE>
+__device__ void diag_finish(const CholArgs& A, long m, int jd, double (&acc)[4][4][2], double (&tacc)[MAXQ],
+                            const DiagSmem& D, const WarpPos& w) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = A.nq, rr = tid >> 2, hh = tid & 3;
+  double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+  double* Cjj = tiles + (size_t)tri_index(jd, jd) * TILE_ELEMS;
+  double* S = D.S;
+  double* trow = D.trow;
+  for (int idx = tid; idx < 8 * TLD; idx += CH_THREADS) trow[idx] = 0.0;
+  __syncthreads();
+  if (w.wm >= w.wn) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
+        const double2 p = *reinterpret_cast<const double2*>(Cjj + tile_off(r, c));
+        if (c <= r) S[r * LDP + c] = p.x - acc[mt][nt][0];
+        if (c + 1 <= r) S[r * LDP + c + 1] = p.y - acc[mt][nt][1];
+      }
+  }
+  // RHS strip: t = R_jd - sum_k L_jd,k Z_k   (row q of trow)
+#pragma unroll
+  for (int qq = 0; qq < MAXQ; ++qq) {
+    if (qq < nq) {
+      double s = tacc[qq];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (hh == 0) trow[qq * TLD + rr] = A.R[(size_t)qq * A.npad + jd * TB + rr] - s;
+    }
+  }
+  __syncthreads();
+  if (NAIVE) potf2_simple(S, trow, D.dinv, D.W8s, D.s_bad, nq);
+  else potf2_blocked(S, trow, D.dinv, D.W8s, D.lbuf, D.s_bad);
+  const int bad = *D.s_bad;
+  if (tid == 0 && bad && A.info[m] == 0) A.info[m] = jd * TB + bad;
+  // ---- outputs: L_jj, the 8x8 inverse blocks, Z_j, log-det partial
+  store_L(S, Cjj, CH_THREADS);
+  {
+    double* w8 = A.W8 + ((size_t)m * A.nt + jd) * 1024;
+    for (int idx = tid; idx < 1024; idx += CH_THREADS) w8[idx] = D.W8s[idx];
+  }
+  for (int idx = tid; idx < nq * TB; idx += CH_THREADS) {
+    const int q = idx >> 7, r = idx & (TB - 1);
+    A.Z[((size_t)m * A.nq + q) * A.npad + jd * TB + r] = trow[q * TLD + r];
+  }
+  {
+    double v = (tid < TB) ? log(fabs(S[tid * LDP + tid])) : 0.0;   // padded rows are exactly 1
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) D.s_red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int i = 0; i < 4; ++i) s += D.s_red[i];
+      A.logdet[m] = (jd == 0 ? 0.0 : A.logdet[m]) + s;
+    }
+  }
+}
+
+constexpr int DIAG_EXTRA_ELEMS = 8 * TLD + TB + 1024 + 16 + 64;
 
 template <bool NAIVE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chol_diag_kernel(CholArgs A, int j) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);                 // NSTAGE*32 KiB, aliased by S
-  double* trow = stages + (size_t)NSTAGE * STAGE_ELEMS;                 // [8][TLD]
-  double* dinv = trow + 8 * TLD;                                        // [128]
-  double* W8s = dinv + TB;                                              // [16][64]
-  uint64_t* full = reinterpret_cast<uint64_t*>(W8s + 1024);
-  int* s_bad = reinterpret_cast<int*>(full + NSTAGE + 2);
-  __shared__ double s_red[CH_THREADS / 32];
+  DiagSmem D;
+  D.S = stages;
+  D.trow = stages + (size_t)NSTAGE * STAGE_ELEMS;                       // [8][TLD]
+  D.dinv = D.trow + 8 * TLD;                                            // [128]
+  D.W8s = D.dinv + TB;                                                  // [16][64]
+  D.s_red = D.W8s + 1024;                                               // [16]
+  D.lbuf = D.s_red + 16;                                                // [64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(D.lbuf + 64);
+  D.s_bad = reinterpret_cast<int*>(full + NSTAGE + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpPos w{warp & 3, warp >> 2, lane >> 2, lane & 3};
   const long m = blockIdx.x;
-  double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+  const double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
   const double* rowj = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
-  double* Cjj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
   const int nq = A.nq;
   const double* zb = A.Z + (size_t)m * A.nq * A.npad;
   init_barriers(full, NSTAGE);
-  for (int idx = tid; idx < 8 * TLD; idx += CH_THREADS) trow[idx] = 0.0;
 
   double acc[4][4][2];
   zero_acc(acc);
@@ -582,76 +821,12 @@ chol_diag_kernel(CholArgs A, int j) {
         for (int qq = 0; qq < MAXQ; ++qq)
           if (qq < nq) tacc[qq] = fma(lv, zb[(size_t)qq * A.npad + q * KS + 4 * hh + e], tacc[qq]);
       }
-  } else {
-    gemm_stream<true, true>(acc, rowj, rowj, nslab, stages, full, it, w,
-      [&](const double* Bs, int q) {
-        // fused forward substitution: t[r] -= L_jk[r][c] * Z_k[c]   (likelihood_func.py:183-193)
-        const double2* lp = reinterpret_cast<const double2*>(Bs + rr * KS + ((hh ^ (rr & 3)) << 2));
-        double2 l01 = lp[0], l23 = lp[1];
-        const int col = q * KS + 4 * hh;
-#pragma unroll
-        for (int qq = 0; qq < MAXQ; ++qq) {
-          if (qq < nq) {
-            const double* z = zb + (size_t)qq * A.npad + col;
-            double s = tacc[qq];
-            s = fma(l01.x, z[0], s); s = fma(l01.y, z[1], s);
-            s = fma(l23.x, z[2], s); s = fma(l23.y, z[3], s);
-            tacc[qq] = s;
-          }
-        }
-      });
+  } else if (nslab > 0) {
+    gemm_stream<true>(acc, rowj, rowj, nslab, stages, STAGE_ELEMS, full, it, w,
+                      RhsHook{tacc, zb, A.npad, nq, rr, hh, 0});
+    syrk_reduce(acc, stages, w, lane);
   }
-  // ---- S = Psi_jj - acc (lower warp tiles only), into the POTF2 scratch (aliases stages)
-  double* S = stages;
-  __syncthreads();
-  if (w.wm >= w.wn) {
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
-        const double2 p = *reinterpret_cast<const double2*>(Cjj + tile_off(r, c));
-        if (c <= r) S[r * LDP + c] = p.x - acc[mt][nt][0];
-        if (c + 1 <= r) S[r * LDP + c + 1] = p.y - acc[mt][nt][1];
-      }
-  }
-  // RHS strip: t = R_j - sum_k L_jk Z_k   (row q of trow)
-#pragma unroll
-  for (int qq = 0; qq < MAXQ; ++qq) {
-    if (qq < nq) {
-      double s = tacc[qq];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (hh == 0) trow[qq * TLD + rr] = A.R[(size_t)qq * A.npad + j * TB + rr] - s;
-    }
-  }
-  __syncthreads();
-  if (NAIVE) potf2_simple(S, trow, dinv, W8s, s_bad, nq);
-  else potf2_blocked(S, trow, dinv, W8s, s_bad);
-  const int bad = *s_bad;
-  if (tid == 0 && bad && A.info[m] == 0) A.info[m] = j * TB + bad;
-  // ---- outputs: L_jj, the 8x8 inverse blocks, Z_j, log-det partial
-  store_L(S, Cjj, CH_THREADS);
-  {
-    double* w8 = A.W8 + ((size_t)m * A.nt + j) * 1024;
-    for (int idx = tid; idx < 1024; idx += CH_THREADS) w8[idx] = W8s[idx];
-  }
-  for (int idx = tid; idx < nq * TB; idx += CH_THREADS) {
-    const int q = idx >> 7, r = idx & (TB - 1);
-    A.Z[((size_t)m * A.nq + q) * A.npad + j * TB + r] = trow[q * TLD + r];
-  }
-  {
-    double v = (tid < TB) ? log(fabs(S[tid * LDP + tid])) : 0.0;   // padded rows are exactly 1
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_red[warp] = v;
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int i = 0; i < 4; ++i) s += s_red[i];
-      A.logdet[m] = (j == 0 ? 0.0 : A.logdet[m]) + s;
-    }
-  }
+  diag_finish<NAIVE>(A, m, j, acc, tacc, D, w);
 }
 
 // 8x8 inverse blocks of an imported factor (predictor_load path): one CTA per tile column
@@ -679,6 +854,21 @@ w8_from_tiles_kernel(CholArgs A) {
 // re-distributed through shared memory so that each warp owns 8 complete rows (rows are
 // independent), then solved right-looking column tile by column tile: the finished 8x8 tile
 // times the 8x8 inverse block, followed by DMMA updates of the column tiles to its right.
+//
+// "Next diagonal" role (A.fuse_diag, CTA with i == j+1): once L_{j+1,j} is known the whole
+// tile row j+1 is final, so the same CTA goes on to the diagonal tile j+1: SYRK over the row
+// (tiles 0..j-1 re-streamed from L2, tile j straight from the shared-memory copy of X), then
+// diag_finish (POTF2, 8x8 inverses, Z_{j+1}, log-det).  No separate diagonal launches.
+//
+// Shared memory (doubles):  [0, 5*4096)  GEMM stages (2 slabs each); Cs/Xs = first 16384,
+//   Ws = stage 4;  SYRK stages (1 slab each) at [16384, 16384 + 5*2048);  W8s at 26624;
+//   diag extras (trow, dinv, s_red) behind it; S scratch aliases [0, 128*LDP).
+constexpr int PANEL_W8_OFF = TILE_ELEMS + NSTAGE * SLAB_ELEMS;          // 26624 doubles = 208 KiB
+constexpr int PANEL_EXTRA_OFF = PANEL_W8_OFF + 1024;
+static_assert(PANEL_W8_OFF >= NSTAGE * STAGE_ELEMS, "W8s must not overlap the GEMM stages");
+static_assert(TB * LDP <= PANEL_W8_OFF, "POTF2 scratch must end before W8s");
+static_assert(2 * MAXQ * TB <= 1024 + 8 * TLD, "staged Z tiles must fit in the W8s + trow area");
+
 template <bool NAIVE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chol_panel_kernel(CholArgs A, int j) {
@@ -686,15 +876,25 @@ chol_panel_kernel(CholArgs A, int j) {
   double* stages = reinterpret_cast<double*>(smem_raw);          // 5 x 32 KiB
   double* Cs = stages;                                           // 128 KiB (aliases stages 0..3)
   double* Ws = stages + 4 * STAGE_ELEMS;                         // 2 x 16 KiB (aliases stage 4)
-  double* W8s = stages + (size_t)NSTAGE * STAGE_ELEMS;           // [16][64]
-  uint64_t* full = reinterpret_cast<uint64_t*>(W8s + 1024);
+  double* W8s = stages + PANEL_W8_OFF;                           // [16][64]
+  DiagSmem D;
+  D.S = stages;
+  D.trow = stages + PANEL_EXTRA_OFF;
+  D.dinv = D.trow + 8 * TLD;
+  D.W8s = W8s;
+  D.s_red = D.dinv + TB;
+  D.lbuf = D.s_red + 16;
+  uint64_t* full = reinterpret_cast<uint64_t*>(D.lbuf + 64);
   uint64_t* wfull = full + NSTAGE;
+  D.s_bad = reinterpret_cast<int*>(wfull + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpPos w{warp & 3, warp >> 2, lane >> 2, lane & 3};
   const double *rowA, *rowB, *Ljj, *W8j;
   double* Cij;
   long ssq_base = 0;
+  long m = 0;
+  bool next_diag = false;
   if (A.pred_mode) {
     const long pt = blockIdx.x;
     double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
@@ -706,13 +906,14 @@ chol_panel_kernel(CholArgs A, int j) {
     ssq_base = pt * TB;
   } else {
     const int i = j + 1 + blockIdx.x;
-    const long m = blockIdx.y;
+    m = blockIdx.y;
     double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
     rowA = tiles + (size_t)tri_index(i, 0) * TILE_ELEMS;
     rowB = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
     Cij = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;
     Ljj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
     W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;
+    next_diag = A.fuse_diag && blockIdx.x == 0;
   }
   init_barriers(full, NSTAGE + 2);
 
@@ -720,7 +921,7 @@ chol_panel_kernel(CholArgs A, int j) {
   zero_acc(acc);
   uint32_t it = 0;
   if (NAIVE) gemm_naive(acc, rowA, rowB, NSLAB * j, w);
-  else gemm_stream<false, false>(acc, rowA, rowB, NSLAB * j, stages, full, it, w, NoSlabOp());
+  else gemm_stream<false>(acc, rowA, rowB, NSLAB * j, stages, STAGE_ELEMS, full, it, w, NoSlabOp());
 
   // ---- C = Psi_ij - acc  -> Cs (tile layout)
   __syncthreads();
@@ -806,7 +1007,10 @@ chol_panel_kernel(CholArgs A, int j) {
   double rs = 0.0;
 #pragma unroll
   for (int ct = 0; ct < 16; ++ct) {
-    *reinterpret_cast<double2*>(Cij + tile_off(xr, 8 * ct + 2 * tq)) = make_double2(x[ct][0], x[ct][1]);
+    const double2 xv = make_double2(x[ct][0], x[ct][1]);
+    const int off = tile_off(xr, 8 * ct + 2 * tq);
+    *reinterpret_cast<double2*>(Cij + off) = xv;
+    if (next_diag) *reinterpret_cast<double2*>(Cs + off) = xv;     // Xs: operand of the SYRK below
     rs = fma(x[ct][0], x[ct][0], rs);
     rs = fma(x[ct][1], x[ct][1], rs);
   }
@@ -818,6 +1022,40 @@ chol_panel_kernel(CholArgs A, int j) {
       *dst = (j == 0 ? 0.0 : *dst) + rs;
     }
   }
+  if (!next_diag) return;
+
+  // ================= next diagonal tile jd = j + 1 of matrix m (CTA-uniform branch)
+  const int jd = j + 1;
+  const double* zb = A.Z + (size_t)m * A.nq * A.npad;
+  zero_acc(acc);
+  double tacc[MAXQ];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) tacc[q] = 0.0;
+  const int rr = tid >> 2, hh = tid & 3;
+  fence_proxy_async();   // Ws (generic reads) is about to be overwritten by bulk copies
+  __syncthreads();       // Xs complete
+  if (NAIVE) {
+    // not used (the naive path keeps separate diagonal launches)
+  } else {
+    // Z tiles are staged in the (now free) W8s/trow area; tile 0 first
+    double zreg[2] = {0.0, 0.0};
+    double* zs = W8s;
+    const RhsHookStaged hook0{tacc, zreg, zb, zs, A.npad, A.nq, rr, hh, 0, jd};
+    hook0.preload(0);
+    __syncthreads();
+    // row jd, tiles 0..j-1: streamed; one-slab stages behind Xs
+    gemm_stream<true>(acc, rowA, rowA, NSLAB * j, stages + TILE_ELEMS, SLAB_ELEMS, full, it, w, hook0);
+    // tile j: the X just computed, read in place from shared memory
+    const RhsHookStaged hook{tacc, zreg, zb, zs, A.npad, A.nq, rr, hh, j, jd};
+#pragma unroll 1
+    for (int q = 0; q < NSLAB; ++q) {
+      const double* As = Cs + (size_t)q * SLAB_ELEMS;
+      syrk_slab(acc, As, w);
+      hook(As, q);
+    }
+    syrk_reduce(acc, stages + TILE_ELEMS, w, lane);
+  }
+  diag_finish<NAIVE>(A, m, jd, acc, tacc, D, w);
 }
 
 // ============================================================================ K4
@@ -1160,7 +1398,7 @@ static inline int cur_dev() {
   return d & 63;
 }
 constexpr size_t DIAG_SMEM = ((size_t)NSTAGE * STAGE_ELEMS + DIAG_EXTRA_ELEMS) * 8 + (NSTAGE + 2) * 8 + 16;
-constexpr size_t PANEL_SMEM = ((size_t)NSTAGE * STAGE_ELEMS + 1024) * 8 + (NSTAGE + 2) * 8;
+constexpr size_t PANEL_SMEM = ((size_t)PANEL_EXTRA_OFF + 8 * TLD + TB + 16 + 64) * 8 + (NSTAGE + 2) * 8 + 16;
 static_assert(DIAG_SMEM <= 227 * 1024 && PANEL_SMEM <= 227 * 1024, "shared memory budget");
 static_assert((size_t)TB * LDP * 8 + 16 <= (size_t)NSTAGE * STAGE_ELEMS * 8, "POTF2 scratch must fit in the stage buffers");
 
