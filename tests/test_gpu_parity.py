@@ -299,3 +299,71 @@ def test_kpls_and_composite_population(kb):
     ref3 = ko.likelihood_population(popv, copy.deepcopy(info2), True, check_pd=False)
     nll3, _ = kb.likelihood_batch(popv, info2, True)
     assert relerr(nll3, ref3) < TOL_NLL
+
+
+# ------------------------------------------------------------------ drop-in classes (BASELINE config 1)
+def _branin(X):
+    a, b, c, r, s, t = 1.0, 5.1 / (4 * np.pi ** 2), 5 / np.pi, 6.0, 10.0, 1 / (8 * np.pi)
+    x1, x2 = X[:, 0], X[:, 1]
+    return (a * (x2 - b * x1 ** 2 + c * x1 - r) ** 2 + s * (1 - t) * np.cos(x1) + s)[:, None]
+
+
+def test_krigdemo_train_and_predict_drop_in(kb):
+    """KrigDemo-equivalent (KrigDemo.py:22-118): Ordinary Kriging, Gaussian kernel, Branin 2-D,
+    50 low-discrepancy samples, L-BFGS-B with 7 restarts, predict a 100x100 grid.  The trained
+    KrigInfo is then handed to the oracle: same NLL at the optimum, same predictions."""
+    from kadal_b200 import Kriging
+    from scipy.stats import qmc
+    lb, ub = np.array([-5.0, 0.0]), np.array([10.0, 15.0])
+    X = qmc.scale(qmc.Sobol(2, scramble=False).random(51)[1:], lb, ub)
+    y = _branin(X)
+    K = {"X": X, "y": y, "lb": lb, "ub": ub, "nvar": 2, "problem": "branin", "nugget": -6,
+         "nrestart": 7, "kernel": ["gaussian"], "optimizer": "lbfgsb"}
+    model = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+    model.train(disp=False)
+    info = model.KrigInfo
+    assert model.train_stats["evals"] > model.train_stats["batches"] >= 1     # restarts ran in lock step
+    # the optimum the GPU search found is a genuine improvement over the start points' box centre
+    ref = copy.deepcopy(info)
+    nll_ref = ko.likelihood(np.array(info["Theta"], dtype=float), ref, "all", False, check_pd=False)["NegLnLike"]
+    n = X.shape[0]
+    cond = np.linalg.cond(ref["Psi"] + np.eye(n) * 1e-6)
+    assert relerr(info["NegLnLike"], nll_ref) < nll_tol(cond)
+    centre = ko.likelihood(np.zeros(2), copy.deepcopy(info), "default", False, check_pd=False)
+    assert info["NegLnLike"] <= centre + 1e-9
+    g1, g2 = np.meshgrid(np.linspace(lb[0], ub[0], 100), np.linspace(lb[1], ub[1], 100))
+    xg = np.column_stack([g1.ravel(), g2.ravel()])
+    p = model.predict(xg, ["pred", "SSqr"])
+    pr = ko.prediction(xg, ref, ["pred", "SSqr"])
+    s2 = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
+    scale = float(np.max(np.abs(y)))
+    assert np.max(np.abs(p[0] - pr[0])) / scale < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+    assert relerr(p[1].ravel(), pr[1].ravel(), 1e-6 * s2) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
+    # the surrogate interpolates the samples (nugget 1e-6)
+    assert np.max(np.abs(model.predict(X, ["pred"]) - y)) < 1e-3 * scale
+
+
+def test_kpls_class_cmaes_drop_in(kb):
+    """KPLS (kpls_model.py): PLS rotations on the host (scikit-learn, as the reference), CMA-ES
+    populations evaluated in GPU batches, prediction through the projected distances."""
+    from kadal_b200 import KPLS
+    rng = np.random.default_rng(3)
+    n, d = 150, 12
+    X = rng.uniform(-1, 1, (n, d))
+    y = (X[:, :4].sum(1) ** 2)[:, None] + 0.5 * X[:, 5:6] + 3.0
+    K = {"X": X, "y": y, "lb": -np.ones(d), "ub": np.ones(d), "nvar": d, "nugget": -6, "n_princomp": 3,
+         "nrestart": 2, "kernel": ["gaussian"], "optimizer": "cmaes"}
+    model = KPLS(K, standardization=True, standtype="default", normy=False, trainvar=False)
+    model.train(disp=False, seed=1)
+    info = model.KrigInfo
+    assert info["plscoeff"].shape == (d, 3) and info["type"] == "kpls"
+    ref = copy.deepcopy(info)
+    ko.likelihood(np.array(info["Theta"], dtype=float), ref, "all", False, check_pd=False)
+    cond = np.linalg.cond(ref["Psi"] + np.eye(n) * 1e-6)
+    assert relerr(info["NegLnLike"], ref["NegLnLike"]) < nll_tol(cond)
+    xp = rng.uniform(-1, 1, (500, d))
+    p = model.predict(xp, ["pred", "SSqr"])
+    pr = ko.prediction(xp, ref, ["pred", "SSqr"])
+    s2 = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
+    assert relerr(p[0].ravel(), pr[0].ravel()) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+    assert relerr(p[1].ravel(), pr[1].ravel(), 1e-6 * s2) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
