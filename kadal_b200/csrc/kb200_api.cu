@@ -77,6 +77,12 @@ struct kb200_model {
   DevBuf pL, pW, palpha, pw, pcand;
   double pbeta = 0, psigma2 = 0, pbtb = 0;
   PredSlot slot[2];
+  // candidate groups of one likelihood batch run on their own streams so that the tail of one
+  // group's launch (partially filled last wave, long "next diagonal" CTAs) overlaps the other's
+  static constexpr int MAXG = 4;
+  int ngroups = 2;
+  cudaStream_t gstream[MAXG] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAXG] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf norm_a, norm_b, stats;
   unsigned long long launches = 0;
   size_t ws_cap_bytes = 0;
@@ -186,6 +192,15 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
   } while (0)
   MCK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   for (int s = 0; s < 2; ++s) MCK(cudaStreamCreateWithFlags(&m->slot[s].stream, cudaStreamNonBlocking));
+  {
+    const char* eg = getenv("KB200_GROUPS");
+    if (eg) m->ngroups = std::max(1, std::min((int)kb200_model::MAXG, atoi(eg)));
+    for (int g = 0; g < m->ngroups; ++g) {
+      MCK(cudaStreamCreateWithFlags(&m->gstream[g], cudaStreamNonBlocking));
+      MCK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
+    }
+    MCK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  }
   MCK(m->X.reserve((size_t)n * d * 8));
   MCK(cudaMemcpy(m->X.p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice));
   // R = [y F]^T, zero padded: [nq][npad]
@@ -233,6 +248,11 @@ void kb200_model_destroy(kb200_model* m) {
     for (auto& o : sl.out) o.release();
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
+  for (int g = 0; g < kb200_model::MAXG; ++g) {
+    if (m->gstream[g]) cudaStreamDestroy(m->gstream[g]);
+    if (m->ev_join[g]) cudaEventDestroy(m->ev_join[g]);
+  }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -368,21 +388,36 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
   CK(cudaMemsetAsync(d_info, 0, (size_t)P * sizeof(int), st));
   for (int p0 = 0; p0 < P; p0 += Pb) {
     const int pb = std::min(Pb, P - p0);
-    const double* cand = m->cand.d() + (size_t)p0 * m->cstride;
-    rc = assemble(m, cand, pb, m->tiles.d(), 1, st);
-    if (rc) return rc;
-    rc = factorize(m, pb, m->tiles.d(), m->W.d(), m->Z.d(), m->logdet.d(), d_info + p0, st);
-    if (rc) return rc;
-    FinArgs f;
-    memset(&f, 0, sizeof(f));
-    f.Z = m->Z.d(); f.logdet = m->logdet.d(); f.info = d_info + p0;
-    f.cand = cand; f.cand_stride = m->cstride;
-    f.nq = m->nq; f.npad = m->npad; f.n = m->n;
-    f.trainvar = trainvar; f.nsamp = m->nsamp;
-    f.nll = d_nll + p0;
-    {
-      Timed t(m, KB200_PROF_FINALIZE, st);
-      CK(launch_finalize(f, pb, st));
+    const int G = pb >= 32 * m->ngroups ? m->ngroups : 1;
+    if (G > 1) CK(cudaEventRecord(m->ev_fork, st));
+    for (int g = 0; g < G; ++g) {
+      const int o0 = (int)((long)pb * g / G), o1 = (int)((long)pb * (g + 1) / G), pg = o1 - o0;
+      cudaStream_t sg = G > 1 ? m->gstream[g] : st;
+      if (G > 1) CK(cudaStreamWaitEvent(sg, m->ev_fork, 0));
+      const double* cand = m->cand.d() + (size_t)(p0 + o0) * m->cstride;
+      double* tiles = m->tiles.d() + (size_t)o0 * m->tiles_per_mat * TILE_ELEMS;
+      double* W8 = m->W.d() + (size_t)o0 * m->nt * 1024;
+      double* Z = m->Z.d() + (size_t)o0 * m->nq * m->npad;
+      double* logdet = m->logdet.d() + o0;
+      rc = assemble(m, cand, pg, tiles, 1, sg);
+      if (rc) return rc;
+      rc = factorize(m, pg, tiles, W8, Z, logdet, d_info + p0 + o0, sg);
+      if (rc) return rc;
+      FinArgs f;
+      memset(&f, 0, sizeof(f));
+      f.Z = Z; f.logdet = logdet; f.info = d_info + p0 + o0;
+      f.cand = cand; f.cand_stride = m->cstride;
+      f.nq = m->nq; f.npad = m->npad; f.n = m->n;
+      f.trainvar = trainvar; f.nsamp = m->nsamp;
+      f.nll = d_nll + p0 + o0;
+      {
+        Timed t(m, KB200_PROF_FINALIZE, sg);
+        CK(launch_finalize(f, pg, sg));
+      }
+      if (G > 1) {
+        CK(cudaEventRecord(m->ev_join[g], sg));
+        CK(cudaStreamWaitEvent(st, m->ev_join[g], 0));
+      }
     }
   }
   return 0;

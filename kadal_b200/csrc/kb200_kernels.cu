@@ -264,35 +264,45 @@ __device__ __forceinline__ void syrk_reduce(double (&acc)[4][4][2], double* red,
 
 // acc += A(128 x 16*nslab) * B(128 x 16*nslab)^T (SYRK = false) or the lower blocks of A A^T
 // (SYRK = true, one operand), streamed slab by slab from HBM/L2 with cp.async.bulk into an
-// NSTAGE-deep mbarrier pipeline.  `it` is the running slab counter (identical in all
-// threads) that defines stage and parity; `stage_elems` is the stage stride in doubles.
+// NSTAGE-deep ring.  full[st] (tx-count mbarrier) says "slab landed"; empty[st] (16 arrivals,
+// one per warp) says "every warp is done with it", so there is NO CTA-wide barrier per slab:
+// warps drift freely and the producer (thread 0) refills a stage two slabs after it was
+// consumed, when its empty barrier has normally completed already.  `it` is the running slab
+// counter (identical in all threads) that defines stage and parity; `stage_elems` is the stage
+// stride in doubles.  Callers must __syncthreads() before reusing the stage memory.
+constexpr int LOOKAHEAD = NSTAGE - 2;
 template <bool SYRK, typename OnSlab>
 __device__ __forceinline__ void gemm_stream(double (&acc)[4][4][2], const double* __restrict__ gA,
                                             const double* __restrict__ gB, int nslab,
                                             double* stages, int stage_elems, uint64_t* full, uint32_t& it,
                                             const WarpPos& w, OnSlab on_slab) {
   const int tid = threadIdx.x;
+  uint64_t* empty = full + NSTAGE + 2;
   auto issue = [&](int q, uint32_t cur) {
     const int st = cur % NSTAGE;
+    const uint32_t use = cur / NSTAGE;
+    if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
     double* dst = stages + (size_t)st * stage_elems;
     mbar_expect_tx(&full[st], SYRK ? SLAB_BYTES : 2 * SLAB_BYTES);
     bulk_g2s(dst, gA + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
     if (!SYRK) bulk_g2s(dst + SLAB_ELEMS, gB + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
   };
   if (tid == 0) {
-    const int pro = nslab < NSTAGE - 1 ? nslab : NSTAGE - 1;
+    const int pro = nslab < LOOKAHEAD ? nslab : LOOKAHEAD;
     for (int q = 0; q < pro; ++q) issue(q, it + q);
   }
   for (int q = 0; q < nslab; ++q) {
     const uint32_t cur = it + q;
     const int st = cur % NSTAGE;
-    if (tid == 0 && q + NSTAGE - 1 < nslab) issue(q + NSTAGE - 1, cur + NSTAGE - 1);
+    if (tid == 0 && q + LOOKAHEAD < nslab) issue(q + LOOKAHEAD, cur + LOOKAHEAD);
     mbar_wait(&full[st], (cur / NSTAGE) & 1);
     const double* As = stages + (size_t)st * stage_elems;
     if (SYRK) syrk_slab(acc, As, w);
     else mma_slab(acc, As, As + SLAB_ELEMS, w);
     on_slab(As, q);
-    __syncthreads();
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+    if (SYRK && (q & 7) == 7) __syncthreads();   // tile boundary: publishes the staged Z tile
   }
   it += nslab;
 }
@@ -301,9 +311,13 @@ struct NoSlabOp {
   __device__ __forceinline__ void operator()(const double*, int) const {}
 };
 
-__device__ __forceinline__ void init_barriers(uint64_t* bars, int nbar) {
+// barrier block: full[NSTAGE] + wfull[2] (one arrival + tx bytes), then empty[NSTAGE] (one
+// arrival per warp)
+constexpr int NBARRIERS = 2 * NSTAGE + 2;
+__device__ __forceinline__ void init_barriers(uint64_t* bars) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nbar; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < NSTAGE + 2; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < NSTAGE; ++i) mbar_init(&bars[NSTAGE + 2 + i], CH_THREADS / 32);
     fence_mbar_init();
   }
   __syncthreads();
@@ -792,7 +806,7 @@ chol_diag_kernel(CholArgs A, int j) {
   D.s_red = D.W8s + 1024;                                               // [16]
   D.lbuf = D.s_red + 16;                                                // [64]
   uint64_t* full = reinterpret_cast<uint64_t*>(D.lbuf + 64);
-  D.s_bad = reinterpret_cast<int*>(full + NSTAGE + 2);
+  D.s_bad = reinterpret_cast<int*>(full + NBARRIERS);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpPos w{warp & 3, warp >> 2, lane >> 2, lane & 3};
@@ -801,7 +815,7 @@ chol_diag_kernel(CholArgs A, int j) {
   const double* rowj = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
   const int nq = A.nq;
   const double* zb = A.Z + (size_t)m * A.nq * A.npad;
-  init_barriers(full, NSTAGE);
+  init_barriers(full);
 
   double acc[4][4][2];
   zero_acc(acc);
@@ -886,7 +900,7 @@ chol_panel_kernel(CholArgs A, int j) {
   D.lbuf = D.s_red + 16;
   uint64_t* full = reinterpret_cast<uint64_t*>(D.lbuf + 64);
   uint64_t* wfull = full + NSTAGE;
-  D.s_bad = reinterpret_cast<int*>(wfull + 2);
+  D.s_bad = reinterpret_cast<int*>(full + NBARRIERS);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpPos w{warp & 3, warp >> 2, lane >> 2, lane & 3};
@@ -915,7 +929,7 @@ chol_panel_kernel(CholArgs A, int j) {
     W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;
     next_diag = A.fuse_diag && blockIdx.x == 0;
   }
-  init_barriers(full, NSTAGE + 2);
+  init_barriers(full);
 
   double acc[4][4][2];
   zero_acc(acc);
@@ -1397,8 +1411,8 @@ static inline int cur_dev() {
   cudaGetDevice(&d);
   return d & 63;
 }
-constexpr size_t DIAG_SMEM = ((size_t)NSTAGE * STAGE_ELEMS + DIAG_EXTRA_ELEMS) * 8 + (NSTAGE + 2) * 8 + 16;
-constexpr size_t PANEL_SMEM = ((size_t)PANEL_EXTRA_OFF + 8 * TLD + TB + 16 + 64) * 8 + (NSTAGE + 2) * 8 + 16;
+constexpr size_t DIAG_SMEM = ((size_t)NSTAGE * STAGE_ELEMS + DIAG_EXTRA_ELEMS) * 8 + NBARRIERS * 8 + 16;
+constexpr size_t PANEL_SMEM = ((size_t)PANEL_EXTRA_OFF + 8 * TLD + TB + 16 + 64) * 8 + NBARRIERS * 8 + 16;
 static_assert(DIAG_SMEM <= 227 * 1024 && PANEL_SMEM <= 227 * 1024, "shared memory budget");
 static_assert((size_t)TB * LDP * 8 + 16 <= (size_t)NSTAGE * STAGE_ELEMS * 8, "POTF2 scratch must fit in the stage buffers");
 
