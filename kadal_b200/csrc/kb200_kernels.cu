@@ -25,6 +25,9 @@ namespace kb200 {
 // (prediction).  256 threads; lane -> (row = lane/4, 32-byte chunk = lane%4), so a warp
 // writes 8 consecutive 128-byte lines of a slab (1 KiB contiguous).
 constexpr int CORR_THREADS = 256;
+#ifndef KB200_CORR_FAST_BLOCKS
+#define KB200_CORR_FAST_BLOCKS 3
+#endif
 
 __device__ __forceinline__ double standardize1(double x, int normtype, double a, double b) {
   if (normtype == 1) {  // 'default': ((x-lb)/(ub-lb) - 0.5) * 2   samplingplan.py:77-83
@@ -35,13 +38,16 @@ __device__ __forceinline__ double standardize1(double x, int normtype, double a,
   return x;
 }
 
-__global__ void __launch_bounds__(CORR_THREADS)
+template <bool FAST>
+__global__ void __launch_bounds__(CORR_THREADS, FAST ? KB200_CORR_FAST_BLOCKS : 2)
 corr_tile_kernel(CorrArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int d = A.spec.d;
   const int lda = d | 1;
   double* As = reinterpret_cast<double*>(smem_raw);          // [128][lda]
   double* Bt = As + ((TB * lda + 1) & ~1);                   // [d][128]
+  double* th2 = Bt + d * TB;                                 // [d] theta^2, then [d] RN(1/theta^2)
+  constexpr bool fast = FAST;   // one Gaussian kernel, non-KPLS (chosen by the launcher)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, ch = lane & 3;
 
@@ -63,6 +69,8 @@ corr_tile_kernel(CorrArgs A) {
     m = 0;
   }
   const double* cand = A.cand + m * A.cand_stride;
+  if (fast && tid < 2 * d) th2[tid] = cand[2 * A.spec.ntheta + tid];   // theta2 | rtheta2 are adjacent
+  const double w0 = cand[4 * A.spec.ntheta];
 
   // ---- row coordinates -> As
   if (A.mode == CORR_ASSEMBLE) {
@@ -117,7 +125,10 @@ corr_tile_kernel(CorrArgs A) {
         } else {
           if (gc0 >= A.n) need = false;
         }
-        if (need) q = corr_quad(A.spec, cand, As + row * lda, Bt + c0, TB);
+        if (need) {
+          if (FAST) q = corr_quad_gauss(d, th2, th2 + d, w0, As + row * lda, Bt + c0, TB);
+          else q = corr_quad(A.spec, cand, As + row * lda, Bt + c0, TB);
+        }
         else q = quad_set(0.0);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -387,17 +398,18 @@ __device__ __forceinline__ void sqrt_rsqrt(double x, double& s, double& twice_h)
 
 // warp-level Cholesky of the 32x32 block at B (stride LDP): lane r owns row r in registers.
 // Column k of L is broadcast through shared memory (lbuf, 2 x 32 doubles, double buffered: one
-// STS + wide LDS per lane instead of 31 double shuffles); the only value on the critical path,
-// the next pivot a[k+1][k+1] - l[k+1]^2, is formed in its own lane and shuffled.
+// STS + wide LDS per lane instead of 31 double shuffles: 2x faster, tools/microbench).  A lone
+// warp retires roughly one FP64 instruction per 8 cycles here, so the step cost follows the
+// instruction count (variants with a shorter dependency chain but more arithmetic were slower).
 // dinv[k] = 1/L_kk.  Returns first bad pivot (global index + 1) or 0.
 __device__ __noinline__ int potf2_32_warp(double* B, double* dinv, double* lbuf, int lane, int base) {
   double a[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? B[lane * LDP + c] : 0.0;
   int bad = 0;
-  double piv = __shfl_sync(FULLMASK, a[0], 0);
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
+    double piv = __shfl_sync(FULLMASK, a[k], k);
     const bool ok = piv > 0.0;
     bad = (!ok && bad == 0) ? base + k + 1 : bad;
     piv = ok ? piv : 1.0;
@@ -405,7 +417,6 @@ __device__ __noinline__ int potf2_32_warp(double* B, double* dinv, double* lbuf,
     double dk, h;
     sqrt_rsqrt(piv, dk, h);
     const double l = a2 * h;                           // a[k] / sqrt(piv)
-    if (k + 1 < 32) piv = __shfl_sync(FULLMASK, fma(-l, l, a[k + 1]), k + 1);   // next pivot
     double* lb = lbuf + (k & 1) * 32;
     lb[lane] = l;
     __syncwarp();
@@ -930,6 +941,12 @@ chol_panel_kernel(CholArgs A, int j) {
     next_diag = A.fuse_diag && blockIdx.x == 0;
   }
   init_barriers(full);
+  if (j > 0) {
+    // the C tile is needed only after the GEMM phase: pull it into L2 now (2 lines per thread)
+    const char* cp = reinterpret_cast<const char*>(Cij) + (size_t)tid * 256;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(cp));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + 128));
+  }
 
   double acc[4][4][2];
   zero_acc(acc);
@@ -948,7 +965,8 @@ chol_panel_kernel(CholArgs A, int j) {
       const double2 p = *reinterpret_cast<const double2*>(Cij + off);
       *reinterpret_cast<double2*>(Cs + off) = make_double2(p.x - acc[mt][nt][0], p.y - acc[mt][nt][1]);
     }
-  fence_proxy_async();   // Ws region was last written by the async proxy; order generic accesses
+  // (Ws / W8s are refilled by bulk copies after generic-proxy READS only: the CTA barrier below
+  //  orders them, as in any TMA ring; no generic-proxy write is ever read by the async proxy)
   __syncthreads();
 
   if (NAIVE) {
@@ -1046,7 +1064,6 @@ chol_panel_kernel(CholArgs A, int j) {
 #pragma unroll
   for (int q = 0; q < MAXQ; ++q) tacc[q] = 0.0;
   const int rr = tid >> 2, hh = tid & 3;
-  fence_proxy_async();   // Ws (generic reads) is about to be overwritten by bulk copies
   __syncthreads();       // Xs complete
   if (NAIVE) {
     // not used (the naive path keeps separate diagonal launches)
@@ -1394,7 +1411,7 @@ __global__ void predict_epilogue_kernel(EpiArgs A) {
 // ====================================================================== launchers
 static inline size_t corr_smem_bytes(int d) {
   const int lda = d | 1;
-  return (size_t)(((TB * lda + 1) & ~1) + d * TB) * sizeof(double);
+  return (size_t)(((TB * lda + 1) & ~1) + d * TB + 2 * d) * sizeof(double);
 }
 
 #define KB_LAUNCH_CHECK()                          \
@@ -1421,11 +1438,16 @@ cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t 
   if (sm > 227 * 1024) return cudaErrorInvalidValue;
   const int dev = cur_dev();
   if (sm > g_corr_attr[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(corr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm > 48 * 1024 ? sm : 48 * 1024));
+    const int want = (int)(sm > 48 * 1024 ? sm : 48 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(corr_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(corr_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) return e;
     g_corr_attr[dev] = sm;
   }
-  corr_tile_kernel<<<dim3(grid_x, grid_y), CORR_THREADS, sm, st>>>(a);
+  const bool fast = a.spec.nkernel == 1 && a.spec.kid[0] == K_GAUSS && !a.spec.kpls;
+  if (fast) corr_tile_kernel<true><<<dim3(grid_x, grid_y), CORR_THREADS, sm, st>>>(a);
+  else corr_tile_kernel<false><<<dim3(grid_x, grid_y), CORR_THREADS, sm, st>>>(a);
   KB_LAUNCH_CHECK();
   return cudaSuccess;
 }
