@@ -128,6 +128,11 @@ int kb200_debug_psi(kb200_model* m, const double* x, int nbhyp, int trainvar,
 int kb200_profile_enable(kb200_model* m, int on);
 int kb200_profile_get(kb200_model* m, double* ms, unsigned long long* counts, int reset);
 
+/* Number of candidate groups (1..4, default 2 or $KB200_GROUPS) a likelihood batch is split into;
+ * every group runs its launch sequence on its own stream so that launch tails overlap.  With 1
+ * all kernels are serialised on the caller's stream (what the per-kernel profile wants). */
+int kb200_set_groups(kb200_model* m, int ngroups);
+
 /* Empirical FP64 roof of the device: register-resident DMMA (mode 0) or DFMA (mode 1)
  * loops, best of 5, in TFLOP/s. */
 int kb200_fp64_probe(int device, int mode, double* tflops);

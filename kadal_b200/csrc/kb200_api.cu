@@ -816,6 +816,18 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
 
 extern "C" {
 
+int kb200_set_groups(kb200_model* m, int ngroups) {
+  if (!m) return fail_arg("null model");
+  if (ngroups < 1 || ngroups > kb200_model::MAXG) return fail_arg("kb200_set_groups: 1..4 groups");
+  CK(cudaSetDevice(m->device));
+  for (int g = 0; g < ngroups; ++g) {
+    if (!m->gstream[g]) CK(cudaStreamCreateWithFlags(&m->gstream[g], cudaStreamNonBlocking));
+    if (!m->ev_join[g]) CK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
+  }
+  m->ngroups = ngroups;
+  return 0;
+}
+
 int kb200_profile_enable(kb200_model* m, int on) {
   if (!m) return fail_arg("null model");
   m->prof_on = on != 0;

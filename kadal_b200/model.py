@@ -173,6 +173,10 @@ class GpuModel:
                                          int(bool(limit_ge)), *ptrs, stats, c_void_p(stream)))
         return (int(stats[0]), int(stats[1])) if want_stats else None
 
+    def set_groups(self, ngroups):
+        """Number of candidate groups (streams) of a likelihood batch; 1 serialises the kernels."""
+        check(self.lib.kb200_set_groups(self.handle, int(ngroups)))
+
     def profile(self, on):
         check(self.lib.kb200_profile_enable(self.handle, int(bool(on))))
 
