@@ -99,47 +99,57 @@ def predict_flops_per_point(n, d, var=True, c_exp=20):
 
 # ------------------------------------------------------------------ clocks sampler
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed region: NVML polled from a thread every
+    10 ms (nvidia-smi -lms needs ~1 s to start, longer than the timed region); nvidia-smi once as a
+    fallback."""
+    NAMES = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.t, self.stop_flag, self.h = index, [], None, False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, mx, pw, rs))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+            time.sleep(0.01)
+
+    def stop(self):
+        if self.h is None:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,power.draw",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                sm, mx, pw = [float(v) for v in out.strip().split(",")]
+                return {"sm_mhz": sm, "sm_max_mhz": mx, "power_w_max": pw, "samples": 1, "reasons": [],
+                        "note": "NVML unavailable: one nvidia-smi sample after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        sm = [r[0] for r in self.rows]
+        reasons = sorted(nm for nm, bit in self.NAMES.items() if any(r[3] & bit for r in self.rows))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[1] for r in self.rows) if sm else None,
+                "power_w_max": max(r[2] for r in self.rows) if sm else None, "samples": len(sm), "reasons": reasons}
 
 
 def measured_peaks():
@@ -246,12 +256,12 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     warm = max(args.warmup, 3)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()          # nvidia-smi needs ~1 s to start sampling: begin before the warm-up
     for _ in range(warm):
         step()
     barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # NVML poll thread: samples only while the timed steps run
     launches0 = model.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

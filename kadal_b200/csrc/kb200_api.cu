@@ -65,6 +65,7 @@ struct kb200_model {
   long tiles_per_mat = 0;
   double nsamp = 0;
   int flags = 0;
+  int sm_count = 148;
   int kid[MAXK];
   int cstride = 0;
   std::vector<double> hy, hF;
@@ -190,6 +191,7 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
       return rc;                       \
     }                                  \
   } while (0)
+  MCK(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
   MCK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   for (int s = 0; s < 2; ++s) MCK(cudaStreamCreateWithFlags(&m->slot[s].stream, cudaStreamNonBlocking));
   {
@@ -685,6 +687,27 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     {
       Timed t(m, KB200_PROF_EPILOGUE, st);
       CK(launch_epilogue(e, st));
+    }
+    return 0;
+  }
+  // small models: everything in one fused kernel, nothing of size n x npred in HBM
+  static const bool no_fused = getenv("KB200_NO_FUSED_PREDICT") != nullptr;
+  if (!no_fused && !(m->flags & KB200_FLAG_NAIVE) &&
+      predict_small_supported(m->n, m->d, m->nkernel, m->kid[0], m->h > 0 ? 1 : 0)) {
+    PredSmallArgs ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.n = m->n; ps.d = m->d; ps.nt = m->nt; ps.ntheta = m->ntheta;
+    ps.X = m->X.d(); ps.cand = m->pcand.d(); ps.L = m->pL.d(); ps.W8 = m->pW.d();
+    ps.alpha = m->palpha.d(); ps.wvec = m->pw.d();
+    ps.xpts = d_x; ps.npts = npts; ps.normtype = normtype;
+    ps.norm_a = m->norm_a.d(); ps.norm_b = m->norm_b.d();
+    ps.epi = e;
+    ps.epi.npts = npts;
+    ps.epi.pred = outs[0]; ps.epi.ssqr = outs[1]; ps.epi.s = outs[2]; ps.epi.ei = outs[3];
+    ps.epi.poi = outs[4]; ps.epi.pof = outs[5]; ps.epi.ufun = outs[6];
+    {
+      Timed t(m, KB200_PROF_PREDSOLVE, st);
+      CK(launch_predict_small(ps, m->sm_count, st));
     }
     return 0;
   }

@@ -1379,43 +1379,288 @@ __global__ void add_diag_kernel(double* tiles, int n, const double* eps_ptr) {
 // ======================================================================= epilogue
 // prediction.py:233-235 (mean), :245-251 (SSqr, s), :258-310 (acquisition values),
 // akmcs.py:281-285 (U-function)
-__global__ void predict_epilogue_kernel(EpiArgs A) {
+__device__ __forceinline__ void epilogue_point(const EpiArgs& A, long i, double fdot, double udot, double ssq,
+                                               long& zero_ss, int& any) {
   const double tiny = 2.2250738585072014e-308;
   const double RSQ2 = 0.7071067811865475;        // 1/np.sqrt(2)
   const double SQ2PI = 2.5066282746310002;       // np.sqrt(2*np.pi)
+  const double f = A.beta + fdot;
+  if (A.pred) A.pred[i] = f;
+  if (!A.need_var) return;
+  const double u = udot - 1.0;
+  const double term1 = 1.0 - ssq;
+  const double term2 = u * (u / A.btb);
+  const double ssqr = A.sigma2 * (term1 + term2);
+  const double s = sqrt(fabs(ssqr));
+  if (A.ssqr) A.ssqr[i] = ssqr;
+  if (A.s) A.s[i] = s;
+  if (ssqr == 0.0) ++zero_ss;
+  if (A.ei) {
+    const double dlt = A.ymin - f;
+    const double t1 = dlt * (0.5 + 0.5 * erf(RSQ2 * dlt / s));
+    const double t2 = s / SQ2PI * exp(-0.5 * (dlt * dlt) / ssqr);
+    if (t1 != 0.0 || t2 != 0.0) any = 1;
+    A.ei[i] = -(t1 + t2 + tiny);
+  }
+  if (A.poi) A.poi[i] = -(0.5 + 0.5 * erf(RSQ2 * (A.ymin - f) / s));
+  if (A.pof) {
+    const double z = A.limit_ge ? (f - A.limit) / s : (A.limit - f) / s;
+    A.pof[i] = 0.5 + 0.5 * erf(RSQ2 * z);
+  }
+  if (A.ufun) A.ufun[i] = fabs(f) / s;
+}
+
+__global__ void predict_epilogue_kernel(EpiArgs A) {
   long zero_ss = 0;
   int any = 0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.npts; i += (long)gridDim.x * blockDim.x) {
-    const double f = A.beta + A.fdot[i];
-    if (A.pred) A.pred[i] = f;
-    if (!A.need_var) continue;
-    const double u = A.udot[i] - 1.0;
-    const double term1 = 1.0 - A.ssq[i];
-    const double term2 = u * (u / A.btb);
-    const double ssqr = A.sigma2 * (term1 + term2);
-    const double s = sqrt(fabs(ssqr));
-    if (A.ssqr) A.ssqr[i] = ssqr;
-    if (A.s) A.s[i] = s;
-    if (ssqr == 0.0) ++zero_ss;
-    if (A.ei) {
-      const double dlt = A.ymin - f;
-      const double t1 = dlt * (0.5 + 0.5 * erf(RSQ2 * dlt / s));
-      const double t2 = s / SQ2PI * exp(-0.5 * (dlt * dlt) / ssqr);
-      if (t1 != 0.0 || t2 != 0.0) any = 1;
-      A.ei[i] = -(t1 + t2 + tiny);
-    }
-    if (A.poi) A.poi[i] = -(0.5 + 0.5 * erf(RSQ2 * (A.ymin - f) / s));
-    if (A.pof) {
-      const double z = A.limit_ge ? (f - A.limit) / s : (A.limit - f) / s;
-      A.pof[i] = 0.5 + 0.5 * erf(RSQ2 * z);
-    }
-    if (A.ufun) A.ufun[i] = fabs(f) / s;
-  }
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.npts; i += (long)gridDim.x * blockDim.x)
+    epilogue_point(A, i, A.fdot[i], A.need_var ? A.udot[i] : 0.0, A.need_var ? A.ssq[i] : 0.0, zero_ss, any);
   if (A.stats) {
     if (zero_ss) atomicAdd(reinterpret_cast<unsigned long long*>(A.stats), (unsigned long long)zero_ss);
     if (any) atomicOr(reinterpret_cast<unsigned long long*>(A.stats + 1), 1ull);
   }
 }
+
+// ================================================================ fused small-n predictor
+// n <= 256 (one or two sample tiles), one Gaussian kernel, d <= 8: the whole of
+// prediction.py:159-251 for 128 points per CTA pass in ONE kernel -- standardise, psi in
+// DMMA C-fragment layout straight into registers (each warp owns 8 points), psi^T alpha and
+// psi^T w, right-looking DMMA TRSM against L_00, DMMA GEMM against L_10 with V_0 as the A
+// operand from shared memory, TRSM against L_11, ||v||^2 and the epilogue.  Nothing of size
+// n x npred touches HBM (the general path writes the psi chunk and re-reads it per tile
+// column: 29 GB per 4e6 points at n = 200).  The factor slabs stream from L2 through a 3-stage
+// cp.async.bulk ring shared by the 16 warps; the schedule runs ahead across point tiles.
+constexpr int PS_VLD = TB + 4;
+constexpr int PS_NST = 3;
+constexpr int PS_LOOK = 2;
+constexpr int PS_MAXD = 8;
+
+// sum_k (a_k - b_k)^2 / theta_k^2 for two neighbouring samples, numpy's order for d <= 8
+__device__ __forceinline__ void gauss_pair_sum(int d, const double* th2, const double* a, const double* bt2,
+                                               double& S0, double& S1) {
+  auto term = [&](int k, double& t0, double& t1) {
+    const double ak = a[k];
+    const double2 b = *reinterpret_cast<const double2*>(bt2 + k * 256);
+    const double t2 = th2[k], r2 = th2[PS_MAXD + k];
+    const double d0 = __dsub_rn(ak, b.x), d1 = __dsub_rn(ak, b.y);
+    t0 = div_by_rcp(__dmul_rn(d0, d0), t2, r2);
+    t1 = div_by_rcp(__dmul_rn(d1, d1), t2, r2);
+  };
+  if (d < 8) {
+    S0 = 0.0; S1 = 0.0;
+    for (int k = 0; k < d; ++k) {
+      double t0, t1;
+      term(k, t0, t1);
+      S0 = __dadd_rn(S0, t0);
+      S1 = __dadd_rn(S1, t1);
+    }
+  } else {   // d == 8: ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+    double p[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) term(k, p[k], q[k]);
+    S0 = __dadd_rn(__dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])), __dadd_rn(__dadd_rn(p[4], p[5]), __dadd_rn(p[6], p[7])));
+    S1 = __dadd_rn(__dadd_rn(__dadd_rn(q[0], q[1]), __dadd_rn(q[2], q[3])), __dadd_rn(__dadd_rn(q[4], q[5]), __dadd_rn(q[6], q[7])));
+  }
+}
+
+// right-looking TRSM of an 8-row strip (C fragments x) against a diagonal tile of which only the
+// first `nslab` slabs matter; its slabs arrive as ring entries seq0 + s.  The column bound NCT
+// is compile time on purpose: with a run-time column bound x[] drops out of the register file
+// (272 bytes of stack, 85 M local-memory wavefronts in profile r1i).
+template <int NCT, typename Acquire, typename Release>
+__device__ __forceinline__ void trsm_strip(double (&x)[16][2], int seq0, int nslab, const double* W8, int lane,
+                                           Acquire acquire, Release release) {
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int s = 0; s < NCT / 2; ++s) {
+    if (s >= nslab) break;               // trailing slabs hold identity padding only
+    const double* Ls = acquire(seq0 + s);
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt) {
+      const int t = 2 * s + tt;
+      double a0, a1;
+      cfrag_to_afrag(x[t][0], x[t][1], a0, a1, lane);
+      double y0 = 0.0, y1 = 0.0;
+      dmma884(y0, y1, a0, W8[t * 64 + g * 8 + tq]);
+      dmma884(y0, y1, a1, W8[t * 64 + g * 8 + 4 + tq]);
+      x[t][0] = y0;
+      x[t][1] = y1;
+      if (t < NCT - 1) {
+        cfrag_to_afrag(y0, y1, a0, a1, lane);
+        a0 = -a0;
+        a1 = -a1;
+#pragma unroll
+        for (int ct = t + 1; ct < NCT; ++ct) {
+          const double* lrow = Ls + (8 * ct + g) * KS + tq;
+          dmma884(x[ct][0], x[ct][1], a0, lrow[((2 * tt) ^ (g & 3)) << 2]);
+          dmma884(x[ct][0], x[ct][1], a1, lrow[((2 * tt + 1) ^ (g & 3)) << 2]);
+        }
+      }
+    }
+    release(seq0 + s);
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+predict_small_kernel(PredSmallArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int d = A.d, lda = d | 1, n = A.n, nt = A.nt;
+  double* Vs = reinterpret_cast<double*>(smem_raw);              // [128][PS_VLD]  V_0 = L_00^-1 psi_0
+  double* stages = Vs + TB * PS_VLD;                             // PS_NST slabs
+  double* W8s = stages + PS_NST * SLAB_ELEMS;                    // [2][1024]
+  double* Bt = W8s + 2048;                                       // [d][256] samples, transposed, zero padded
+  double* alph = Bt + PS_MAXD * 256;                             // [256]
+  double* wv = alph + 256;                                       // [256]
+  double* th2 = wv + 256;                                        // [PS_MAXD] theta^2 | [PS_MAXD] 1/theta^2
+  double* As = th2 + 2 * PS_MAXD;                                // [128][lda] standardised points
+  uint64_t* full = reinterpret_cast<uint64_t*>(As + TB * (PS_MAXD + 1));
+  uint64_t* empty = full + PS_NST;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+  const int row = 8 * warp + g;
+  const int ntiles = (int)((A.npts + TB - 1) / TB);
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nct1 = nt == 2 ? (n - TB + 7) >> 3 : 0;              // valid 8-column tiles of sample tile 1
+  const int ns1 = (nct1 + 1) >> 1;                               // slabs of L_11 that matter
+  const int NS = nt == 2 ? 16 + ns1 : 8;                         // slabs per point tile
+  const int total = my_tiles * NS;
+
+  if (tid == 0) {
+    for (int i = 0; i < PS_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CH_THREADS / 32); }
+    fence_mbar_init();
+  }
+  for (int idx = tid; idx < nt * 1024; idx += CH_THREADS) W8s[idx] = A.W8[idx];
+  for (int idx = tid; idx < d * 256; idx += CH_THREADS) {
+    const int k = idx >> 8, c = idx & 255;
+    Bt[idx] = c < n ? A.X[(size_t)c * d + k] : 0.0;
+  }
+  for (int idx = tid; idx < 256; idx += CH_THREADS) {
+    alph[idx] = idx < nt * TB ? A.alpha[idx] : 0.0;
+    wv[idx] = idx < nt * TB ? A.wvec[idx] : 0.0;
+  }
+  if (tid < d) { th2[tid] = A.cand[2 * A.ntheta + tid]; th2[PS_MAXD + tid] = A.cand[3 * A.ntheta + tid]; }
+  const double w0 = A.cand[4 * A.ntheta];
+  __syncthreads();
+
+  auto issue = [&](int seq) {          // thread 0 only
+    const int i = seq % NS, st = seq % PS_NST;
+    const int use = seq / PS_NST;
+    if (use > 0) mbar_wait(&empty[st], (uint32_t)((use - 1) & 1));
+    const double* src = i < 8 ? A.L + (size_t)i * SLAB_ELEMS
+                      : i < 16 ? A.L + (size_t)TILE_ELEMS + (size_t)(i - 8) * SLAB_ELEMS
+                               : A.L + (size_t)2 * TILE_ELEMS + (size_t)(i - 16) * SLAB_ELEMS;
+    mbar_expect_tx(&full[st], SLAB_BYTES);
+    bulk_g2s(stages + (size_t)st * SLAB_ELEMS, src, SLAB_BYTES, &full[st]);
+  };
+  auto acquire = [&](int seq) -> const double* {
+    if (tid == 0 && seq + PS_LOOK < total) issue(seq + PS_LOOK);
+    const int st = seq % PS_NST;
+    mbar_wait(&full[st], (uint32_t)((seq / PS_NST) & 1));
+    return stages + (size_t)st * SLAB_ELEMS;
+  };
+  auto release = [&](int seq) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[seq % PS_NST]);
+  };
+  if (tid == 0)
+    for (int q = 0; q < PS_LOOK && q < total; ++q) issue(q);
+
+  // psi of sample tile `tile` for this thread's row: columns 8 ct + 2 tq (+1), ct < nct
+  double x[16][2];
+  double fa, ua;
+  auto psi_tile = [&](int tile, int nct) {
+    const double* arow = As + row * lda;
+#pragma unroll
+    for (int ct = 0; ct < 16; ++ct) {
+      double e0 = 0.0, e1 = 0.0;
+      if (ct < nct) {
+        const int col = TB * tile + 8 * ct + 2 * tq;
+        double S0, S1;
+        gauss_pair_sum(d, th2, arow, Bt + col, S0, S1);
+        e0 = col < n ? __dmul_rn(w0, exp(-0.5 * S0)) : 0.0;
+        e1 = col + 1 < n ? __dmul_rn(w0, exp(-0.5 * S1)) : 0.0;
+        const double2 al = *reinterpret_cast<const double2*>(alph + col);
+        const double2 ww = *reinterpret_cast<const double2*>(wv + col);
+        fa = fma(e0, al.x, fa); fa = fma(e1, al.y, fa);
+        ua = fma(e0, ww.x, ua); ua = fma(e1, ww.y, ua);
+      }
+      x[ct][0] = e0;
+      x[ct][1] = e1;
+    }
+  };
+  long zero_ss = 0;
+  int any = 0;
+  int iter = 0;
+  for (int pt = blockIdx.x; pt < ntiles; pt += gridDim.x, ++iter) {
+    __syncthreads();                      // every warp is done with the previous tile's As
+    for (int idx = tid; idx < TB * d; idx += CH_THREADS) {
+      const int r = idx / d, k = idx - r * d;
+      const long gp = (long)pt * TB + r;
+      double v = 0.0;
+      if (gp < A.npts) v = standardize1(A.xpts[(size_t)gp * d + k], A.normtype, A.norm_a ? A.norm_a[k] : 0.0, A.norm_b ? A.norm_b[k] : 1.0);
+      As[r * lda + k] = v;
+    }
+    __syncthreads();
+    const int seq = iter * NS;
+    fa = 0.0; ua = 0.0;
+    double ssq = 0.0;
+    // one pass per sample tile; every helper is expanded exactly once so that x[] stays in
+    // registers (a lambda called from two places is outlined and x[] would live on the stack)
+#pragma unroll 1
+    for (int tile = 0; tile < nt; ++tile) {
+      const int nct = tile == 0 ? 16 : nct1;
+      psi_tile(tile, nct);
+      if (tile == 1) {
+        // x = psi_1 - V_0 L_10^T : A fragments of V_0 straight from shared memory
+        const double* vrow = Vs + row * PS_VLD + tq;
+#pragma unroll 1
+        for (int s = 0; s < NSLAB; ++s) {
+          const double* Ls = acquire(seq + 8 + s);
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            const int t = 2 * s + tt;
+            const double a0 = -vrow[8 * t], a1 = -vrow[8 * t + 4];
+#pragma unroll
+            for (int ct = 0; ct < 16; ++ct) {
+              if (ct < nct1) {
+                const double* lrow = Ls + (8 * ct + g) * KS + tq;
+                dmma884(x[ct][0], x[ct][1], a0, lrow[((2 * tt) ^ (g & 3)) << 2]);
+                dmma884(x[ct][0], x[ct][1], a1, lrow[((2 * tt + 1) ^ (g & 3)) << 2]);
+              }
+            }
+          }
+          release(seq + 8 + s);
+        }
+      }
+      // (one call site: with several instantiations behind branches ptxas spills x[])
+      trsm_strip<16>(x, tile == 0 ? seq : seq + 16, tile == 0 ? 8 : ns1, W8s + tile * 1024, lane, acquire, release);
+#pragma unroll
+      for (int ct = 0; ct < 16; ++ct) {
+        ssq = fma(x[ct][0], x[ct][0], ssq);
+        ssq = fma(x[ct][1], x[ct][1], ssq);
+      }
+      if (tile == 0 && nt == 2) {
+#pragma unroll
+        for (int ct = 0; ct < 16; ++ct)
+          *reinterpret_cast<double2*>(Vs + row * PS_VLD + 8 * ct + 2 * tq) = make_double2(x[ct][0], x[ct][1]);
+        __syncwarp();                     // V_0 rows are read back by this warp only
+      }
+    }
+    fa += __shfl_xor_sync(FULLMASK, fa, 1); fa += __shfl_xor_sync(FULLMASK, fa, 2);
+    ua += __shfl_xor_sync(FULLMASK, ua, 1); ua += __shfl_xor_sync(FULLMASK, ua, 2);
+    ssq += __shfl_xor_sync(FULLMASK, ssq, 1); ssq += __shfl_xor_sync(FULLMASK, ssq, 2);
+    const long gp = (long)pt * TB + row;
+    if (tq == 0 && gp < A.npts) epilogue_point(A.epi, gp, fa, ua, ssq, zero_ss, any);
+  }
+  if (A.epi.stats) {
+    if (zero_ss) atomicAdd(reinterpret_cast<unsigned long long*>(A.epi.stats), (unsigned long long)zero_ss);
+    if (any) atomicOr(reinterpret_cast<unsigned long long*>(A.epi.stats + 1), 1ull);
+  }
+}
+
+constexpr size_t PS_SMEM = ((size_t)TB * PS_VLD + PS_NST * SLAB_ELEMS + 2048 + PS_MAXD * 256 + 512 + 2 * PS_MAXD +
+                            TB * (PS_MAXD + 1)) * 8 + 2 * PS_NST * 8;
+static_assert(PS_SMEM <= 227 * 1024, "predict_small_kernel shared memory");
 
 // ====================================================================== launchers
 static inline size_t corr_smem_bytes(int d) {
@@ -1578,6 +1823,25 @@ __global__ void __launch_bounds__(CH_THREADS, 1) fp64_probe_kernel(int iters, in
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
   if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t launch_predict_small(const PredSmallArgs& a, int sm_count, cudaStream_t st) {
+  static bool attr[64] = {false};
+  const int dev = cur_dev();
+  if (!attr[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(predict_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM);
+    if (e != cudaSuccess) return e;
+    attr[dev] = true;
+  }
+  const long tiles = (a.npts + TB - 1) / TB;
+  const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+  predict_small_kernel<<<grid, CH_THREADS, PS_SMEM, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+bool predict_small_supported(int n, int d, int nkernel, int kid0, int kpls) {
+  return n <= 2 * TB && d <= PS_MAXD && nkernel == 1 && kid0 == K_GAUSS && !kpls;
 }
 
 cudaError_t launch_fp64_probe(int blocks, int iters, int mode, double* sink, cudaStream_t st) {

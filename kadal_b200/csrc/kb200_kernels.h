@@ -98,7 +98,25 @@ struct EpiArgs {
   unsigned long long* stats;   // [0] = #(SSqr == 0), [1] = any nonzero EI term
 };
 
+struct PredSmallArgs {
+  int n, d, nt, ntheta;
+  const double* X;       // [n][d] training inputs
+  const double* cand;    // parameter row of the fitted model
+  const double* L;       // predictor tiles L_00, L_10, L_11
+  const double* W8;      // [nt][1024]
+  const double* alpha;   // [nt*128]
+  const double* wvec;    // [nt*128]
+  const double* xpts;    // [npts][d] raw points
+  long npts;
+  int normtype;
+  const double* norm_a;
+  const double* norm_b;
+  EpiArgs epi;           // outputs / scalars (fdot, udot, ssq unused)
+};
+
 cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st);
+cudaError_t launch_predict_small(const PredSmallArgs& a, int sm_count, cudaStream_t st);
+bool predict_small_supported(int n, int d, int nkernel, int kid0, int kpls);
 cudaError_t launch_chol_diag(const CholArgs& a, int j, int nmat, cudaStream_t st);
 cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);
 cudaError_t launch_w8_from_tiles(const CholArgs& a, int nmat, cudaStream_t st);
