@@ -367,3 +367,106 @@ def test_kpls_class_cmaes_drop_in(kb):
     s2 = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
     assert relerr(p[0].ravel(), pr[0].ravel()) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
     assert relerr(p[1].ravel(), pr[1].ravel(), 1e-6 * s2) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
+
+
+# ------------------------------------------------------------------ BASELINE configs 3, 4, 5 at full size
+def test_c3_full_size_bulk_predict_properties(kb):
+    """C3: n=200, d=6, pred + s + U over 10^7 Monte-Carlo points in ONE call (the reference chunks
+    to 10 000 rows, akmcs.py:91-106).  Size-independent properties: any slice of the bulk result
+    equals the same points predicted on their own (bit-identical), a random sample of 4000 points
+    matches the oracle, U = |f|/s, and the fused small-n kernel agrees with the general tiled path."""
+    w = ko.workload("C3")
+    info = ko.make_kriginfo(w["X"], w["y"])
+    kb.likelihood(w["theta"].copy(), info, "all", False)
+    ref = copy.deepcopy(info)
+    npts = 10 ** 7
+    xp = ko.mc_points(npts, 6, seed=2)
+    out = kb.predict_arrays(xp, info, ("pred", "s", "ufun"))
+    f, s, u = out["pred"], out["s"], out["ufun"]
+    assert f.shape == (npts,) and np.all(np.isfinite(f)) and np.all(s >= 0)
+    assert np.array_equal(u, np.abs(f) / s)
+    sl = slice(4_999_871, 5_000_129)                  # straddles point-tile and chunk boundaries
+    sub = kb.predict_arrays(xp[sl], info, ("pred", "s"))
+    assert np.array_equal(sub["pred"], f[sl]) and np.array_equal(sub["s"], s[sl])
+    idx = np.random.default_rng(4).choice(npts, 4000, replace=False)
+    pr = ko.prediction(xp[idx], ref, ["pred", "s"])
+    s2 = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
+    assert relerr(f[idx], pr[0].ravel()) < TOL_MEAN
+    assert relerr(s[idx], pr[1].ravel(), 1e-3 * np.sqrt(s2)) < TOL_VAR
+    # argmin of the U-function (the AK-MCS learning criterion, akmcs.py:281-285) on the sample
+    assert int(np.argmin(u[idx])) == int(np.argmin(np.abs(pr[0].ravel()) / pr[1].ravel()))
+    # the fused small-n kernel against the general tiled path (debug kernels: plain-FMA GEMM, per-row
+    # substitution) on the same model
+    from kadal_b200 import _capi
+    from kadal_b200.model import GpuModel
+    gm = GpuModel(w["X"], w["y"], np.ones((200, 1)), [0], naive=True)
+    assert gm.fit_state(w["theta"], False, -6.0, want_U=False, want_Psi=False)["info"] == 0
+    o2 = gm.predict(xp[:5000], _capi.OUT_PRED | _capi.OUT_S, _capi.NORM_DEFAULT, -np.ones(6), np.ones(6))
+    assert relerr(o2["pred"], f[:5000]) < 1e-11
+    assert relerr(o2["s"], s[:5000], 1e-3 * np.sqrt(s2)) < 1e-8
+    gm.close()
+
+
+def test_c4_full_model_prediction_against_oracle(kb):
+    """C4: n=800, d=20 (7 sample tiles), 'pred' only as sobol_ind.py:45-71 requests; 2x10^5 points
+    here (the 2x10^7 of the config are the same kernel, sharded), oracle on a 3000-point sample."""
+    w = ko.workload("C4")
+    info = ko.make_kriginfo(w["X"], w["y"])
+    kb.likelihood(w["theta"].copy(), info, "all", False)
+    ref = copy.deepcopy(info)
+    ko.likelihood(w["theta"].copy(), ref, "all", False, check_pd=False)
+    cond = np.linalg.cond(ref["Psi"] + np.eye(800) * 1e-6)
+    assert relerr(info["NegLnLike"], ref["NegLnLike"]) < nll_tol(cond)
+    xp = np.random.default_rng(12).uniform(-1, 1, (200_000, 20))
+    f = kb.predict_arrays(xp, info, ("pred",))["pred"]
+    idx = np.random.default_rng(13).choice(len(xp), 3000, replace=False)
+    pr = ko.prediction(xp[idx], ref, ["pred"])
+    assert relerr(f[idx], pr.ravel()) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+    # mean + variance through the general tiled path (n > 256) on a subset
+    pv = kb.predict_arrays(xp[idx[:600]], info, ("pred", "ssqr"))
+    rv = ko.prediction(xp[idx[:600]], ref, ["pred", "SSqr"])
+    s2 = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
+    assert relerr(pv["pred"], rv[0].ravel()) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+    assert relerr(pv["ssqr"], rv[1].ravel(), 1e-6 * s2) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
+
+
+def test_c5_kpls_n4000_factor_and_candidate_scoring(kb):
+    """C5: KPLS, d=100, n=4000 (32 tiles per dimension: 528 factor tiles, blocked tensor-core
+    Cholesky), 3 PLS components.  The oracle needs a 12.8 GB temporary and ~1 min per evaluation at
+    this size, so full size is checked through properties: U^T U = Psi + eps I, interpolation of the
+    samples, positive variances, batched == single evaluation; the oracle is used at n=500."""
+    w = ko.workload("C5")
+    info = ko.make_kriginfo(w["X"], w["y"], pls=w["pls"], n_princomp=3)
+    x = w["theta"]
+    kb.likelihood(x.copy(), info, "all", False)
+    U, Psi = info["U"], info["Psi"]
+    n = 4000
+    A = Psi + np.eye(n) * 1e-6
+    assert np.allclose(np.tril(U, -1), 0.0)
+    assert np.linalg.norm(U.T @ U - A) / np.linalg.norm(A) < 1e-14
+    # Psi itself against the kernel definition on a 300 x 300 corner (kernelfunc.py:42-47)
+    Xn = info["X_norm"] if "X_norm" in info else info["X"]
+    dd = (Xn[:300, None, :] - Xn[None, :300, :]) ** 2
+    S = ((dd @ (w["pls"] ** 2)) / (10.0 ** x) ** 2).sum(-1)
+    assert np.max(np.abs(np.exp(-0.5 * S) - Psi[:300, :300])) < 1e-14
+    nll_b, inf = kb.likelihood_batch(np.vstack([x, x + 0.05]), info, False)
+    assert inf[0] == 0 and relerr(nll_b[0], info["NegLnLike"]) < 1e-13
+    # EHVI-style candidate scoring: pred + SSqr for a [n_pop, d] population (EHVIcomputation.py:169-172)
+    cand = np.random.default_rng(21).uniform(-1, 1, (1500, 100))
+    p = kb.predict_arrays(np.vstack([info["X"][:200], cand]), info, ("pred", "ssqr"))
+    s2 = float(np.asarray(info["SigmaSqr"]).ravel()[0])
+    assert np.max(np.abs(p["pred"][:200] - info["y"][:200, 0])) < 1e-3 * np.ptp(info["y"])
+    assert np.all(p["ssqr"][200:] > -1e-9 * s2) and np.all(p["ssqr"][:200] < 1e-3 * s2)
+    # oracle parity of the same model family at a size the oracle finishes in seconds
+    ws = ko.workload("C5", scale=0.125)
+    si = ko.make_kriginfo(ws["X"], ws["y"], pls=ws["pls"], n_princomp=3)
+    ref = copy.deepcopy(si)
+    kb.likelihood(x.copy(), si, "all", False)
+    ko.likelihood(x.copy(), ref, "all", False, check_pd=False)
+    cond = np.linalg.cond(ref["Psi"] + np.eye(500) * 1e-6)
+    assert relerr(si["NegLnLike"], ref["NegLnLike"]) < nll_tol(cond)
+    q = kb.prediction(cand[:400], si, ["pred", "SSqr"])
+    qr = ko.prediction(cand[:400], ref, ["pred", "SSqr"])
+    s2s = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
+    assert relerr(q[0], qr[0]) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+    assert relerr(q[1], qr[1], 1e-6 * s2s) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
