@@ -105,6 +105,11 @@ int kb200_predict_dev(kb200_model* m, const double* d_x, long long npred, int no
                       double* d_ei, double* d_poi, double* d_pof, double* d_ufun,
                       unsigned long long* stats, void* stream);
 
+/* Leave-one-out predictions of the installed fit: loo[i] = prediction at sample i of the model
+ * refitted without it at the same hyper-parameters (beta re-estimated) -- what
+ * supports/krigloocv2.py:7-34 computes with n refits -- in closed form from the factor. */
+int kb200_loocv(kb200_model* m, double* loo /* n */);
+
 /* Introspection used by the tests / bench. */
 int kb200_model_dims(const kb200_model* m, int* n, int* d, int* p, int* ntheta, int* nkernel);
 /* kernel launches issued by this model since creation (bench.py "gpu_launches") */

@@ -751,6 +751,38 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
   return 0;
 }
 
+extern "C" int kb200_loocv(kb200_model* m, double* loo) {
+  if (!m || !loo) return fail_arg("kb200_loocv: null argument");
+  if (!m->has_pred) return fail_arg("kb200_loocv: no fit installed (call kb200_fit_state or kb200_predictor_load)");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = m->stream;
+  PredSlot& sl = m->slot[0];
+  const long ct = chunk_tiles_for(m);
+  const long cpts = ct * TB;
+  CK(sl.chunk.reserve((size_t)ct * m->nt * TILE_ELEMS * 8));
+  CK(sl.ssq.reserve((size_t)cpts * 8));
+  CK(sl.out[0].reserve((size_t)m->npad * 8));
+  CholArgs pa = chol_args(m, m->pL.d(), m->pW.d(), nullptr, nullptr, nullptr);
+  pa.pred_mode = 1;
+  pa.chunk = sl.chunk.d();
+  pa.ssq = sl.ssq.d();
+  for (long p0 = 0; p0 < m->n; p0 += cpts) {
+    const long np = std::min<long>(cpts, m->n - p0);
+    const int tiles = (int)((np + TB - 1) / TB);
+    CK(launch_identity_chunk(sl.chunk.d(), tiles, m->nt, p0 / TB, st));
+    m->launches++;
+    for (int j = 0; j < m->nt; ++j) {
+      Timed t(m, KB200_PROF_PREDSOLVE, st);
+      CK(launch_chol_panel(pa, j, tiles, 1, st));
+    }
+    CK(launch_loo(m->R.d(), m->palpha.d(), m->pw.d(), sl.ssq.d(), m->pbtb, m->n, p0, (int)np, sl.out[0].d(), st));
+    m->launches++;
+  }
+  CK(cudaMemcpyAsync(loo, sl.out[0].p, (size_t)m->n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 static int predict_prepare(kb200_model* m, int normtype, const double* norm_a, const double* norm_b,
                            unsigned want, double* const outs[7], cudaStream_t st) {
   if (!m->has_pred) return fail_arg("kb200_predict: no predictor installed (call kb200_fit_state or kb200_predictor_load)");

@@ -1674,6 +1674,48 @@ static inline size_t corr_smem_bytes(int d) {
     if (e__ != cudaSuccess) return e__;            \
   } while (0)
 
+// ================================================================== leave-one-out (LOOCV)
+// krigloocv2.py:7-34 refits the model n times on n-1 samples at fixed theta and predicts the
+// left-out sample.  With A = Psi + eps I = L L^T, alpha = A^-1 (y - F beta), w = A^-1 F that is
+// the closed form (Dubrule 1983)   y_loo[i] = y[i] - alpha[i] / (A^-1_ii - w[i]^2 / (F^T A^-1 F)),
+// and A^-1_ii = ||L^-1 e_i||^2 comes out of the predictor's own variance machinery when the
+// "correlation vectors" are the unit vectors: identity_chunk_kernel builds them, the panel kernel
+// (pred mode) solves them, loo_kernel finishes.
+__global__ void identity_chunk_kernel(double* chunk, int nt, long pt0) {
+  // chunk tile (pt, j): rows = points pt0*128 + pt*128 + r, columns = samples j*128 + c
+  double* T = chunk + ((size_t)blockIdx.x * nt + blockIdx.y) * TILE_ELEMS;
+  const bool diag = (pt0 + blockIdx.x) == blockIdx.y;
+  for (int idx = threadIdx.x; idx < TILE_ELEMS; idx += blockDim.x) T[idx] = 0.0;
+  __syncthreads();
+  if (diag)
+    for (int r = threadIdx.x; r < TB; r += blockDim.x) T[tile_off(r, r)] = 1.0;
+}
+
+__global__ void loo_kernel(const double* y, const double* alpha, const double* w, const double* ssq, double btb,
+                           int n, long p0, int np, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const long gi = p0 + i;
+  if (gi >= n) return;
+  const double q = ssq[i] - w[gi] * (w[gi] / btb);
+  out[gi] = y[gi] - alpha[gi] / q;
+}
+
+cudaError_t launch_identity_chunk(double* chunk, int tiles, int nt, long pt0, cudaStream_t st) {
+  identity_chunk_kernel<<<dim3(tiles, nt), 256, 0, st>>>(chunk, nt, pt0);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_loo(const double* y, const double* alpha, const double* w, const double* ssq, double btb, int n,
+                       long p0, int np, double* out, cudaStream_t st) {
+  loo_kernel<<<(np + 255) / 256, 256, 0, st>>>(y, alpha, w, ssq, btb, n, p0, np, out);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+
+
 // dynamic-smem opt-in is per device (context): remember what was set for each device
 static size_t g_corr_attr[64] = {0};
 static bool g_chol_attr[64] = {false};

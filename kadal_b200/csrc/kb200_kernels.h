@@ -115,6 +115,9 @@ struct PredSmallArgs {
 };
 
 cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st);
+cudaError_t launch_identity_chunk(double* chunk, int tiles, int nt, long pt0, cudaStream_t st);
+cudaError_t launch_loo(const double* y, const double* alpha, const double* w, const double* ssq, double btb, int n,
+                       long p0, int np, double* out, cudaStream_t st);
 cudaError_t launch_predict_small(const PredSmallArgs& a, int sm_count, cudaStream_t st);
 bool predict_small_supported(int n, int d, int nkernel, int kid0, int kpls);
 cudaError_t launch_chol_diag(const CholArgs& a, int j, int nmat, cudaStream_t st);

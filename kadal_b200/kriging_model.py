@@ -368,9 +368,9 @@ class Kriging:
         return bestx, bestf
 
     def loocvcalc(self, metrictype="mape", type="standard"):
-        """Leave-one-out cross validation (kriging_model.py:260-297).  Both reference
-        variants return the same quantity; it is evaluated with the closed-form
-        leave-one-out predictor on the GPU factor (see :mod:`kadal_b200.loocv`)."""
+        """Leave-one-out cross validation (kriging_model.py:260-297).  'standard'
+        (krigloocv2.py: n refits in the reference) is one closed-form GPU pass over the factor;
+        'fast' (krigloocv.py) is not built (see :mod:`kadal_b200.loocv`)."""
         if type not in ("fast", "standard"):
             raise ValueError('"type" only accept fast or standard')
         from .loocv import loocv

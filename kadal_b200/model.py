@@ -173,6 +173,12 @@ class GpuModel:
                                          int(bool(limit_ge)), *ptrs, stats, c_void_p(stream)))
         return (int(stats[0]), int(stats[1])) if want_stats else None
 
+    def loocv(self):
+        """Leave-one-out predictions (n,) of the installed fit (krigloocv2.py semantics)."""
+        out = np.empty(self.n, dtype=np.float64)
+        check(self.lib.kb200_loocv(self.handle, ptr(out)))
+        return out
+
     def set_groups(self, ngroups):
         """Number of candidate groups (streams) of a likelihood batch; 1 serialises the kernels."""
         check(self.lib.kb200_set_groups(self.handle, int(ngroups)))

@@ -470,3 +470,42 @@ def test_c5_kpls_n4000_factor_and_candidate_scoring(kb):
     s2s = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
     assert relerr(q[0], qr[0]) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
     assert relerr(q[1], qr[1], 1e-6 * s2s) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
+
+
+# ------------------------------------------------------------------ LOOCV
+def _loocv2_bruteforce(info):
+    """krigloocv2.py:7-34 restated with the oracle: n refits at fixed theta, one-point predictions."""
+    n = info["nsamp"]
+    out = np.zeros((n, 1))
+    for i in range(n):
+        t = copy.deepcopy(info)
+        t["F"] = np.delete(info["F"], i, 0)
+        t["y"] = np.delete(info["y"], i, 0)
+        t["X_norm"] = np.delete(info["X_norm"], i, 0)
+        t["nsamp"] = n - 1
+        t = ko.likelihood(np.array(info["Theta"], dtype=float), t, "all", False, check_pd=False)
+        t["standardization"] = False
+        t["X"] = t["X_norm"]
+        out[i, 0] = ko.prediction(info["X_norm"][i, :], t, ["pred"])
+    return out
+
+
+@pytest.mark.parametrize("n,d,kernel", [(70, 3, "gaussian"), (150, 4, "matern52"), (260, 5, "gaussian")])
+def test_loocv_standard_matches_n_refits(kb, n, d, kernel):
+    from kadal_b200.loocv import loocv
+    from kadal_b200.errperf import errperf
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(2 * X.sum(1, keepdims=True)) + X[:, :1] ** 2 + 3.0
+    info = ko.make_kriginfo(X, y, kernel=(kernel,))
+    kb.likelihood(np.full(d, -0.1), info, "all", False)
+    err, pred = loocv(info, errtype="rmse", type="standard")
+    ref = _loocv2_bruteforce(info)
+    cond = np.linalg.cond(info["Psi"] + np.eye(n) * 1e-6)
+    assert pred.shape == (n, 1)
+    assert relerr(pred, ref) < max(TOL_MEAN, 5 * cond * 2.0 ** -53)
+    assert abs(err - errperf(y, ref, "rmse")) <= 1e-7 * max(1.0, abs(err))
+    with pytest.raises(NotImplementedError):
+        loocv(info, type="fast")
+    with pytest.raises(ValueError):
+        loocv(info, type="other")
