@@ -105,6 +105,14 @@ int kb200_predict_dev(kb200_model* m, const double* d_x, long long npred, int no
                       double* d_ei, double* d_poi, double* d_pof, double* d_ufun,
                       unsigned long long* stats, void* stream);
 
+/* AK-MCS learning / stopping quantities over a Monte-Carlo population without shipping the
+ * npred predictions back (reliability_analysis/akmcs.py:267-297): U = abs(G)/s with its minimum and
+ * first arg-min (lfucalc :281-285), counts[0] = #(G <= 0) (pfcalc :267-271), counts[1] =
+ * #(G - 1.96 s <= 0), counts[2] = #(G + 1.96 s <= 0) (stopcrit :287-297); G = 'pred', s = 's'. */
+int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int normtype,
+                       const double* norm_a, const double* norm_b, double* min_u,
+                       long long* argmin_u, unsigned long long* counts);
+
 /* Leave-one-out predictions of the installed fit: loo[i] = prediction at sample i of the model
  * refitted without it at the same hyper-parameters (beta re-estimated) -- what
  * supports/krigloocv2.py:7-34 computes with n refits -- in closed form from the factor. */

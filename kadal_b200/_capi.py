@@ -55,6 +55,8 @@ SIGNATURES = {
     "kb200_fp64_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_double_p]),
     "kb200_set_groups": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "kb200_loocv": (ctypes.c_int, [c_void_p, c_void_p]),
+    "kb200_akmcs_reduce": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
+                                          c_double_p, ctypes.POINTER(ctypes.c_longlong), c_u64_p]),
     "kb200_debug_psi": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        ctypes.c_int, c_void_p]),
 }

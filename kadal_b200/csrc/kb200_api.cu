@@ -84,7 +84,7 @@ struct kb200_model {
   int ngroups = 2;
   cudaStream_t gstream[MAXG] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[MAXG] = {nullptr, nullptr, nullptr, nullptr};
-  DevBuf norm_a, norm_b, stats;
+  DevBuf norm_a, norm_b, stats, akpart;
   unsigned long long launches = 0;
   size_t ws_cap_bytes = 0;
   // optional per-kernel-class event timing (kb200_profile_*)
@@ -242,7 +242,7 @@ void kb200_model_destroy(kb200_model* m) {
   DevBuf* bufs[] = {&m->X, &m->R, &m->pls, &m->pls2, &m->tiles, &m->W, &m->Z, &m->cand, &m->xdev,
                     &m->nll, &m->info, &m->logdet, &m->sigma2, &m->beta, &m->btb, &m->resid,
                     &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand,
-                    &m->norm_a, &m->norm_b, &m->stats};
+                    &m->norm_a, &m->norm_b, &m->stats, &m->akpart};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < 2; ++s) {
     PredSlot& sl = m->slot[s];
@@ -824,6 +824,62 @@ int kb200_predict_dev(kb200_model* m, const double* d_x, long long npred, int no
     CK(cudaMemcpyAsync(stats, m->stats.p, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
+  return 0;
+}
+
+int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int normtype,
+                       const double* norm_a, const double* norm_b, double* min_u,
+                       long long* argmin_u, unsigned long long* counts) {
+  if (!m || !x || !min_u || !argmin_u || !counts) return fail_arg("kb200_akmcs_reduce: null argument");
+  if (npred < 1) return fail_arg("kb200_akmcs_reduce: empty population");
+  CK(cudaSetDevice(m->device));
+  const unsigned want = KB200_OUT_PRED | KB200_OUT_S;
+  double* dummy[7] = {(double*)1, nullptr, (double*)1, nullptr, nullptr, nullptr, nullptr};
+  int rc = predict_prepare(m, normtype, norm_a, norm_b, want, dummy, m->stream);
+  if (rc) return rc;
+  struct Part { double min_u; long long arg; unsigned long long c0, cm, cp; };
+  static_assert(sizeof(Part) == AK_PARTIAL_BYTES, "AkPartial layout");
+  const long ct = chunk_tiles_for(m) * TB;
+  const long sc = std::max<long>(ct, (1L << 19) / ct * ct);
+  const long nchunks = (npred + sc - 1) / sc;
+  std::vector<Part> host((size_t)nchunks * AK_BLOCKS);
+  CK(m->akpart.reserve((size_t)nchunks * AK_BLOCKS * sizeof(Part)));
+  long it = 0;
+  for (long p0 = 0; p0 < npred; p0 += sc, ++it) {
+    PredSlot& sl = m->slot[it & 1];
+    cudaStream_t st = sl.stream;
+    const long np = std::min<long>(sc, npred - p0);
+    CK(sl.x.reserve((size_t)std::min<long>(sc, npred) * m->d * 8));
+    CK(cudaMemcpyAsync(sl.x.p, x + (size_t)p0 * m->d, (size_t)np * m->d * 8, cudaMemcpyHostToDevice, st));
+    double* outs[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    CK(sl.out[0].reserve((size_t)std::min<long>(sc, npred) * 8));
+    CK(sl.out[2].reserve((size_t)std::min<long>(sc, npred) * 8));
+    outs[0] = sl.out[0].d();
+    outs[2] = sl.out[2].d();
+    rc = predict_core(m, sl, sl.x.d(), np, normtype, want, 0.0, 0.0, 1, outs, st);
+    if (rc) return rc;
+    CK(launch_akmcs_reduce(outs[0], outs[2], np, p0, static_cast<char*>(m->akpart.p) + (size_t)it * AK_BLOCKS * sizeof(Part),
+                           AK_BLOCKS, st));
+    m->launches++;
+  }
+  CK(cudaStreamSynchronize(m->slot[0].stream));
+  CK(cudaStreamSynchronize(m->slot[1].stream));
+  CK(cudaMemcpy(host.data(), m->akpart.p, host.size() * sizeof(Part), cudaMemcpyDeviceToHost));
+  double bu = INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  unsigned long long c[3] = {0, 0, 0};
+  for (const Part& p : host) {
+    const bool un = p.min_u != p.min_u, bn = bu != bu;
+    bool better;
+    if (un != bn) better = un;
+    else if (un) better = p.arg < bi;
+    else better = p.min_u < bu || (p.min_u == bu && p.arg < bi);
+    if (better) { bu = p.min_u; bi = p.arg; }
+    c[0] += p.c0; c[1] += p.cm; c[2] += p.cp;
+  }
+  *min_u = bu;
+  *argmin_u = bi;
+  counts[0] = c[0]; counts[1] = c[1]; counts[2] = c[2];
   return 0;
 }
 

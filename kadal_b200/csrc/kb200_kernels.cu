@@ -1701,6 +1701,63 @@ __global__ void loo_kernel(const double* y, const double* alpha, const double* w
   out[gi] = y[gi] - alpha[gi] / q;
 }
 
+// ================================================== AK-MCS reductions (akmcs.py:267-297)
+// From G = pred and sigma_G = s of a Monte-Carlo population: U = |G| / s with its minimum and
+// first arg-min (lfucalc), #(G <= 0) (pfcalc), #(G - 1.96 s <= 0) and #(G + 1.96 s <= 0)
+// (stopcrit).  One partial record per block; the handful of records is combined on the host.
+struct AkPartial {
+  double min_u;
+  long long arg;
+  unsigned long long c0, cm, cp;
+};
+
+__device__ __forceinline__ bool ak_better(double u, long long i, double bu, long long bi) {
+  // np.argmin order: NaN first, then smaller value, ties -> smaller index
+  const bool un = u != u, bn = bu != bu;
+  if (un != bn) return un;
+  if (un) return i < bi;
+  return u < bu || (u == bu && i < bi);
+}
+
+__global__ void __launch_bounds__(256)
+akmcs_reduce_kernel(const double* __restrict__ G, const double* __restrict__ S, long n, long base, AkPartial* out) {
+  double bu = INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  unsigned long long c0 = 0, cm = 0, cp = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double g = G[i], sg = S[i];
+    const double u = fabs(g) / sg;
+    if (ak_better(u, base + i, bu, bi)) { bu = u; bi = base + i; }
+    c0 += g <= 0.0;
+    cm += (g - 1.96 * sg) <= 0.0;
+    cp += (g + 1.96 * sg) <= 0.0;
+  }
+  __shared__ double su[256];
+  __shared__ long long si[256];
+  __shared__ unsigned long long sc[3][256];
+  const int t = threadIdx.x;
+  su[t] = bu; si[t] = bi; sc[0][t] = c0; sc[1][t] = cm; sc[2][t] = cp;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) {
+      if (ak_better(su[t + o], si[t + o], su[t], si[t])) { su[t] = su[t + o]; si[t] = si[t + o]; }
+      sc[0][t] += sc[0][t + o]; sc[1][t] += sc[1][t + o]; sc[2][t] += sc[2][t + o];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    AkPartial p;
+    p.min_u = su[0]; p.arg = si[0]; p.c0 = sc[0][0]; p.cm = sc[1][0]; p.cp = sc[2][0];
+    out[blockIdx.x] = p;
+  }
+}
+
+cudaError_t launch_akmcs_reduce(const double* G, const double* S, long n, long base, void* out, int nblocks, cudaStream_t st) {
+  akmcs_reduce_kernel<<<nblocks, 256, 0, st>>>(G, S, n, base, static_cast<AkPartial*>(out));
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
 cudaError_t launch_identity_chunk(double* chunk, int tiles, int nt, long pt0, cudaStream_t st) {
   identity_chunk_kernel<<<dim3(tiles, nt), 256, 0, st>>>(chunk, nt, pt0);
   KB_LAUNCH_CHECK();

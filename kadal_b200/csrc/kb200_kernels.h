@@ -115,6 +115,9 @@ struct PredSmallArgs {
 };
 
 cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st);
+constexpr int AK_BLOCKS = 592;          // 4 x 148
+constexpr int AK_PARTIAL_BYTES = 40;    // {double min_u; long long arg; unsigned long long c0, cm, cp;}
+cudaError_t launch_akmcs_reduce(const double* G, const double* S, long n, long base, void* out, int nblocks, cudaStream_t st);
 cudaError_t launch_identity_chunk(double* chunk, int tiles, int nt, long pt0, cudaStream_t st);
 cudaError_t launch_loo(const double* y, const double* alpha, const double* w, const double* ssq, double btb, int n,
                        long p0, int np, double* out, cudaStream_t st);

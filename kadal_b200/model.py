@@ -173,6 +173,18 @@ class GpuModel:
                                          int(bool(limit_ge)), *ptrs, stats, c_void_p(stream)))
         return (int(stats[0]), int(stats[1])) if want_stats else None
 
+    def akmcs_reduce(self, x, normtype=0, norm_a=None, norm_b=None):
+        """(min U, argmin U, [#(G<=0), #(G-1.96s<=0), #(G+1.96s<=0)]) over the population x."""
+        x = as_f64(np.atleast_2d(x))
+        if x.shape[1] != self.d:
+            raise ValueError("population has %d columns, model has %d" % (x.shape[1], self.d))
+        na = as_f64(norm_a) if norm_a is not None else None
+        nb = as_f64(norm_b) if norm_b is not None else None
+        mu, arg, cnt = ctypes.c_double(), ctypes.c_longlong(), (ctypes.c_ulonglong * 3)()
+        check(self.lib.kb200_akmcs_reduce(self.handle, ptr(x), x.shape[0], int(normtype), ptr(na), ptr(nb),
+                                          ctypes.byref(mu), ctypes.byref(arg), cnt))
+        return float(mu.value), int(arg.value), [int(c) for c in cnt]
+
     def loocv(self):
         """Leave-one-out predictions (n,) of the installed fit (krigloocv2.py semantics)."""
         out = np.empty(self.n, dtype=np.float64)

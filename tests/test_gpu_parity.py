@@ -509,3 +509,36 @@ def test_loocv_standard_matches_n_refits(kb, n, d, kernel):
         loocv(info, type="fast")
     with pytest.raises(ValueError):
         loocv(info, type="other")
+
+
+# ------------------------------------------------------------------ AK-MCS reductions
+def test_akmcs_reductions_match_the_reference_formulas(kb):
+    """lfucalc / pfcalc / stopcrit / covpf of akmcs.py:267-297 on a 1.3e6-point population: the
+    device-side reduction must equal the same formulas applied to the bulk predictions."""
+    from kadal_b200.reliability import akmcs_reductions
+    w = ko.workload("C3")
+    y = w["y"] - 3.6                                   # limit state G = 0 cuts through the population
+    info = ko.make_kriginfo(w["X"], y)
+    kb.likelihood(w["theta"].copy(), info, "all", False)
+    pop = ko.mc_points(1_300_003, 6, seed=5)
+    r = akmcs_reductions(pop, info)
+    o = kb.predict_arrays(pop, info, ("pred", "s"))
+    G, sg = o["pred"], o["s"]
+    U = np.abs(G) / sg
+    assert r["minUloc"] == int(np.argmin(U)) and r["minU"] == float(np.min(U))
+    n = len(pop)
+    pf = np.count_nonzero(G <= 0) / n
+    assert 0.0 < pf < 1.0 and r["Pf"] == pf and r["nGless"] == np.count_nonzero(G <= 0)
+    assert r["cov"] == float(np.sqrt((1 - pf) / (pf * n)))
+    pfp, pfn = np.count_nonzero(G - 1.96 * sg <= 0) / n, np.count_nonzero(G + 1.96 * sg <= 0) / n
+    assert r["stop_criteria"] == (pfp - pfn) / pf
+    # a population that never fails: the reference's sentinel values
+    safe = akmcs_reductions(pop[:1000] * 0.0, ko_shift(info, +50.0, kb), )
+    assert safe["Pf"] == 0 and safe["cov"] == 1000 and safe["stop_criteria"] == 100
+
+
+def ko_shift(info, dy, kb):
+    """Same model with the response shifted by dy (refit at the same theta)."""
+    K = ko.make_kriginfo(info["X"], info["y"] + dy)
+    kb.likelihood(np.array(info["Theta"], dtype=float), K, "all", False)
+    return K
