@@ -113,6 +113,22 @@ int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int nor
                        const double* norm_a, const double* norm_b, double* min_u,
                        long long* argmin_u, unsigned long long* counts);
 
+/* 2-objective expected hyper-volume improvement of npop candidates over a Pareto front
+ * (optim_tools/ehvi/exi2d.py:7-84 as called by EHVIcomputation.py:57 and :169-175): pareto is
+ * [k][2] row-major (any order, k <= 1022), ref the reference point, candidate i has means
+ * mu[2 i], mu[2 i + 1] and spreads s[2 i], s[2 i + 1] (the reference passes the kriging variance
+ * SSqr here, EHVIcomputation.py:176; the library takes whatever it is given).  out[i] =
+ * sign * exi2d(pareto, ref, mu_i, s_i); ehvicalc_vec uses sign = -1.  Host pointers.  No model
+ * handle: the front is the only state. */
+int kb200_ehvi2d(int device, const double* pareto, int k, const double* ref, const double* mu,
+                 const double* s, long long npop, double sign, double* out);
+/* Same with device pointers and element stride `inc` between candidates (inc = 2 with mu1 = mu0 + 1
+ * for the [npop][2] layout, inc = 1 for one array per objective, e.g. the outputs of two
+ * kb200_predict_dev calls); d_pareto is a device copy of the front; runs on `stream`. */
+int kb200_ehvi2d_dev(int device, const double* d_pareto, int k, const double* ref,
+                     const double* d_mu0, const double* d_mu1, const double* d_s0, const double* d_s1,
+                     long long inc, long long npop, double sign, double* d_out, void* stream);
+
 /* Leave-one-out predictions of the installed fit: loo[i] = prediction at sample i of the model
  * refitted without it at the same hyper-parameters (beta re-estimated) -- what
  * supports/krigloocv2.py:7-34 computes with n refits -- in closed form from the factor. */

@@ -70,6 +70,9 @@ struct kb200_model {
   int cstride = 0;
   std::vector<double> hy, hF;
   DevBuf X, R, pls, pls2;
+  // KPLS: hyper-parameter independent projected-distance planes (kb200_kpls.cu), built on first use
+  DevBuf kplanes_sq, kplanes_abs;
+  bool kplanes_ready = false, kplanes_on = true;
   cudaStream_t stream = nullptr;
   // likelihood workspace
   DevBuf tiles, W, Z, cand, xdev, nll, info, logdet, sigma2, beta, btb, resid, rhs2, sol2;
@@ -80,10 +83,11 @@ struct kb200_model {
   PredSlot slot[2];
   // candidate groups of one likelihood batch run on their own streams so that the tail of one
   // group's launch (partially filled last wave, long "next diagonal" CTAs) overlaps the other's
-  static constexpr int MAXG = 4;
+  static constexpr int MAXG = 8;
   int ngroups = 2;
-  cudaStream_t gstream[MAXG] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[MAXG] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t gstream[MAXG] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAXG] = {nullptr};
+  int group_min = 32;   // fewest candidates per group
   DevBuf norm_a, norm_b, stats, akpart;
   unsigned long long launches = 0;
   size_t ws_cap_bytes = 0;
@@ -196,7 +200,14 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
   for (int s = 0; s < 2; ++s) MCK(cudaStreamCreateWithFlags(&m->slot[s].stream, cudaStreamNonBlocking));
   {
     const char* eg = getenv("KB200_GROUPS");
+    // default policy (measured, profiles/r1k_groups.md): two groups for the C2 shape; large
+    // matrices with small populations (C5: nt = 32, P ~ 16) have few CTAs per tile column and
+    // gain from four groups of >= 4 candidates.  KB200_GROUPS / kb200_set_groups() override.
+    m->ngroups = m->nt >= 16 ? 4 : 2;
+    m->group_min = std::max(2, std::min(32, 128 / m->nt));
     if (eg) m->ngroups = std::max(1, std::min((int)kb200_model::MAXG, atoi(eg)));
+    const char* em = getenv("KB200_GROUP_MIN");
+    if (em) m->group_min = std::max(1, atoi(em));
     for (int g = 0; g < m->ngroups; ++g) {
       MCK(cudaStreamCreateWithFlags(&m->gstream[g], cudaStreamNonBlocking));
       MCK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
@@ -223,6 +234,10 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
     MCK(cudaMemcpy(m->pls.p, pls, p2.size() * 8, cudaMemcpyHostToDevice));
     MCK(cudaMemcpy(m->pls2.p, p2.data(), p2.size() * 8, cudaMemcpyHostToDevice));
   }
+  {
+    const char* ek = getenv("KB200_KPLS_PLANES");
+    if (ek && atoi(ek) == 0) m->kplanes_on = false;
+  }
   MCK(m->stats.reserve(16));
   {
     size_t fr = 0, tot = 0;
@@ -239,7 +254,7 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
 void kb200_model_destroy(kb200_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  DevBuf* bufs[] = {&m->X, &m->R, &m->pls, &m->pls2, &m->tiles, &m->W, &m->Z, &m->cand, &m->xdev,
+  DevBuf* bufs[] = {&m->X, &m->R, &m->pls, &m->pls2, &m->kplanes_sq, &m->kplanes_abs, &m->tiles, &m->W, &m->Z, &m->cand, &m->xdev,
                     &m->nll, &m->info, &m->logdet, &m->sigma2, &m->beta, &m->btb, &m->resid,
                     &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand,
                     &m->norm_a, &m->norm_b, &m->stats, &m->akpart};
@@ -327,8 +342,48 @@ static CholArgs chol_args(kb200_model* m, double* tiles, double* W, double* Z, d
   return a;
 }
 
+// KPLS (kernelfunc.py:41-47, 58-64): the distance planes do not depend on the candidate
+static bool kpls_planes_usable(const kb200_model* m) {
+  return m->h > 0 && m->h < 8 && m->kplanes_on && m->tiles_per_mat <= 65535 && !(m->flags & KB200_FLAG_NAIVE);
+}
+
+static int kpls_planes_build(kb200_model* m, cudaStream_t st) {
+  if (m->kplanes_ready) return 0;
+  bool need_sq = false, need_abs = false;
+  for (int k = 0; k < m->nkernel; ++k) (m->kid[k] == K_GAUSS ? need_sq : need_abs) = true;
+  const size_t bytes = (size_t)m->h * m->tiles_per_mat * TILE_ELEMS * 8;
+  if (need_sq) {
+    CK(m->kplanes_sq.reserve(bytes));
+    Timed t(m, KB200_PROF_OTHER, st);
+    CK(launch_kpls_planes(m->X.d(), m->n, m->d, m->h, m->pls2.d(), 0, m->kplanes_sq.d(), m->tiles_per_mat, st));
+  }
+  if (need_abs) {
+    CK(m->kplanes_abs.reserve(bytes));
+    Timed t(m, KB200_PROF_OTHER, st);
+    CK(launch_kpls_planes(m->X.d(), m->n, m->d, m->h, m->pls.d(), 1, m->kplanes_abs.d(), m->tiles_per_mat, st));
+  }
+  // the planes are read by the candidate-group streams: make them visible device-wide first
+  CK(cudaStreamSynchronize(st));
+  m->kplanes_ready = true;
+  return 0;
+}
+
 // assemble + factorise Pb candidates whose parameter rows start at d_cand
 static int assemble(kb200_model* m, const double* d_cand, int Pb, double* tiles, int add_eps, cudaStream_t st) {
+  if (kpls_planes_usable(m)) {
+    int rc = kpls_planes_build(m, st);
+    if (rc) return rc;
+    KplsAsmArgs k;
+    memset(&k, 0, sizeof(k));
+    k.n = m->n; k.h = m->h; k.nkernel = m->nkernel; k.add_eps = add_eps;
+    for (int i = 0; i < MAXK; ++i) k.kid[i] = m->kid[i];
+    k.tiles_per_mat = m->tiles_per_mat;
+    k.planes_sq = m->kplanes_sq.d(); k.planes_abs = m->kplanes_abs.d();
+    k.cand = d_cand; k.cand_stride = m->cstride; k.out = tiles;
+    Timed t(m, KB200_PROF_ASSEMBLE, st);
+    CK(launch_kpls_assemble(k, Pb, st));
+    return 0;
+  }
   CorrArgs c;
   memset(&c, 0, sizeof(c));
   c.spec = make_spec(m);
@@ -390,7 +445,7 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
   CK(cudaMemsetAsync(d_info, 0, (size_t)P * sizeof(int), st));
   for (int p0 = 0; p0 < P; p0 += Pb) {
     const int pb = std::min(Pb, P - p0);
-    const int G = pb >= 32 * m->ngroups ? m->ngroups : 1;
+    const int G = std::max(1, std::min(m->ngroups, pb / m->group_min));
     if (G > 1) CK(cudaEventRecord(m->ev_fork, st));
     for (int g = 0; g < G; ++g) {
       const int o0 = (int)((long)pb * g / G), o1 = (int)((long)pb * (g + 1) / G), pg = o1 - o0;
@@ -927,9 +982,75 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
 
 extern "C" {
 
+// ---------------------------------------------------------------- EHVI
+static int ehvi_core(int device, const double* d_pareto, int k, const double* ref, const double* mu0,
+                     const double* mu1, const double* s0, const double* s1, long inc, long npop, double sign,
+                     double* d_out, cudaStream_t st) {
+  if (k < 0 || k > 1022) return fail_arg("kb200_ehvi2d: 0 <= k <= 1022 Pareto points supported");
+  const size_t k1 = (size_t)k + 1;
+  double* ws = nullptr;     // S [2k] | c2 [k] | splus [(k+1)^2]
+  CK(cudaMallocAsync((void**)&ws, (3 * (size_t)k + 2 + k1 * k1) * 8, st));
+  double* S = ws;
+  double* c2 = ws + 2 * (size_t)k + 1;
+  double* splus = c2 + k + 1;
+  int rc = 0;
+  cudaError_t e = launch_ehvi_tables(d_pareto, k, ref[0], ref[1], S, c2, splus, st);
+  if (e != cudaSuccess) rc = fail("ehvi tables", e);
+  if (!rc) {
+    EhviArgs a;
+    a.k = k; a.r0 = ref[0]; a.r1 = ref[1]; a.S = S; a.c2 = c2; a.splus = splus;
+    a.mu0 = mu0; a.mu1 = mu1; a.s0 = s0; a.s1 = s1; a.inc = inc; a.sign = sign; a.out = d_out;
+    e = launch_ehvi_score(a, npop, st);
+    if (e != cudaSuccess) rc = fail("ehvi score", e);
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+int kb200_ehvi2d_dev(int device, const double* d_pareto, int k, const double* ref,
+                     const double* d_mu0, const double* d_mu1, const double* d_s0, const double* d_s1,
+                     long long inc, long long npop, double sign, double* d_out, void* stream) {
+  if (!ref || !d_mu0 || !d_mu1 || !d_s0 || !d_s1 || !d_out || (k > 0 && !d_pareto))
+    return fail_arg("kb200_ehvi2d_dev: null argument");
+  CK(cudaSetDevice(device));
+  return ehvi_core(device, d_pareto, k, ref, d_mu0, d_mu1, d_s0, d_s1, (long)inc, (long)npop, sign, d_out,
+                   (cudaStream_t)stream);
+}
+
+int kb200_ehvi2d(int device, const double* pareto, int k, const double* ref, const double* mu,
+                 const double* s, long long npop, double sign, double* out) {
+  if (!ref || !mu || !s || !out || (k > 0 && !pareto)) return fail_arg("kb200_ehvi2d: null argument");
+  if (npop < 1) return 0;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return fail_arg("kb200: no CUDA device (there is no CPU fallback)");
+  CK(cudaSetDevice(device));
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  double* buf = nullptr;    // pareto [2k] | mu [2 npop] | s [2 npop] | out [npop]
+  const size_t np = (size_t)npop;
+  cudaError_t e = cudaMalloc((void**)&buf, (2 * (size_t)k + 2 + 5 * np) * 8);
+  if (e != cudaSuccess) { cudaStreamDestroy(st); return fail("cudaMalloc", e); }
+  double* d_par = buf;
+  double* d_mu = buf + 2 * (size_t)k + 2;
+  double* d_s = d_mu + 2 * np;
+  double* d_out = d_s + 2 * np;
+  int rc = 0;
+  auto CKL = [&](cudaError_t err, const char* what) { if (err != cudaSuccess && !rc) rc = fail(what, err); };
+  if (k > 0) CKL(cudaMemcpyAsync(d_par, pareto, 2 * (size_t)k * 8, cudaMemcpyHostToDevice, st), "H2D pareto");
+  CKL(cudaMemcpyAsync(d_mu, mu, 2 * np * 8, cudaMemcpyHostToDevice, st), "H2D mu");
+  CKL(cudaMemcpyAsync(d_s, s, 2 * np * 8, cudaMemcpyHostToDevice, st), "H2D s");
+  if (!rc) rc = ehvi_core(device, d_par, k, ref, d_mu, d_mu + 1, d_s, d_s + 1, 2, (long)npop, sign, d_out, st);
+  if (!rc) CKL(cudaMemcpyAsync(out, d_out, np * 8, cudaMemcpyDeviceToHost, st), "D2H out");
+  CKL(cudaStreamSynchronize(st), "sync");
+  cudaFree(buf);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
 int kb200_set_groups(kb200_model* m, int ngroups) {
   if (!m) return fail_arg("null model");
-  if (ngroups < 1 || ngroups > kb200_model::MAXG) return fail_arg("kb200_set_groups: 1..4 groups");
+  if (ngroups < 1 || ngroups > kb200_model::MAXG) return fail_arg("kb200_set_groups: 1..8 groups");
   CK(cudaSetDevice(m->device));
   for (int g = 0; g < ngroups; ++g) {
     if (!m->gstream[g]) CK(cudaStreamCreateWithFlags(&m->gstream[g], cudaStreamNonBlocking));

@@ -114,6 +114,37 @@ struct PredSmallArgs {
   EpiArgs epi;           // outputs / scalars (fdot, udot, ssq unused)
 };
 
+// KPLS assembly from cached projected-distance planes (kb200_kpls.cu)
+struct KplsAsmArgs {
+  int n, h, nkernel, add_eps;
+  int kid[MAXK];
+  long tiles_per_mat;
+  const double* planes_sq;   // [h][tiles_per_mat] tiles: sum_k (dx_k)^2 pls_kc^2   (gaussian) or null
+  const double* planes_abs;  // [h][tiles_per_mat] tiles: sum_k |dx_k| pls_kc       (exponential) or null
+  const double* cand;        // [P][cand_stride]
+  int cand_stride;
+  double* out;               // [P][tiles_per_mat] tiles
+};
+cudaError_t launch_kpls_planes(const double* X, int n, int d, int h, const double* coef, int absmode, double* planes,
+                               long tiles_per_mat, cudaStream_t st);
+cudaError_t launch_kpls_assemble(const KplsAsmArgs& a, int P, cudaStream_t st);
+
+// 2-objective EHVI (kb200_ehvi.cu)
+struct EhviArgs {
+  int k;                       // Pareto points
+  double r0, r1;               // reference point
+  const double* S;             // [k][2] front sorted on objective 1
+  const double* c2;            // [k] objective-2 values ascending
+  const double* splus;         // [(k+1)][(k+1)] dominated hyper-volume per cell
+  const double *mu0, *mu1, *s0, *s1;   // candidate i at index i * inc
+  long inc;
+  double sign;                 // +1: exi2d, -1: ehvicalc_vec's -exi2d
+  double* out;                 // [npop]
+};
+cudaError_t launch_ehvi_tables(const double* P, int k, double r0, double r1, double* S, double* c2, double* splus,
+                               cudaStream_t st);
+cudaError_t launch_ehvi_score(const EhviArgs& a, long npop, cudaStream_t st);
+
 cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st);
 constexpr int AK_BLOCKS = 592;          // 4 x 148
 constexpr int AK_PARTIAL_BYTES = 40;    // {double min_u; long long arg; unsigned long long c0, cm, cp;}

@@ -122,9 +122,44 @@ def c2_anchor(ref):
     print("c2_anchor.npz KAT", repr(kat))
 
 
+def ehvi_fronts():
+    """Deterministic Pareto fronts + candidates of the EHVI goldens (shared with the tests)."""
+    rng = np.random.default_rng(2024)
+    cases = []
+    for k in (1, 2, 5, 13, 40):
+        a = np.sort(rng.uniform(0, 1, k))
+        b = np.sort(rng.uniform(0, 1, k))[::-1]
+        P = np.c_[a, b][rng.permutation(k)]          # non-dominated, rows shuffled
+        r = np.array([1.2, 1.3])
+        mu = np.vstack([rng.uniform(-0.2, 1.4, (10, 2)), P[:2] + 1e-3, [[1.5, 1.6]]])   # inside, on the front, beyond r
+        s = np.vstack([rng.uniform(1e-3, 0.5, (10, 2)), np.full((len(mu) - 10, 2), 0.05)])
+        cases.append((P, r, mu, s))
+    return cases
+
+
+def ehvi2d():
+    """exi2d outputs of the live reference (kadal/optim_tools/ehvi/exi2d.py) — SURVEY.md §8 f1."""
+    import warnings
+    ref_loader._ensure_path()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from kadal.optim_tools.ehvi.exi2d import exi2d
+    out = {}
+    for c, (P, r, mu, s) in enumerate(ehvi_fronts()):
+        out["P%d" % c], out["r%d" % c], out["mu%d" % c], out["s%d" % c] = P, r, mu, s
+        out["v%d" % c] = np.array([exi2d(P, r, mu[i], s[i]) for i in range(len(mu))])
+    out["ncases"] = len(ehvi_fronts())
+    np.savez_compressed(os.path.join(HERE, "ehvi2d.npz"), **out)
+    print("ehvi2d.npz", [float(out["v%d" % c].max()) for c in range(out["ncases"])])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ehvi":
+        ehvi2d()
+        sys.exit(0)
     ref = ref_loader.load()
     appendix_c(ref)
     c3_like(ref)
     std_norm(ref)
     c2_anchor(ref)
+    ehvi2d()

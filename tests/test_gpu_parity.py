@@ -301,6 +301,40 @@ def test_kpls_and_composite_population(kb):
     assert relerr(nll3, ref3) < TOL_NLL
 
 
+def test_kpls_plane_cache_is_bit_identical_to_on_the_fly_assembly(kb, monkeypatch):
+    """KPLS distances sum_k g(dx_k) pls_kc do not depend on theta (kernelfunc.py:41-47, 58-64): the
+    library caches the h planes per model and assembles every candidate's Psi from them.  Same
+    operations in the same order as the on-the-fly kernel -> bit-identical Psi and NLL; both against
+    the oracle for gaussian, exponential (signed pls) and a gaussian+exponential composite."""
+    from kadal_b200.model import GpuModel
+    rng = np.random.default_rng(18)
+    n, d, h = 300, 14, 3
+    X = rng.uniform(-1, 1, (n, d))
+    y = (X[:, :4].sum(1) ** 2)[:, None] + 3
+    pls = np.abs(rng.standard_normal((d, h))) / 3     # positive: the exponential KPLS kernel stays PD
+    pop = rng.uniform(-0.3, 0.8, (6, h))
+    for kernels, extra in ((("gaussian",), 0), (("exponential",), 0), (("gaussian", "exponential"), 2)):
+        info = ko.make_kriginfo(X, y, kernel=kernels, pls=pls, n_princomp=h)
+        pp = np.hstack([pop, rng.uniform(0.2, 1, (6, extra))]) if extra else pop
+        ref = ko.likelihood_population(pp, copy.deepcopy(info), False, check_pd=False)
+        kids = [{"gaussian": 0, "exponential": 1}[k] for k in kernels]
+        res = {}
+        for on in ("1", "0"):
+            monkeypatch.setenv("KB200_KPLS_PLANES", on)
+            gm = GpuModel(X, y, np.ones((n, 1)), kids, pls=pls)
+            nll, inf = gm.lik_batch(pp, False, -6.0)
+            psi = gm.debug_psi(pp[0], False, -6.0)
+            res[on] = (nll, psi)
+            assert not inf.any()
+            gm.close()
+        assert np.array_equal(res["1"][0], res["0"][0]) and np.array_equal(res["1"][1], res["0"][1])
+        A = copy.deepcopy(info)
+        ko.likelihood(pp[0].copy(), A, "all", False, check_pd=False)
+        assert np.max(np.abs(res["1"][1] - A["Psi"])) < 1e-14
+        conds = conds_of(info, pp)
+        assert all(relerr(a, b) < nll_tol(c) for a, b, c in zip(res["1"][0], ref, conds))
+
+
 # ------------------------------------------------------------------ drop-in classes (BASELINE config 1)
 def _branin(X):
     a, b, c, r, s, t = 1.0, 5.1 / (4 * np.pi ** 2), 5 / np.pi, 6.0, 10.0, 1 / (8 * np.pi)
