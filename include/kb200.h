@@ -113,6 +113,17 @@ int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int nor
                        const double* norm_a, const double* norm_b, double* min_u,
                        long long* argmin_u, unsigned long long* counts);
 
+/* Saltelli sums for Sobol indices without shipping predictions back
+ * (sensitivity_analysis/sobol_ind.py:45-141): A, B are the two [N][d] sample matrices (host), set q
+ * builds C_q = B with the columns k where from_a[q*d + k] != 0 taken from A (one column: first /
+ * total order :108-109; two columns: second order :152-154).  With ya, yb, yc_q the 'pred' outputs
+ * on A, B, C_q:  base = {sum ya, sum ya^2, sum yb, sum yb^2},  ya_yc[q] = sum ya*yc_q,
+ * yb_yc[q] = sum yb*yc_q.  The caller forms fo_2, denom and the indices (:84-85, :136-139, :180-182);
+ * under data parallelism every rank passes its row shard and the sums are added. */
+int kb200_sobol_sums(kb200_model* m, const double* A, const double* B, long long N, int normtype,
+                     const double* norm_a, const double* norm_b, const unsigned char* from_a, int nsets,
+                     double* base, double* ya_yc, double* yb_yc);
+
 /* 2-objective expected hyper-volume improvement of npop candidates over a Pareto front
  * (optim_tools/ehvi/exi2d.py:7-84 as called by EHVIcomputation.py:57 and :169-175): pareto is
  * [k][2] row-major (any order, k <= 1022), ref the reference point, candidate i has means

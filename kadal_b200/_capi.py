@@ -57,6 +57,8 @@ SIGNATURES = {
     "kb200_loocv": (ctypes.c_int, [c_void_p, c_void_p]),
     "kb200_akmcs_reduce": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
                                           c_double_p, ctypes.POINTER(ctypes.c_longlong), c_u64_p]),
+    "kb200_sobol_sums": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
+                                        c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p]),
     "kb200_ehvi2d": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p,
                                     ctypes.c_longlong, ctypes.c_double, c_void_p]),
     "kb200_ehvi2d_dev": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -89,6 +89,7 @@ struct kb200_model {
   cudaEvent_t ev_fork = nullptr, ev_join[MAXG] = {nullptr};
   int group_min = 32;   // fewest candidates per group
   DevBuf norm_a, norm_b, stats, akpart;
+  DevBuf sobB, sobC, sobY, sobAcc, sobPart, sobMask;
   unsigned long long launches = 0;
   size_t ws_cap_bytes = 0;
   // optional per-kernel-class event timing (kb200_profile_*)
@@ -257,7 +258,8 @@ void kb200_model_destroy(kb200_model* m) {
   DevBuf* bufs[] = {&m->X, &m->R, &m->pls, &m->pls2, &m->kplanes_sq, &m->kplanes_abs, &m->tiles, &m->W, &m->Z, &m->cand, &m->xdev,
                     &m->nll, &m->info, &m->logdet, &m->sigma2, &m->beta, &m->btb, &m->resid,
                     &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand,
-                    &m->norm_a, &m->norm_b, &m->stats, &m->akpart};
+                    &m->norm_a, &m->norm_b, &m->stats, &m->akpart,
+                    &m->sobB, &m->sobC, &m->sobY, &m->sobAcc, &m->sobPart, &m->sobMask};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < 2; ++s) {
     PredSlot& sl = m->slot[s];
@@ -981,6 +983,62 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
 }  // extern "C"
 
 extern "C" {
+
+// ------------------------------------------------- Saltelli sums
+int kb200_sobol_sums(kb200_model* m, const double* A, const double* B, long long N, int normtype,
+                     const double* norm_a, const double* norm_b, const unsigned char* from_a, int nsets,
+                     double* base, double* ya_yc, double* yb_yc) {
+  if (!m || !A || !B || !base || (nsets > 0 && (!from_a || !ya_yc || !yb_yc)))
+    return fail_arg("kb200_sobol_sums: null argument");
+  if (N < 1 || nsets < 0) return fail_arg("kb200_sobol_sums: empty sample");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = m->stream;
+  double* dummy[7] = {(double*)1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rc = predict_prepare(m, normtype, norm_a, norm_b, KB200_OUT_PRED, dummy, st);
+  if (rc) return rc;
+  const long sc = std::min<long>((long)N, 1L << 18);
+  const size_t cb = (size_t)sc * m->d * 8;
+  PredSlot& sl = m->slot[0];
+  CK(sl.x.reserve(cb));
+  CK(m->sobB.reserve(cb));
+  CK(m->sobC.reserve(cb));
+  CK(m->sobY.reserve((size_t)3 * sc * 8));
+  CK(m->sobAcc.reserve((size_t)(4 + 2 * nsets) * 8));
+  CK(m->sobPart.reserve((size_t)2 * SOBOL_BLOCKS * 8));
+  CK(m->sobMask.reserve((size_t)std::max(1, nsets) * m->d));
+  if (nsets) CK(cudaMemcpyAsync(m->sobMask.p, from_a, (size_t)nsets * m->d, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(m->sobAcc.p, 0, (size_t)(4 + 2 * nsets) * 8, st));
+  double *ya = m->sobY.d(), *yb = ya + sc, *yc = yb + sc, *acc = m->sobAcc.d(), *part = m->sobPart.d();
+  const unsigned char* masks = static_cast<const unsigned char*>(m->sobMask.p);
+  for (long p0 = 0; p0 < N; p0 += sc) {
+    const long np = std::min<long>(sc, (long)N - p0);
+    CK(cudaMemcpyAsync(sl.x.p, A + (size_t)p0 * m->d, (size_t)np * m->d * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->sobB.p, B + (size_t)p0 * m->d, (size_t)np * m->d * 8, cudaMemcpyHostToDevice, st));
+    double* outs[7] = {ya, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    rc = predict_core(m, sl, sl.x.d(), np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
+    if (rc) return rc;
+    outs[0] = yb;
+    rc = predict_core(m, sl, m->sobB.d(), np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
+    if (rc) return rc;
+    CK(launch_sobol_dot(ya, nullptr, nullptr, np, 1, part, acc + 0, acc + 1, st));
+    CK(launch_sobol_dot(yb, nullptr, nullptr, np, 1, part, acc + 2, acc + 3, st));
+    m->launches += 4;
+    for (int q = 0; q < nsets; ++q) {
+      CK(launch_sobol_compose(sl.x.d(), m->sobB.d(), masks + (size_t)q * m->d, np, m->d, m->sobC.d(), st));
+      outs[0] = yc;
+      rc = predict_core(m, sl, m->sobC.d(), np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
+      if (rc) return rc;
+      CK(launch_sobol_dot(ya, yb, yc, np, 0, part, acc + 4 + 2 * q, acc + 5 + 2 * q, st));
+      m->launches += 3;
+    }
+  }
+  std::vector<double> h((size_t)4 + 2 * nsets);
+  CK(cudaMemcpyAsync(h.data(), acc, h.size() * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < 4; ++i) base[i] = h[i];
+  for (int q = 0; q < nsets; ++q) { ya_yc[q] = h[4 + 2 * q]; yb_yc[q] = h[5 + 2 * q]; }
+  return 0;
+}
 
 // ---------------------------------------------------------------- EHVI
 static int ehvi_core(int device, const double* d_pareto, int k, const double* ref, const double* mu0,

@@ -145,6 +145,13 @@ cudaError_t launch_ehvi_tables(const double* P, int k, double r0, double r1, dou
                                cudaStream_t st);
 cudaError_t launch_ehvi_score(const EhviArgs& a, long npop, cudaStream_t st);
 
+// Saltelli sums (kb200_sobol.cu)
+constexpr int SOBOL_BLOCKS = 296;       // 2 x 148
+cudaError_t launch_sobol_compose(const double* A, const double* B, const unsigned char* from_a, long n, int d, double* C,
+                                 cudaStream_t st);
+cudaError_t launch_sobol_dot(const double* u, const double* v, const double* w, long n, int mode, double* partial,
+                             double* acc0, double* acc1, cudaStream_t st);
+
 cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t st);
 constexpr int AK_BLOCKS = 592;          // 4 x 148
 constexpr int AK_PARTIAL_BYTES = 40;    // {double min_u; long long arg; unsigned long long c0, cm, cp;}
