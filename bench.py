@@ -342,12 +342,23 @@ def run_ours(args, rank, local_rank, world):
     # algorithmic flops per launch class -> achieved TFLOP/s of each kernel
     # the panel kernel now also carries the diagonal tiles j >= 1 (SYRK, POTF2, forward substitution)
     diag0 = P * (128.0 ** 3 / 3.0 + 2 * 128.0 * 128.0)
-    cls_flops = {"assemble": assemble_flops(N_C2, D_C2, P), "chol_diag": diag0,
-                 "chol_panel": chol_panel_flops(N_C2, P) + chol_diag_flops(N_C2, P) - diag0}
-    cls_name = {"assemble": "corr_tile_kernel (Psi assembly, fp64 FMA pipe + exp)",
-                "chol_diag": "chol_diag_kernel (diagonal tile 0: blocked in-smem POTF2)",
-                "chol_panel": "chol_panel_kernel (fp64 DMMA GEMM + right-looking DMMA TRSM; CTA (j+1,j) also does the "
-                              "SYRK + blocked POTF2 + forward substitution of diagonal tile j+1)"}
+    nt_c2 = (N_C2 + 127) // 128
+    half_path = prof["chol_diag"][1] >= nt_c2 * args.steps      # one diagonal launch per tile column
+    if half_path:
+        cls_flops = {"assemble": assemble_flops(N_C2, D_C2, P), "chol_diag": chol_diag_flops(N_C2, P),
+                     "chol_panel": chol_panel_flops(N_C2, P)}
+        cls_name = {"assemble": "corr_tile_kernel (Psi assembly, fp64 FMA pipe + exp)",
+                    "chol_diag": "chol_diag_half_kernel (half-SM CTA per diagonal tile: DMMA SYRK over the tile row, fused "
+                                 "forward substitution, blocked POTF2 on a packed triangle)",
+                    "chol_panel": "chol_panel_half_kernel (half-SM CTAs, two per SM: 64 x 128 block of tile (i,j), fp64 DMMA "
+                                  "GEMM + right-looking DMMA TRSM against the fully resident L_jj)"}
+    else:
+        cls_flops = {"assemble": assemble_flops(N_C2, D_C2, P), "chol_diag": diag0,
+                     "chol_panel": chol_panel_flops(N_C2, P) + chol_diag_flops(N_C2, P) - diag0}
+        cls_name = {"assemble": "corr_tile_kernel (Psi assembly, fp64 FMA pipe + exp)",
+                    "chol_diag": "chol_diag_kernel (diagonal tile 0: blocked in-smem POTF2)",
+                    "chol_panel": "chol_panel_kernel (fp64 DMMA GEMM + right-looking DMMA TRSM; CTA (j+1,j) also does the "
+                                  "SYRK + blocked POTF2 + forward substitution of diagonal tile j+1)"}
     per_kernel = {}
     for k, fl in cls_flops.items():
         ms_k, cnt_k = prof[k]

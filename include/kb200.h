@@ -154,6 +154,10 @@ int kb200_debug_psi(kb200_model* m, const double* x, int nbhyp, int trainvar,
                     double nugget_log10, int add_eps, double* Psi);
 
 
+/* debug / parity: raw tile storage (tile-major layout of DESIGN.md section 3) of candidate `cand` of the
+ * last likelihood batch: tiles_per_mat * 16384 doubles */
+int kb200_debug_tiles(kb200_model* m, int cand, double* out);
+
 /* Per-kernel-class device timing with CUDA events on the launching stream (bench.py's
  * roofline): enable, run, then read accumulated milliseconds and launch counts. */
 #define KB200_PROF_ASSEMBLE 0   /* corr_tile_kernel, Psi assembly            */

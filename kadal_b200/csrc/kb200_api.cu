@@ -73,6 +73,7 @@ struct kb200_model {
   // KPLS: hyper-parameter independent projected-distance planes (kb200_kpls.cu), built on first use
   DevBuf kplanes_sq, kplanes_abs;
   bool kplanes_ready = false, kplanes_on = true;
+  int half_mode = -1;       // half-SM factorisation kernels (kb200_half.cu): -1 auto, 0 off, 1 on
   cudaStream_t stream = nullptr;
   // likelihood workspace
   DevBuf tiles, W, Z, cand, xdev, nll, info, logdet, sigma2, beta, btb, resid, rhs2, sol2;
@@ -236,6 +237,8 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
     MCK(cudaMemcpy(m->pls2.p, p2.data(), p2.size() * 8, cudaMemcpyHostToDevice));
   }
   {
+    const char* eh = getenv("KB200_HALF");
+    if (eh) m->half_mode = atoi(eh) != 0 ? 1 : 0;
     const char* ek = getenv("KB200_KPLS_PLANES");
     if (ek && atoi(ek) == 0) m->kplanes_on = false;
   }
@@ -404,6 +407,26 @@ static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z
                      int* info, cudaStream_t st) {
   CholArgs a = chol_args(m, tiles, W, Z, logdet, info);
   a.fuse_diag = a.naive ? 0 : 1;
+  // Half-SM kernels (kb200_half.cu, two CTAs per SM) up to 16 tiles per dimension; for larger matrices the
+  // per-candidate critical path (one half-SM CTA per diagonal tile) decides and the full-SM kernels with
+  // the diagonal work fused into the panel CTA are faster (C5, n = 4000, P = 16: 18.5 vs 21.1 ms,
+  // profiles/r1k_half.md).  The choice depends on the model only, never on the batch size: any sub-batch
+  // of a population is bit-identical to the full batch.  $KB200_HALF = 0 / 1 forces one path.
+  const bool use_half = !a.naive && (m->half_mode == 1 || (m->half_mode < 0 && m->nt <= 16));
+  if (use_half) {
+    a.fuse_diag = 0;
+    for (int j = 0; j < m->nt; ++j) {
+      {
+        Timed t(m, KB200_PROF_DIAG, st);
+        CK(launch_chol_diag_half(a, j, Pb, st));
+      }
+      if (j + 1 < m->nt) {
+        Timed t(m, KB200_PROF_PANEL, st);
+        CK(launch_chol_panel_half(a, j, 2 * (m->nt - 1 - j), Pb, st));
+      }
+    }
+    return 0;
+  }
   for (int j = 0; j < m->nt; ++j) {
     if (j == 0 || !a.fuse_diag) {
       Timed t(m, KB200_PROF_DIAG, st);
@@ -789,7 +812,8 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     }
     for (int j = 0; j < m->nt; ++j) {
       Timed t(m, KB200_PROF_PREDSOLVE, st);
-      CK(launch_chol_panel(pa, j, tiles, 1, st));
+      if (m->half_mode == 1 && !pa.naive) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // (no gain measured)
+      else CK(launch_chol_panel(pa, j, tiles, 1, st));
     }
     EpiArgs ee = e;
     ee.npts = np; ee.fdot = sl.fdot.d() + p0; ee.udot = sl.udot.d() + p0; ee.ssq = sl.ssq.d();
@@ -830,7 +854,8 @@ extern "C" int kb200_loocv(kb200_model* m, double* loo) {
     m->launches++;
     for (int j = 0; j < m->nt; ++j) {
       Timed t(m, KB200_PROF_PREDSOLVE, st);
-      CK(launch_chol_panel(pa, j, tiles, 1, st));
+      if (m->half_mode == 1 && !pa.naive) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // (no gain measured)
+      else CK(launch_chol_panel(pa, j, tiles, 1, st));
     }
     CK(launch_loo(m->R.d(), m->palpha.d(), m->pw.d(), sl.ssq.d(), m->pbtb, m->n, p0, (int)np, sl.out[0].d(), st));
     m->launches++;
@@ -1104,6 +1129,16 @@ int kb200_ehvi2d(int device, const double* pareto, int k, const double* ref, con
   cudaFree(buf);
   cudaStreamDestroy(st);
   return rc;
+}
+
+// debug: raw tile storage of candidate `cand` of the last likelihood batch (tiles_per_mat * 16384 doubles)
+int kb200_debug_tiles(kb200_model* m, int cand, double* out) {
+  if (!m || !out) return fail_arg("kb200_debug_tiles: null argument");
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, m->tiles.d() + (size_t)cand * m->tiles_per_mat * TILE_ELEMS,
+                (size_t)m->tiles_per_mat * TILE_ELEMS * 8, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int kb200_set_groups(kb200_model* m, int ngroups) {

@@ -1,0 +1,712 @@
+// kadal_b200 — half-SM factorisation kernels (two CTAs per SM).
+//
+// The full-tile kernels of kb200_kernels.cu own an SM each (512 threads x 128 registers, 208 KiB
+// of shared memory), so every phase of a CTA that is not tensor-pipe bound -- pipeline fill, the
+// C tile fetch, the dependency chains of the triangular solve, the strictly sequential pivots of
+// POTF2 (about 40 us per diagonal tile), the stores -- leaves the FP64 datapath of that SM idle
+// (ncu r1i: 40-74 % DMMA pipe utilisation per launch).  Here every CTA is half an SM:
+//
+//   chol_panel_half_kernel  256 threads, 104 KiB: 64 rows x 128 columns of tile (i,j):
+//                           X = (Psi_ij - L_i,0..j-1 L_j,0..j-1^T) L_jj^-T.  Rows of a triangular
+//                           solve are independent, so the two halves of a tile never talk.
+//                           (also prediction: 64 points x one sample tile)
+//   chol_diag_half_kernel   256 threads, ~100 KiB: diagonal tile j: SYRK over the tile row
+//                           (8 warps x 17 of the 136 lower 8x8 tiles: row blocks w and 15-w),
+//                           fused forward substitution of [y F], blocked POTF2 on a PACKED lower
+//                           triangle (66 KiB instead of 132), 8x8 inverse blocks, log-det.
+//
+// Two of them are resident per SM (of the same or of different launches / candidate groups), so the
+// warp schedulers always have tensor-pipe work from one CTA while the other is in a latency-bound
+// phase.  Same data layout, same arithmetic per element as the full-tile kernels (the GEMM core,
+// the right-looking 8x8-inverse TRSM and the blocked POTF2 are the same algorithms).
+// Reference call sites replaced: likelihood_func.py:168-213 (maincalc), prediction.py:245-251.
+#include <cmath>
+#include "kb200_kernels.h"
+
+namespace kb200 {
+namespace {
+
+constexpr int HT = 256;                       // threads per CTA
+constexpr int HWARPS = HT / 32;
+constexpr int HROWS = 64;                     // rows of a half tile
+constexpr int HALF_SLAB = HROWS * KS;         // 1024 doubles = 8 KiB
+constexpr uint32_t HALF_BYTES = HALF_SLAB * 8;
+constexpr int HNST = 4;                       // GEMM ring: stage = A half slab + B slab = 24 KiB
+constexpr int HSTAGE = HALF_SLAB + SLAB_ELEMS;
+constexpr int HLOOK = HNST - 2;
+constexpr int DNST = 5;                       // SYRK ring of the diagonal kernel: one 16 KiB slab per stage
+constexpr int DLOOK = DNST - 2;
+constexpr int TLD = TB + 4;
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+struct WarpPos {
+  int wm, wn, g, t;
+};
+
+__device__ __forceinline__ int half_off(int r, int c) {   // element (r, c) of a 64 x 128 half tile in shared memory
+  return (c >> 4) * HALF_SLAB + r * KS + ((((c >> 2) & 3) ^ (r & 3)) << 2) + (c & 3);
+}
+__device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }   // packed lower triangle: S[tri(r) + c]
+
+// C-fragment (c0,c1 = T[g][2t], T[g][2t+1]) of an 8x8 tile -> its two A-fragments (T[g][t], T[g][4+t])
+__device__ __forceinline__ void cfrag_to_afrag(double c0, double c1, double& a0, double& a1, int lane) {
+  const int src0 = (lane & ~3) + ((lane & 3) >> 1);
+  const double v00 = __shfl_sync(FULLMASK, c0, src0), v01 = __shfl_sync(FULLMASK, c1, src0);
+  const double v10 = __shfl_sync(FULLMASK, c0, src0 + 2), v11 = __shfl_sync(FULLMASK, c1, src0 + 2);
+  a0 = (lane & 1) ? v01 : v00;
+  a1 = (lane & 1) ? v11 : v10;
+}
+
+// sqrt(x), 1/(2 sqrt(x)) of a positive normal double (same sequence as the full-tile kernels)
+__device__ __forceinline__ void sqrt_rsqrt(double x, double& s, double& h_out) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double t = x * y, h = 0.5 * y;
+  double e = fma(-t, h, 0.5);
+  t = fma(t, e, t);
+  h = fma(h, e, h);
+  e = fma(-t, h, 0.5);
+  t = fma(t, e, t);
+  h = fma(h, e, h);
+  s = fma(fma(-t, t, x), h, t);
+  h_out = h;
+}
+
+// ------------------------------------------------------------------ GEMM core (8 warps: 2 x 4 of 32x32)
+__device__ __forceinline__ void mma_slab_h(double (&acc)[4][4][2], const double* As, const double* Bs, const WarpPos& w) {
+#pragma unroll
+  for (int kq = 0; kq < 4; ++kq) {
+    const int sw = ((kq ^ (w.g & 3)) << 2) + w.t;
+    double a[4], b[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) a[mt] = As[(32 * w.wm + 8 * mt + w.g) * KS + sw];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[(32 * w.wn + 8 * nt + w.g) * KS + sw];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+
+// ------------------------------------------------------------------ POTF2 on a packed lower triangle
+// warp-level Cholesky of the 32x32 block at (o, o): lane r owns row o + r in registers; column k is
+// broadcast through lbuf (2 x 32 doubles).  dinv[k] = 1 / L_kk.  Returns first bad pivot + 1 or 0.
+__device__ __noinline__ int potf2_32_warp_t(double* S, int o, double* dinv, double* lbuf, int lane) {
+  double a[32];
+  double* row = S + tri(o + lane) + o;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? row[c] : 0.0;
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    double piv = __shfl_sync(FULLMASK, a[k], k);
+    const bool ok = piv > 0.0;
+    bad = (!ok && bad == 0) ? o + k + 1 : bad;
+    piv = ok ? piv : 1.0;
+    const double a2 = a[k] + a[k];
+    double dk, h;
+    sqrt_rsqrt(piv, dk, h);
+    const double l = a2 * h;
+    double* lb = lbuf + (k & 1) * 32;
+    lb[lane] = l;
+    __syncwarp();
+#pragma unroll
+    for (int c = k + 1; c < 32; ++c) a[c] = fma(-l, lb[c], a[c]);
+    a[k] = (lane == k) ? dk : l;
+    if (lane == k) dinv[o + k] = h + h;
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c <= lane) row[c] = a[c];
+  return bad;
+}
+
+// inverses of the four 8x8 diagonal sub-blocks of the 32x32 block at (o, o); out: 4 x 64 doubles
+__device__ __forceinline__ void inv8_warp_t(const double* S, int o, const double* dinv, double* out, int lane) {
+  const int blk = lane >> 3, c = lane & 7;
+  const int r0 = o + 8 * blk;
+  double w[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const double* Lr = S + tri(r0 + r) + r0;
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < r; ++t) s = fma(Lr[t], w[t], s);
+    w[r] = ((r == c) ? 1.0 : -s) * dinv[r0 + r];
+    if (r < c) w[r] = 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) out[blk * 64 + r * 8 + c] = w[r];
+}
+
+// one 8-row strip against the 32x32 block at (o, o): rows <- rows * L_kk^-T (right-looking, DMMA).
+// xrow: this lane's row (row g of the strip) at column o.
+__device__ __forceinline__ void strip_trsm32_t(double* xrow, const double* S, int o, const double* W8, int lane) {
+  const int g = lane >> 2, tq = lane & 3;
+  double x[4][2];
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) {
+    x[ct][0] = xrow[8 * ct + 2 * tq];
+    x[ct][1] = xrow[8 * ct + 2 * tq + 1];
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    double a0, a1;
+    cfrag_to_afrag(x[t][0], x[t][1], a0, a1, lane);
+    double y0 = 0.0, y1 = 0.0;
+    dmma884(y0, y1, a0, W8[t * 64 + g * 8 + tq]);
+    dmma884(y0, y1, a1, W8[t * 64 + g * 8 + 4 + tq]);
+    x[t][0] = y0;
+    x[t][1] = y1;
+    if (t < 3) {
+      cfrag_to_afrag(y0, y1, a0, a1, lane);
+      a0 = -a0;
+      a1 = -a1;
+#pragma unroll
+      for (int ct = t + 1; ct < 4; ++ct) {
+        const double* Lr = S + tri(o + 8 * ct + g) + o + 8 * t + tq;
+        dmma884(x[ct][0], x[ct][1], a0, Lr[0]);
+        dmma884(x[ct][0], x[ct][1], a1, Lr[4]);
+      }
+    }
+  }
+#pragma unroll
+  for (int ct = 0; ct < 4; ++ct) {
+    xrow[8 * ct + 2 * tq] = x[ct][0];
+    xrow[8 * ct + 2 * tq + 1] = x[ct][1];
+  }
+}
+
+// trailing update after the 32-wide panel at column o: items it0 <= it < it1 of "lower 16x16 blocks in
+// row-major triangular order, then the RHS 8x16 blocks", warp `widx` of `nw`.
+__device__ __forceinline__ void trailing_update32_t(double* S, double* trow, int o, int it0, int it1, int widx, int nw,
+                                                    int lane) {
+  const int g = lane >> 2, tq = lane & 3;
+  const int base = o + 32;
+  const int nb = (TB - base) >> 4;
+  const int ntri = nb * (nb + 1) / 2;
+  const int nitems = ntri + nb;
+  if (it1 > nitems) it1 = nitems;
+  for (int it = it0 + widx; it < it1; it += nw) {
+    if (it < ntri) {
+      int bi = 0;
+      while ((bi + 1) * (bi + 2) / 2 <= it) ++bi;
+      const int bj = it - bi * (bi + 1) / 2;
+      double* ar0 = S + tri(base + 16 * bi + g);
+      double* ar1 = S + tri(base + 16 * bi + g + 8);
+      const double* br0 = S + tri(base + 16 * bj + g);
+      const double* br1 = S + tri(base + 16 * bj + g + 8);
+      const int cc = base + 16 * bj + 2 * tq;
+      double c[2][2][2];
+      // (bi == bj: the columns cc + 8.. of row block 0 lie above the diagonal -> not stored, not loaded)
+      const bool up = bi > bj;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const bool ok0 = up || nt == 0;
+        c[0][nt][0] = ok0 ? ar0[cc + 8 * nt] : 0.0;
+        c[0][nt][1] = ok0 ? ar0[cc + 8 * nt + 1] : 0.0;
+        c[1][nt][0] = ar1[cc + 8 * nt];
+        c[1][nt][1] = ar1[cc + 8 * nt + 1];
+      }
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) {
+        const int kc = o + 4 * kq + tq;
+        const double a0 = -ar0[kc], a1 = -ar1[kc];
+        const double b0 = br0[kc], b1 = br1[kc];
+        dmma884(c[0][0][0], c[0][0][1], a0, b0);
+        dmma884(c[0][1][0], c[0][1][1], a0, b1);
+        dmma884(c[1][0][0], c[1][0][1], a1, b0);
+        dmma884(c[1][1][0], c[1][1][1], a1, b1);
+      }
+      // entries above the diagonal do not exist in the packed layout: store only c <= r
+      const int r0 = base + 16 * bi + g, r1 = r0 + 8;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int c0 = cc + 8 * nt;
+        if (c0 <= r0) ar0[c0] = c[0][nt][0];
+        if (c0 + 1 <= r0) ar0[c0 + 1] = c[0][nt][1];
+        if (c0 <= r1) ar1[c0] = c[1][nt][0];
+        if (c0 + 1 <= r1) ar1[c0 + 1] = c[1][nt][1];
+      }
+    } else {
+      const int bj = it - ntri;
+      double* ar0 = trow + g * TLD;
+      const double* br0 = S + tri(base + 16 * bj + g);
+      const double* br1 = S + tri(base + 16 * bj + g + 8);
+      const int cc = base + 16 * bj + 2 * tq;
+      double c[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { c[nt][0] = ar0[cc + 8 * nt]; c[nt][1] = ar0[cc + 8 * nt + 1]; }
+#pragma unroll
+      for (int kq = 0; kq < 8; ++kq) {
+        const int kc = o + 4 * kq + tq;
+        const double a0 = -ar0[kc];
+        dmma884(c[0][0], c[0][1], a0, br0[kc]);
+        dmma884(c[1][0], c[1][1], a0, br1[kc]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { ar0[cc + 8 * nt] = c[nt][0]; ar0[cc + 8 * nt + 1] = c[nt][1]; }
+    }
+  }
+}
+
+// Blocked factorisation of the packed tile S with the RHS strip trow (8 x TLD).  All threads call.
+__device__ void potf2_blocked_t(double* S, double* trow, double* dinv, double* W8s, double* lbuf, int* s_bad) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  if (tid == 0) *s_bad = 0;
+  __syncthreads();
+  for (int kb = 0; kb < 4; ++kb) {
+    const int o = 32 * kb;
+    if (warp == 0) {
+      const int b = potf2_32_warp_t(S, o, dinv, lbuf, lane);
+      __syncwarp();
+      inv8_warp_t(S, o, dinv, W8s + kb * 256, lane);
+      if (lane == 0 && b && *s_bad == 0) *s_bad = b;
+    } else if (kb > 0) {
+      trailing_update32_t(S, trow, o - 32, 3, 1 << 20, warp - 1, nwarp - 1, lane);
+    }
+    __syncthreads();
+    const int nrow_strips = (TB - o - 32) >> 3;
+    for (int st = warp; st <= nrow_strips; st += nwarp) {
+      const int g = lane >> 2;
+      if (st < nrow_strips) strip_trsm32_t(S + tri(o + 32 + 8 * st + g) + o, S, o, W8s + kb * 256, lane);
+      else strip_trsm32_t(trow + g * TLD + o, S, o, W8s + kb * 256, lane);
+    }
+    __syncthreads();
+    if (kb < 3) {
+      trailing_update32_t(S, trow, o, 0, 3, warp, nwarp, lane);
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace
+
+// ============================================================================ diagonal tile
+// smem (doubles): [0, DNST*2048) SYRK ring, aliased by the packed S (8256) | trow 8*TLD | dinv 128 |
+//                 W8s 1024 | s_red 16 | lbuf 64 | barriers full[DNST], empty[DNST] | s_bad
+constexpr int D_RING = DNST * SLAB_ELEMS;
+constexpr int D_TROW = D_RING;
+constexpr int D_DINV = D_TROW + 8 * TLD;
+constexpr int D_W8 = D_DINV + TB;
+constexpr int D_RED = D_W8 + 1024;
+constexpr int D_LBUF = D_RED + 16;
+constexpr int D_ZMAXQ = 4;                       // Z tiles are staged in shared memory for nq <= 4
+constexpr int D_ZS = D_LBUF + 64;                // [2][D_ZMAXQ][128] rolling two-tile buffer
+constexpr int D_BAR = D_ZS + 2 * D_ZMAXQ * TB;
+constexpr size_t D_SMEM = (size_t)(D_BAR + 2 * DNST) * 8 + 16;
+static_assert(TB * (TB + 1) / 2 <= D_RING, "packed S must fit in the ring");
+static_assert(D_SMEM <= 113 * 1024, "two diagonal CTAs per SM");
+
+__global__ void __launch_bounds__(HT, 2)
+chol_diag_half_kernel(CholArgs A, int j) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  double* ring = sm;
+  double* S = sm;
+  double* trow = sm + D_TROW;
+  double* dinv = sm + D_DINV;
+  double* W8s = sm + D_W8;
+  double* s_red = sm + D_RED;
+  double* lbuf = sm + D_LBUF;
+  double* zs = sm + D_ZS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + D_BAR);
+  uint64_t* empty = full + DNST;
+  int* s_bad = reinterpret_cast<int*>(empty + DNST);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const long m = blockIdx.x;
+  double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+  const double* rowj = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
+  double* Cjj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
+  const int nq = A.nq;
+  const double* zb = A.Z + (size_t)m * A.nq * A.npad;
+  if (tid == 0) {
+    for (int i = 0; i < DNST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], HWARPS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // ---- SYRK: warp w owns the 8-row blocks hiR = 15 - w (tiles C = 0..hiR) and loR = w (C = 0..w):
+  //      17 of the 136 lower 8x8 tiles each.  acc[u]: u < nhi -> (hiR, u), else (loR, u - nhi).
+  const int hiR = 15 - warp, loR = warp, nhi = hiR + 1;
+  double acc[17][2];
+#pragma unroll
+  for (int u = 0; u < 17; ++u) acc[u][0] = acc[u][1] = 0.0;
+  double tacc[MAXQ];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) tacc[q] = 0.0;
+  const int rr = tid >> 1, hh = tid & 1;     // RHS hook: row rr, columns 8 hh .. 8 hh + 7 of every slab
+
+  const int nslab = NSLAB * j;
+  auto issue = [&](int q) {
+    const int st = q % DNST, use = q / DNST;
+    if (use > 0) mbar_wait(&empty[st], (uint32_t)((use - 1) & 1));
+    mbar_expect_tx(&full[st], SLAB_BYTES);
+    bulk_g2s(ring + (size_t)st * SLAB_ELEMS, rowj + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
+  };
+  if (tid == 0)
+    for (int q = 0; q < DLOOK && q < nslab; ++q) issue(q);
+  const bool zstaged = nq <= D_ZMAXQ;
+  double zreg[2] = {0.0, 0.0};
+  if (zstaged && nslab > 0) {
+    for (int idx = tid; idx < nq * TB; idx += HT) zs[idx] = zb[(size_t)(idx >> 7) * A.npad + (idx & (TB - 1))];
+    __syncthreads();
+  }
+#pragma unroll 1
+  for (int q = 0; q < nslab; ++q) {
+    const int st = q % DNST;
+    if (tid == 0 && q + DLOOK < nslab) issue(q + DLOOK);
+    mbar_wait(&full[st], (uint32_t)((q / DNST) & 1));
+    const double* As = ring + (size_t)st * SLAB_ELEMS;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+      const int sw = ((kq ^ (g & 3)) << 2) + t;
+      const double a_hi = As[(8 * hiR + g) * KS + sw], a_lo = As[(8 * loR + g) * KS + sw];
+#pragma unroll
+      for (int u = 0; u < 17; ++u) {
+        const int C = u < nhi ? u : u - nhi;
+        const double b = As[(8 * C + g) * KS + sw];
+        dmma884(acc[u][0], acc[u][1], u < nhi ? a_hi : a_lo, b);
+      }
+    }
+    // fused forward substitution: tacc[qq] += L_jk[rr][c] * Z_k[c]      (likelihood_func.py:183-193)
+    // Z_k comes from a rolling two-tile shared-memory buffer: tile k + 1 is fetched into registers at the
+    // first slab of tile k and stored at its last slab (the tile-boundary barrier publishes it), so the
+    // L2 latency of Z never sits in front of a slab.  More than D_ZMAXQ right-hand sides: plain loads.
+    {
+      const int tile = q >> 3, sq = q & 7;
+      const bool more = tile + 1 < j;
+      if (zstaged && sq == 0 && more) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int idx = tid + e * HT;
+          if (idx < nq * TB) zreg[e] = zb[(size_t)(idx >> 7) * A.npad + (tile + 1) * TB + (idx & (TB - 1))];
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int chunk = 2 * hh + cc;
+        const double2* lp = reinterpret_cast<const double2*>(As + rr * KS + ((chunk ^ (rr & 3)) << 2));
+        const double2 l01 = lp[0], l23 = lp[1];
+#pragma unroll
+        for (int qq = 0; qq < MAXQ; ++qq) {
+          if (qq < nq) {
+            double z0, z1, z2, z3;
+            if (zstaged) {
+              const double* z = zs + ((tile & 1) * nq + qq) * TB + sq * KS + 4 * chunk;
+              const double2 za = *reinterpret_cast<const double2*>(z), zc = *reinterpret_cast<const double2*>(z + 2);
+              z0 = za.x; z1 = za.y; z2 = zc.x; z3 = zc.y;
+            } else {
+              const double* z = zb + (size_t)qq * A.npad + q * KS + 4 * chunk;
+              z0 = z[0]; z1 = z[1]; z2 = z[2]; z3 = z[3];
+            }
+            double sacc = tacc[qq];
+            sacc = fma(l01.x, z0, sacc); sacc = fma(l01.y, z1, sacc);
+            sacc = fma(l23.x, z2, sacc); sacc = fma(l23.y, z3, sacc);
+            tacc[qq] = sacc;
+          }
+        }
+      }
+      if (zstaged && sq == 7 && more) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int idx = tid + e * HT;
+          if (idx < nq * TB) zs[(((tile + 1) & 1) * nq) * TB + idx] = zreg[e];
+        }
+      }
+    }
+    if (q > 0) {            // release one slab late (see chol_panel_half_kernel)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[(q - 1) % DNST]);
+    }
+    if (zstaged && (q & 7) == 7) __syncthreads();   // tile boundary: publishes the staged Z tile
+  }
+  __syncthreads();        // every warp is done with the ring: S may overwrite it
+
+  // ---- S = Psi_jj - acc (packed lower triangle), t = R_j - tacc
+  for (int idx = tid; idx < 8 * TLD; idx += HT) trow[idx] = 0.0;
+#pragma unroll
+  for (int u = 0; u < 17; ++u) {
+    const int R = u < nhi ? hiR : loR, C = u < nhi ? u : u - nhi;
+    const int r = 8 * R + g, c = 8 * C + 2 * t;
+    const double2 p = *reinterpret_cast<const double2*>(Cjj + tile_off(r, c));
+    if (c <= r) S[tri(r) + c] = p.x - acc[u][0];
+    if (c + 1 <= r) S[tri(r) + c + 1] = p.y - acc[u][1];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int qq = 0; qq < MAXQ; ++qq) {
+    if (qq < nq) {
+      double s = tacc[qq];
+      s += __shfl_xor_sync(FULLMASK, s, 1);
+      if (hh == 0) trow[qq * TLD + rr] = A.R[(size_t)qq * A.npad + j * TB + rr] - s;
+    }
+  }
+  __syncthreads();
+  potf2_blocked_t(S, trow, dinv, W8s, lbuf, s_bad);
+  const int bad = *s_bad;
+  if (tid == 0 && bad && A.info[m] == 0) A.info[m] = j * TB + bad;
+  // ---- outputs: L_jj (tile layout, zeros above the diagonal), 8x8 inverse blocks, Z_j, log-det partial
+  for (int idx = tid; idx < TILE_ELEMS / 4; idx += HT) {
+    const int ch = idx & 3, row = (idx >> 2) & (TB - 1), s = idx >> 9;
+    const int c0 = s * KS + 4 * ch;
+    double l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) l[e] = (c0 + e <= row) ? S[tri(row) + c0 + e] : 0.0;
+    double2* dl = reinterpret_cast<double2*>(Cjj + s * SLAB_ELEMS + row * KS + ((ch ^ (row & 3)) << 2));
+    dl[0] = make_double2(l[0], l[1]);
+    dl[1] = make_double2(l[2], l[3]);
+  }
+  {
+    double* w8 = A.W8 + ((size_t)m * A.nt + j) * 1024;
+    for (int idx = tid; idx < 1024; idx += HT) w8[idx] = W8s[idx];
+  }
+  for (int idx = tid; idx < nq * TB; idx += HT) {
+    const int q = idx >> 7, r = idx & (TB - 1);
+    A.Z[((size_t)m * A.nq + q) * A.npad + j * TB + r] = trow[q * TLD + r];
+  }
+  {
+    double v = (tid < TB) ? log(fabs(S[tri(tid) + tid])) : 0.0;   // padded rows are exactly 1
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int i = 0; i < 4; ++i) s += s_red[i];
+      A.logdet[m] = (j == 0 ? 0.0 : A.logdet[m]) + s;
+    }
+  }
+}
+
+// ============================================================================ panel (half tile)
+// smem (doubles): [0, HNST*HSTAGE) GEMM ring (4 x 24 KiB); afterwards Cs (64 x 128) in [0, 8192) and the
+//   slabs 0, 1 of L_jj in [8192, 12288); once the rows are in registers Cs is dead and the slabs 2..7 of
+//   L_jj -- only their rows >= 16 s, which is all the solve reads -- are packed into [0, 6912).  The
+//   whole factor tile is then resident: one single-use mbarrier per slab, no slot is ever re-filled
+//   while the solve runs and the eight warps drift freely.  W8s at 12288; barriers behind it.
+constexpr int P_CS = HROWS * TB;                       // 8192
+constexpr int P_WS01 = P_CS;                           // slabs 0 and 1, complete
+constexpr int P_W8 = HNST * HSTAGE;                    // 12288
+constexpr int P_BAR = P_W8 + 1024;
+constexpr int P_NBAR = 2 * HNST + NSLAB + 1;           // full, empty, one per L_jj slab, W8
+constexpr size_t P_SMEM = (size_t)(P_BAR + P_NBAR) * 8 + 16;
+static_assert(P_WS01 + 2 * SLAB_ELEMS <= P_W8, "slabs 0, 1 must fit behind Cs");
+static_assert(P_SMEM <= 113 * 1024, "two panel CTAs per SM");
+__host__ __device__ constexpr int wslab_rows(int s) { return TB - KS * s; }           // rows 16 s .. 127
+__host__ __device__ constexpr int wslab_base(int s) {                                  // packed offset, s >= 2
+  int o = 0;
+  for (int q = 2; q < s; ++q) o += wslab_rows(q) * KS;
+  return o;
+}
+static_assert(wslab_base(NSLAB) <= P_CS, "trimmed slabs 2..7 must fit in the dead Cs area");
+
+__global__ void __launch_bounds__(HT, 2)
+chol_panel_half_kernel(CholArgs A, int j) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  double* Cs = stages;
+  double* W8s = stages + P_W8;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + P_BAR);
+  uint64_t* empty = full + HNST;
+  uint64_t* wbar = empty + HNST;        // [NSLAB]
+  uint64_t* w8bar = wbar + NSLAB;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const WarpPos w{warp & 1, warp >> 1, lane >> 2, lane & 3};
+  const int hr = blockIdx.x & 1;                     // which 64 rows of the tile
+  const double *rowA, *rowB, *Ljj, *W8j;
+  double* Cij;
+  long ssq_base = 0;
+  if (A.pred_mode) {
+    const long pt = blockIdx.x >> 1;
+    double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
+    rowA = base;
+    Cij = base + (size_t)j * TILE_ELEMS;
+    rowB = A.L + (size_t)tri_index(j, 0) * TILE_ELEMS;
+    Ljj = A.L + (size_t)tri_index(j, j) * TILE_ELEMS;
+    W8j = A.W8 + (size_t)j * 1024;
+    ssq_base = pt * TB + hr * HROWS;
+  } else {
+    const int i = j + 1 + (blockIdx.x >> 1);
+    const long m = blockIdx.y;
+    double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+    rowA = tiles + (size_t)tri_index(i, 0) * TILE_ELEMS;
+    rowB = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
+    Cij = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;
+    Ljj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
+    W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;
+  }
+  const double* gA = rowA + hr * HALF_SLAB;          // rows 64 hr .. of every slab are 8 KiB contiguous
+  if (tid == 0) {
+    for (int i = 0; i < HNST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], HWARPS); }
+    for (int i = 0; i < NSLAB; ++i) mbar_init(&wbar[i], 1);
+    mbar_init(w8bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(w8bar, 8192);
+    bulk_g2s(W8s, W8j, 8192, w8bar);
+  }
+  __syncthreads();
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  // ---- GEMM: acc = A(64 x 128 j) B(128 x 128 j)^T, operands streamed slab by slab
+  const int nslab = NSLAB * j;
+  auto issue = [&](int q) {
+    const int st = q % HNST, use = q / HNST;
+    if (use > 0) mbar_wait(&empty[st], (uint32_t)((use - 1) & 1));
+    double* dst = stages + (size_t)st * HSTAGE;
+    mbar_expect_tx(&full[st], HALF_BYTES + SLAB_BYTES);
+    bulk_g2s(dst, gA + (size_t)q * SLAB_ELEMS, HALF_BYTES, &full[st]);
+    bulk_g2s(dst + HALF_SLAB, rowB + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
+  };
+  if (tid == 0)
+    for (int q = 0; q < HLOOK && q < nslab; ++q) issue(q);
+#pragma unroll 1
+  for (int q = 0; q < nslab; ++q) {
+    const int st = q % HNST;
+    if (tid == 0 && q + HLOOK < nslab) issue(q + HLOOK);
+    mbar_wait(&full[st], (uint32_t)((q / HNST) & 1));
+    const double* As = stages + (size_t)st * HSTAGE;
+    mma_slab_h(acc, As, As + HALF_SLAB, w);
+    // Consumer release, one slab late: the stage of slab q - 1 is handed back here.  The bulk copy that
+    // re-fills a stage runs in the async proxy and is not ordered behind generic-proxy loads that are
+    // merely *issued* (an arrive right behind the last LDS of slab q let the copy land under pending loads
+    // with two CTAs per SM, profiles/r1k_half_race.md).  Every DMMA of slab q - 1 precedes this point in
+    // the instruction stream, and a DMMA cannot issue before the loads of its operands have returned, so
+    // nothing of slab q - 1 is still being read.  The ring has a slab of slack for it (refill = slab q - 2).
+    if (q > 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[(q - 1) % HNST]);
+    }
+  }
+  fence_proxy_async();
+  __syncthreads();       // ring drained: Cs and the first two L_jj slabs may overwrite it
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_expect_tx(&wbar[s], SLAB_BYTES);
+      bulk_g2s(stages + P_WS01 + s * SLAB_ELEMS, Ljj + (size_t)s * SLAB_ELEMS, SLAB_BYTES, &wbar[s]);
+    }
+  }
+  // ---- C = Psi_ij - acc -> Cs
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
+      const double2 p = *reinterpret_cast<const double2*>(Cij + tile_off(HROWS * hr + r, c));
+      *reinterpret_cast<double2*>(Cs + half_off(r, c)) = make_double2(p.x - acc[mt][nt][0], p.y - acc[mt][nt][1]);
+    }
+  __syncthreads();
+  // ---- every warp takes 8 complete rows (C-fragment layout, 16 column tiles) and solves them
+  const int g = w.g, tq = w.t;
+  const int xr = 8 * warp + g;
+  double x[16][2];
+#pragma unroll
+  for (int ct = 0; ct < 16; ++ct) {
+    const double2 p = *reinterpret_cast<const double2*>(Cs + half_off(xr, 8 * ct + 2 * tq));
+    x[ct][0] = p.x;
+    x[ct][1] = p.y;
+  }
+  // Cs is dead: the rest of L_jj (rows >= 16 s of slab s) goes where it was
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 2; s < NSLAB; ++s) {
+      const uint32_t bytes = (uint32_t)wslab_rows(s) * KS * 8;
+      mbar_expect_tx(&wbar[s], bytes);
+      bulk_g2s(stages + wslab_base(s), Ljj + (size_t)s * SLAB_ELEMS + (size_t)KS * s * KS, bytes, &wbar[s]);
+    }
+  }
+  mbar_wait(w8bar, 0);
+#pragma unroll
+  for (int s = 0; s < NSLAB; ++s) {
+    mbar_wait(&wbar[s], 0);
+    // virtual slab base: row r of slab s at Ls[r * KS + ...] (rows < 16 s of the trimmed slabs are not there)
+    const double* Ls = s < 2 ? stages + P_WS01 + s * SLAB_ELEMS : stages + wslab_base(s) - KS * s * KS;
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt) {
+      const int t = 2 * s + tt;
+      double a0, a1;
+      cfrag_to_afrag(x[t][0], x[t][1], a0, a1, lane);
+      double y0 = 0.0, y1 = 0.0;
+      dmma884(y0, y1, a0, W8s[t * 64 + g * 8 + tq]);
+      dmma884(y0, y1, a1, W8s[t * 64 + g * 8 + 4 + tq]);
+      x[t][0] = y0;
+      x[t][1] = y1;
+      if (t < 15) {
+        cfrag_to_afrag(y0, y1, a0, a1, lane);
+        a0 = -a0;
+        a1 = -a1;
+#pragma unroll
+        for (int ct = t + 1; ct < 16; ++ct) {
+          const double* lrow = Ls + (8 * ct + g) * KS + tq;
+          const double b0 = lrow[((2 * tt) ^ (g & 3)) << 2];
+          const double b1 = lrow[((2 * tt + 1) ^ (g & 3)) << 2];
+          dmma884(x[ct][0], x[ct][1], a0, b0);
+          dmma884(x[ct][0], x[ct][1], a1, b1);
+        }
+      }
+    }
+  }
+  // ---- store X and, for prediction, accumulate ||x_row||^2
+  double rs = 0.0;
+#pragma unroll
+  for (int ct = 0; ct < 16; ++ct) {
+    *reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + xr, 8 * ct + 2 * tq)) = make_double2(x[ct][0], x[ct][1]);
+    rs = fma(x[ct][0], x[ct][0], rs);
+    rs = fma(x[ct][1], x[ct][1], rs);
+  }
+  if (A.pred_mode) {
+    rs += __shfl_xor_sync(FULLMASK, rs, 1);
+    rs += __shfl_xor_sync(FULLMASK, rs, 2);
+    if (tq == 0) {
+      double* dst = A.ssq + ssq_base + xr;
+      *dst = (j == 0 ? 0.0 : *dst) + rs;
+    }
+  }
+}
+
+// ====================================================================== launchers
+static cudaError_t half_attrs() {
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (done[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(chol_diag_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(chol_panel_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
+  if (e != cudaSuccess) return e;
+  // ask for the largest shared-memory carve-out so that two CTAs fit
+  cudaFuncSetAttribute(chol_diag_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(chol_panel_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  done[dev] = true;
+  return cudaSuccess;
+}
+
+cudaError_t launch_chol_diag_half(const CholArgs& a, int j, int nmat, cudaStream_t st) {
+  cudaError_t e = half_attrs();
+  if (e != cudaSuccess) return e;
+  chol_diag_half_kernel<<<nmat, HT, D_SMEM, st>>>(a, j);
+  return cudaGetLastError();
+}
+
+// grid_x = number of (half) tiles: 2 (nt - 1 - j) for the factorisation, 2 x point tiles for prediction
+cudaError_t launch_chol_panel_half(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st) {
+  cudaError_t e = half_attrs();
+  if (e != cudaSuccess) return e;
+  if (grid_x <= 0 || grid_y <= 0) return cudaSuccess;
+  chol_panel_half_kernel<<<dim3(grid_x, grid_y), HT, P_SMEM, st>>>(a, j);
+  return cudaGetLastError();
+}
+
+}  // namespace kb200

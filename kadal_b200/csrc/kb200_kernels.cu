@@ -311,9 +311,18 @@ __device__ __forceinline__ void gemm_stream(double (&acc)[4][4][2], const double
     if (SYRK) syrk_slab(acc, As, w);
     else mma_slab(acc, As, As + SLAB_ELEMS, w);
     on_slab(As, q);
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+    // release one slab late: every DMMA / FMA of slab q - 1 has been issued by now, so its operand loads
+    // have returned and the bulk copy that re-fills the stage cannot land under them (kb200_half.cu)
+    if (q > 0) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[(cur - 1) % NSTAGE]);
+    }
     if (SYRK && (q & 7) == 7) __syncthreads();   // tile boundary: publishes the staged Z tile
+  }
+  if (nslab > 0) {     // hand back the last slab too (a later call continues on the same barriers)
+    fence_proxy_async();
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[(it + nslab - 1) % NSTAGE]);
   }
   it += nslab;
 }
@@ -974,8 +983,8 @@ chol_panel_kernel(CholArgs A, int j) {
       const double2 p = *reinterpret_cast<const double2*>(Cij + off);
       *reinterpret_cast<double2*>(Cs + off) = make_double2(p.x - acc[mt][nt][0], p.y - acc[mt][nt][1]);
     }
-  // (Ws / W8s are refilled by bulk copies after generic-proxy READS only: the CTA barrier below
-  //  orders them, as in any TMA ring; no generic-proxy write is ever read by the async proxy)
+  // (Ws / W8s are refilled by bulk copies after generic-proxy reads: proxy fence + CTA barrier)
+  fence_proxy_async();
   __syncthreads();
 
   if (NAIVE) {
@@ -1037,6 +1046,7 @@ chol_panel_kernel(CholArgs A, int j) {
           }
         }
       }
+      fence_proxy_async();   // generic-proxy reads of this slot before the bulk copy that re-fills it
       __syncthreads();
       if (tid == 0 && s + 2 < NSLAB) {
         mbar_expect_tx(&wfull[stg], SLAB_BYTES);
@@ -1432,7 +1442,7 @@ __global__ void predict_epilogue_kernel(EpiArgs A) {
 // cp.async.bulk ring shared by the 16 warps; the schedule runs ahead across point tiles.
 constexpr int PS_VLD = TB + 4;
 constexpr int PS_NST = 3;
-constexpr int PS_LOOK = 2;
+constexpr int PS_LOOK = 1;    // with the one-slab-late release below the ring needs NST >= LOOK + 2
 constexpr int PS_MAXD = 8;
 
 // sum_k (a_k - b_k)^2 / theta_k^2 for two neighbouring samples, numpy's order for d <= 8
@@ -1558,9 +1568,13 @@ predict_small_kernel(PredSmallArgs A) {
     mbar_wait(&full[st], (uint32_t)((seq / PS_NST) & 1));
     return stages + (size_t)st * SLAB_ELEMS;
   };
+  // release one slab late (entry seq - 1 when the work on entry seq has been issued): its DMMAs precede
+  // this point, so their operand loads have returned before the bulk copy can re-fill the stage
   auto release = [&](int seq) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[seq % PS_NST]);
+    if (seq > 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[(seq - 1) % PS_NST]);
+    }
   };
   if (tid == 0)
     for (int q = 0; q < PS_LOOK && q < total; ++q) issue(q);

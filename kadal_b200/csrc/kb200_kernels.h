@@ -163,6 +163,9 @@ cudaError_t launch_predict_small(const PredSmallArgs& a, int sm_count, cudaStrea
 bool predict_small_supported(int n, int d, int nkernel, int kid0, int kpls);
 cudaError_t launch_chol_diag(const CholArgs& a, int j, int nmat, cudaStream_t st);
 cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);
+// half-SM variants (kb200_half.cu): two CTAs per SM
+cudaError_t launch_chol_diag_half(const CholArgs& a, int j, int nmat, cudaStream_t st);
+cudaError_t launch_chol_panel_half(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);
 cudaError_t launch_w8_from_tiles(const CholArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_finalize(const FinArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_backsolve(const BackArgs& a, cudaStream_t st);
