@@ -87,6 +87,12 @@ struct kb200_model {
   static constexpr int MAXG = 8;
   int ngroups = 2;
   cudaStream_t gstream[MAXG] = {nullptr};
+  // half-SM path: per group a side stream for the panel tiles below row j + 1, so that the diagonal
+  // tile j + 1 (latency-bound POTF2) runs under them (factorize())
+  cudaStream_t gside[MAXG] = {nullptr};
+  cudaEvent_t ev_d[MAXG] = {nullptr}, ev_p[MAXG] = {nullptr};
+  bool dual = false;        // measured: no gain over two candidate groups at P = 512 (8.32 ms both), kept as an option ($KB200_DUAL=1)
+  int dual_env = -1;
   cudaEvent_t ev_fork = nullptr, ev_join[MAXG] = {nullptr};
   int group_min = 32;   // fewest candidates per group
   DevBuf norm_a, norm_b, stats, akpart;
@@ -237,6 +243,8 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
     MCK(cudaMemcpy(m->pls2.p, p2.data(), p2.size() * 8, cudaMemcpyHostToDevice));
   }
   {
+    const char* ed = getenv("KB200_DUAL");
+    if (ed) { m->dual_env = atoi(ed) != 0 ? 1 : 0; m->dual = m->dual_env == 1; }
     const char* eh = getenv("KB200_HALF");
     if (eh) m->half_mode = atoi(eh) != 0 ? 1 : 0;
     const char* ek = getenv("KB200_KPLS_PLANES");
@@ -272,6 +280,9 @@ void kb200_model_destroy(kb200_model* m) {
   }
   for (int g = 0; g < kb200_model::MAXG; ++g) {
     if (m->gstream[g]) cudaStreamDestroy(m->gstream[g]);
+    if (m->gside[g]) cudaStreamDestroy(m->gside[g]);
+    if (m->ev_d[g]) cudaEventDestroy(m->ev_d[g]);
+    if (m->ev_p[g]) cudaEventDestroy(m->ev_p[g]);
     if (m->ev_join[g]) cudaEventDestroy(m->ev_join[g]);
   }
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -404,7 +415,7 @@ static int assemble(kb200_model* m, const double* d_cand, int Pb, double* tiles,
 }
 
 static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z, double* logdet,
-                     int* info, cudaStream_t st) {
+                     int* info, cudaStream_t st, int g = 0) {
   CholArgs a = chol_args(m, tiles, W, Z, logdet, info);
   a.fuse_diag = a.naive ? 0 : 1;
   // Half-SM kernels (kb200_half.cu, two CTAs per SM) up to 16 tiles per dimension; for larger matrices the
@@ -415,15 +426,56 @@ static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z
   const bool use_half = !a.naive && (m->half_mode == 1 || (m->half_mode < 0 && m->nt <= 16));
   if (use_half) {
     a.fuse_diag = 0;
-    for (int j = 0; j < m->nt; ++j) {
+    const int nt = m->nt;
+    if (!m->dual || nt < 3) {
+      for (int j = 0; j < nt; ++j) {
+        {
+          Timed t(m, KB200_PROF_DIAG, st);
+          CK(launch_chol_diag_half(a, j, Pb, st));
+        }
+        if (j + 1 < nt) {
+          Timed t(m, KB200_PROF_PANEL, st);
+          CK(launch_chol_panel_half(a, j, 2 * (nt - 1 - j), Pb, st));
+        }
+      }
+      return 0;
+    }
+    // Two streams per group.  Column j: tile (j+1, j) alone on the main stream ("P_a"), then the diagonal
+    // tile j+1 behind it; the tiles below ("P_b") on the side stream.  D(j+1) -- SYRK plus the strictly
+    // sequential POTF2 -- needs only tile (j+1, j), so it runs co-resident with the tensor-bound P_b(j)
+    // CTAs of its own group instead of after them.  Dependencies: P_b(j) needs D(j) (L_jj) [ev_d];
+    // P_a(j+1) needs the tiles of row j+2 written by P_b(<= j) [ev_p].
+    if (!m->gside[g]) {
+      CK(cudaStreamCreateWithFlags(&m->gside[g], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&m->ev_d[g], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&m->ev_p[g], cudaEventDisableTiming));
+    }
+    cudaStream_t side = m->gside[g];
+    {
+      Timed t(m, KB200_PROF_DIAG, st);
+      CK(launch_chol_diag_half(a, 0, Pb, st));
+    }
+    for (int j = 0; j + 1 < nt; ++j) {
+      CK(cudaEventRecord(m->ev_d[g], st));               // D(j) done (and everything before it on main)
+      if (j + 2 < nt) {
+        CK(cudaStreamWaitEvent(side, m->ev_d[g], 0));
+        CholArgs b = a;
+        b.i0 = 1;
+        {
+          Timed t(m, KB200_PROF_PANEL, side);
+          CK(launch_chol_panel_half(b, j, 2 * (nt - 2 - j), Pb, side));
+        }
+        CK(cudaEventRecord(m->ev_p[g], side));
+      }
+      {
+        Timed t(m, KB200_PROF_PANEL, st);
+        CK(launch_chol_panel_half(a, j, 2, Pb, st));     // tile (j+1, j); its row was completed by P_b(j-1),
+      }                                                  // which main waited for at the end of the last round
       {
         Timed t(m, KB200_PROF_DIAG, st);
-        CK(launch_chol_diag_half(a, j, Pb, st));
+        CK(launch_chol_diag_half(a, j + 1, Pb, st));
       }
-      if (j + 1 < m->nt) {
-        Timed t(m, KB200_PROF_PANEL, st);
-        CK(launch_chol_panel_half(a, j, 2 * (m->nt - 1 - j), Pb, st));
-      }
+      if (j + 2 < nt) CK(cudaStreamWaitEvent(st, m->ev_p[g], 0));   // before P_a(j+1) and as the final join
     }
     return 0;
   }
@@ -483,7 +535,7 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
       double* logdet = m->logdet.d() + o0;
       rc = assemble(m, cand, pg, tiles, 1, sg);
       if (rc) return rc;
-      rc = factorize(m, pg, tiles, W8, Z, logdet, d_info + p0 + o0, sg);
+      rc = factorize(m, pg, tiles, W8, Z, logdet, d_info + p0 + o0, sg, g);
       if (rc) return rc;
       FinArgs f;
       memset(&f, 0, sizeof(f));
@@ -1150,6 +1202,7 @@ int kb200_set_groups(kb200_model* m, int ngroups) {
     if (!m->ev_join[g]) CK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
   }
   m->ngroups = ngroups;
+  m->dual = m->dual_env == 1 && ngroups > 1;   // 1 group = everything serialised on one stream
   return 0;
 }
 

@@ -530,7 +530,7 @@ chol_panel_half_kernel(CholArgs A, int j) {
     W8j = A.W8 + (size_t)j * 1024;
     ssq_base = pt * TB + hr * HROWS;
   } else {
-    const int i = j + 1 + (blockIdx.x >> 1);
+    const int i = j + 1 + A.i0 + (blockIdx.x >> 1);
     const long m = blockIdx.y;
     double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
     rowA = tiles + (size_t)tri_index(i, 0) * TILE_ELEMS;

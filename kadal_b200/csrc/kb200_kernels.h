@@ -43,6 +43,7 @@ struct CholArgs {
   double* logdet;        // [P]  sum ln L_ii
   int* info;             // [P]
   int naive;             // debug: plain-FMA GEMM instead of the DMMA pipeline
+  int i0;                // half-SM panel: first tile row of this launch is j + 1 + i0
   int fuse_diag;         // panel CTA (j+1, j) also finishes diagonal tile j+1 (no diag launches for j >= 1)
   // prediction-as-extra-rows
   int pred_mode;
