@@ -328,6 +328,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- prediction throughput (configs[2]: n=200, d=6, pred + s), device resident + e2e
     pred = predict_bench(args, rank, local_rank, world, torch, dist, barrier)
+    extra = extra_configs(args, rank, local_rank, world, torch, dist, barrier) if not args.no_extra else None
 
     if rank != 0:
         if world > 1:
@@ -403,6 +404,7 @@ def run_ours(args, rank, local_rank, world):
                                           "(compulsory traffic); not the binding roof (AI >> 6 flop/B)"}},
         "kernel_ms": kernel_ms,
         "predict": pred,
+        "other_configs": extra,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
@@ -475,6 +477,82 @@ def predict_bench(args, rank, local_rank, world, torch, dist, barrier):
             "h2d_bytes_per_step": world * npts * d * 8, "d2h_bytes_per_step": world * npts * 16}
 
 
+def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
+    """BASELINE configs[3] and [4] on this rank's GPU (rank 0 reports; every rank runs the same work so the
+    numbers are per GPU): C4 Sobol surrogate n=800, d=20 'pred' over Saltelli points, C5 KPLS n=4000,
+    d=100, h=3: batched likelihood of a small CMA-ES population and EHVI-style pred + SSqr scoring."""
+    from kadal_b200 import _capi
+    from kadal_b200.model import GpuModel
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- C4
+    rng = np.random.default_rng(7)
+    X = rng.uniform(-1, 1, (800, 20))
+    y = (np.sin(X[:, :3].sum(1)) + 0.05 * rng.standard_normal(800))[:, None] + 3.0
+    m = GpuModel(X, y, np.ones((800, 1)), [0], device=local_rank)
+    assert m.fit_state(np.full(20, 0.4), False, -6.0, want_U=False, want_Psi=False)["info"] == 0
+    npts = 2_000_000
+    g = torch.Generator(device=dev)
+    g.manual_seed(7 + rank)
+    xs = torch.rand(npts, 20, generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    o = torch.empty(npts, dtype=torch.float64, device=dev)
+    lb, ub = -np.ones(20), np.ones(20)
+    ms = timed(lambda: m.predict_dev(xs.data_ptr(), npts, _capi.OUT_PRED, [o.data_ptr(), 0, 0, 0, 0, 0, 0],
+                                     normtype=_capi.NORM_DEFAULT, norm_a=lb, norm_b=ub, stream=stream), 3)
+    pts = npts / (ms * 1e-3)
+    out["c4_sobol_pred"] = {"workload": "C4: n=800, d=20, 'pred' over %d Saltelli points per GPU" % npts, "pts_per_s_per_gpu": pts,
+                            "ms": ms, "fp64_tflops_algorithmic": pts * predict_flops_per_point(800, 20, False) / 1e12,
+                            "hbm_gbs_algorithmic": pts * (8 * 20 + 8) / 1e9}
+    m.close()
+    del xs, o
+    # ---- C5
+    rng = np.random.default_rng(11)
+    n, d, h = 4000, 100, 3
+    X = rng.uniform(-1, 1, (n, d))
+    y = (X[:, :5].sum(1) ** 2)[:, None] + 3.0
+    pls = rng.standard_normal((d, h)) / 10
+    th = np.array([0.3, 0.1, -0.1])
+    m = GpuModel(X, y, np.ones((n, 1)), [0], pls=pls, device=local_rank)
+    P5 = 16
+    pop = th[None, :] + np.random.default_rng(3).uniform(-0.2, 0.2, (P5, h))
+    xd = torch.from_numpy(pop).to(dev)
+    nll = torch.empty(P5, dtype=torch.float64, device=dev)
+    info = torch.empty(P5, dtype=torch.int32, device=dev)
+    ms = timed(lambda: m.lik_batch_dev(xd.data_ptr(), P5, h, False, -6.0, nll.data_ptr(), info.data_ptr(), stream), 2)
+    assert int((info != 0).sum().item()) == 0
+    out["c5_kpls_lik"] = {"workload": "C5: KPLS n=4000, d=100, h=3, population of %d candidates per GPU" % P5,
+                          "evals_per_s_per_gpu": P5 / (ms * 1e-3), "ms": ms,
+                          "chol_tflops": n ** 3 / 3.0 * P5 / (ms * 1e-3) / 1e12}
+    assert m.fit_state(th, False, -6.0, want_U=False, want_Psi=False)["info"] == 0
+    nc = 100_000
+    xs = torch.rand(nc, d, generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    o1 = torch.empty(nc, dtype=torch.float64, device=dev)
+    o2 = torch.empty(nc, dtype=torch.float64, device=dev)
+    lb, ub = -np.ones(d), np.ones(d)
+    ms = timed(lambda: m.predict_dev(xs.data_ptr(), nc, _capi.OUT_PRED | _capi.OUT_SSQR,
+                                     [o1.data_ptr(), o2.data_ptr(), 0, 0, 0, 0, 0], normtype=_capi.NORM_DEFAULT,
+                                     norm_a=lb, norm_b=ub, stream=stream), 2)
+    pts = nc / (ms * 1e-3)
+    out["c5_kpls_score"] = {"workload": "C5: pred + SSqr (EHVI inputs) over %d candidates per GPU" % nc, "pts_per_s_per_gpu": pts,
+                            "ms": ms, "fp64_tflops_algorithmic": pts * (n * n + n * (3 * d + 6 * h + 20)) / 1e12}
+    m.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -483,6 +561,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--predict-points", type=float, default=4e6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 sub-benchmarks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

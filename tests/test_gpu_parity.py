@@ -301,6 +301,41 @@ def test_kpls_and_composite_population(kb):
     assert relerr(nll3, ref3) < TOL_NLL
 
 
+@pytest.mark.parametrize("half", ["0", "1"])
+def test_both_factorisation_paths_against_the_oracle(kb, half, monkeypatch):
+    """The library has two batched Cholesky paths: half-SM CTAs, two per SM (kb200_half.cu, default up to
+    16 tiles per dimension) and full-SM CTAs with the diagonal work fused into the panel kernel (default
+    beyond).  Both are forced here on the same population (n = 700: 6 tiles, ragged last tile) and must
+    meet the NLL tolerance, agree on the arg-min, give reproducible bits from run to run and be
+    independent of the batch composition."""
+    from kadal_b200.model import GpuModel
+    monkeypatch.setenv("KB200_HALF", half)
+    w = ko.workload("C2", scale=0.7)
+    n = w["X"].shape[0]
+    info = ko.make_kriginfo(w["X"], w["y"])
+    pop = np.vstack([w["popB"][:40], w["popA"][:8]])
+    gm = GpuModel(w["X"], w["y"], np.ones((n, 1)), [0])
+    nll, inf = gm.lik_batch(pop, False, -6.0)
+    nll2, _ = gm.lik_batch(pop, False, -6.0)
+    assert not inf.any() and np.array_equal(nll, nll2)
+    perm = np.random.default_rng(1).permutation(len(pop))
+    nll_p, _ = gm.lik_batch(pop[perm], False, -6.0)
+    assert np.array_equal(nll_p, nll[perm])
+    one, _ = gm.lik_batch(pop[5:6], False, -6.0)
+    assert one[0] == nll[5]
+    idx = np.r_[np.argsort(nll)[:6], 40, 41]
+    ref = ko.likelihood_population(pop[idx], copy.deepcopy(info), False, check_pd=False)
+    conds = conds_of(info, pop[idx])
+    assert all(relerr(a, b) < nll_tol(c) for a, b, c in zip(nll[idx], ref, conds))
+    assert idx[int(np.argmin(ref))] == int(np.argmin(nll))
+    st = gm.fit_state(pop[0], False, -6.0)
+    A = copy.deepcopy(info)
+    ko.likelihood(pop[0].copy(), A, "all", False, check_pd=False)
+    Ap = A["Psi"] + np.eye(n) * 1e-6
+    assert np.linalg.norm(st["U"].T @ st["U"] - Ap) / np.linalg.norm(Ap) < 1e-14
+    gm.close()
+
+
 def test_kpls_plane_cache_is_bit_identical_to_on_the_fly_assembly(kb, monkeypatch):
     """KPLS distances sum_k g(dx_k) pls_kc do not depend on theta (kernelfunc.py:41-47, 58-64): the
     library caches the h planes per model and assembles every candidate's Psi from them.  Same
