@@ -38,7 +38,73 @@ __device__ __forceinline__ double standardize1(double x, int normtype, double a,
   return x;
 }
 
-template <bool FAST>
+// the 2 x 8 quads (1 x 4 entries each) of one thread for one (row tile, column tile) pair.
+// INTERIOR: every row and column of the pair is a real sample / point and the pair is not on the
+// diagonal, so none of the per-entry fix-ups (identity padding, nugget, zeroed upper triangle, skipped
+// quads) can apply: 21 of the 36 tiles of C2, all but the last sample tile of a prediction.
+template <bool FAST, int MODE, bool INTERIOR>
+__device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __restrict__ cand, const double* th2,
+                                          double w0, double eps, const double* As, const double* Bt, int lda,
+                                          int ti, int tj, double* tile, int warp, int g, int ch,
+                                          double (&facc)[2], double (&uacc)[2]) {
+  const int d = A.spec.d;
+#pragma unroll 1
+  for (int rgi = 0; rgi < 2; ++rgi) {
+    const int row = 8 * (warp + 8 * rgi) + g;
+    const long grow = (long)ti * TB + row;
+#pragma unroll 1
+    for (int s = 0; s < NSLAB; ++s) {
+      const int c0 = s * KS + 4 * ch;
+      const int gc0 = tj * TB + c0;
+      Quad q;
+      bool need = true;
+      if (!INTERIOR) {
+        if (MODE == CORR_ASSEMBLE) {
+          // skip the strictly-upper part of diagonal tiles and fully padded quads
+          if ((ti == tj && c0 > row) || grow >= A.n || gc0 >= A.n) need = false;
+        } else {
+          if (gc0 >= A.n) need = false;
+        }
+      }
+      if (need) {
+        if (FAST) q = corr_quad_gauss(d, th2, th2 + d, w0, As + row * lda, Bt + c0, TB);
+        else q = corr_quad(A.spec, cand, As + row * lda, Bt + c0, TB);
+      } else {
+        q = quad_set(0.0);
+      }
+      if (!INTERIOR) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int gc = gc0 + e;
+          if (MODE == CORR_ASSEMBLE) {
+            if (grow >= A.n || gc >= A.n) q.v[e] = (grow == gc) ? 1.0 : 0.0;   // identity padding
+            else if (grow == gc && A.add_eps) q.v[e] = __dadd_rn(q.v[e], eps); // Psi + eye*eps
+            else if (ti == tj && gc > grow) q.v[e] = 0.0;
+          } else {
+            if (gc >= A.n) q.v[e] = 0.0;
+          }
+        }
+      }
+      if (MODE == CORR_ASSEMBLE || tile) {
+        double2* dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row * KS + ((ch ^ (row & 3)) << 2));
+        dst[0] = make_double2(q.v[0], q.v[1]);
+        dst[1] = make_double2(q.v[2], q.v[3]);
+      }
+      if (MODE == CORR_PREDICT) {
+        double fa = 0.0, ua = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int gc = gc0 + e;   // alpha / w are zero padded to nt*TB
+          fa = fma(q.v[e], A.alpha[gc], fa);
+          if (A.wvec) ua = fma(q.v[e], A.wvec[gc], ua);
+        }
+        if (rgi == 0) { facc[0] += fa; uacc[0] += ua; } else { facc[1] += fa; uacc[1] += ua; }
+      }
+    }
+  }
+}
+
+template <bool FAST, int MODE>
 __global__ void __launch_bounds__(CORR_THREADS, FAST ? KB200_CORR_FAST_BLOCKS : 2)
 corr_tile_kernel(CorrArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -47,13 +113,12 @@ corr_tile_kernel(CorrArgs A) {
   double* As = reinterpret_cast<double*>(smem_raw);          // [128][lda]
   double* Bt = As + ((TB * lda + 1) & ~1);                   // [d][128]
   double* th2 = Bt + d * TB;                                 // [d] theta^2, then [d] RN(1/theta^2)
-  constexpr bool fast = FAST;   // one Gaussian kernel, non-KPLS (chosen by the launcher)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, ch = lane & 3;
 
   int ti, tj0, tj1;
   long m;  // candidate (assembly) — prediction uses candidate 0
-  if (A.mode == CORR_ASSEMBLE) {
+  if (MODE == CORR_ASSEMBLE) {
     // blockIdx.x -> lower-triangular tile (ti,tj)
     int t = blockIdx.x;
     ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
@@ -69,11 +134,11 @@ corr_tile_kernel(CorrArgs A) {
     m = 0;
   }
   const double* cand = A.cand + m * A.cand_stride;
-  if (fast && tid < 2 * d) th2[tid] = cand[2 * A.spec.ntheta + tid];   // theta2 | rtheta2 are adjacent
+  if (FAST && tid < 2 * d) th2[tid] = cand[2 * A.spec.ntheta + tid];   // theta2 | rtheta2 are adjacent
   const double w0 = cand[4 * A.spec.ntheta];
 
   // ---- row coordinates -> As
-  if (A.mode == CORR_ASSEMBLE) {
+  if (MODE == CORR_ASSEMBLE) {
     for (int idx = tid; idx < TB * d; idx += CORR_THREADS) {
       int r = idx / d, k = idx - r * d;
       int gr = ti * TB + r;
@@ -92,7 +157,7 @@ corr_tile_kernel(CorrArgs A) {
     }
   }
 
-  double facc0 = 0.0, facc1 = 0.0, uacc0 = 0.0, uacc1 = 0.0;
+  double facc[2] = {0.0, 0.0}, uacc[2] = {0.0, 0.0};
   const double eps = cand[4 * A.spec.ntheta + A.spec.nkernel];
 
   for (int tj = tj0; tj < tj1; ++tj) {
@@ -104,65 +169,21 @@ corr_tile_kernel(CorrArgs A) {
     }
     __syncthreads();
     double* tile;
-    if (A.mode == CORR_ASSEMBLE)
+    bool interior;
+    if (MODE == CORR_ASSEMBLE) {
       tile = A.out + ((size_t)m * A.tiles_per_mat + tri_index(ti, tj)) * TILE_ELEMS;
-    else
+      interior = ti != tj && (ti + 1) * TB <= A.n;
+    } else {
       tile = A.out ? A.out + ((size_t)ti * A.nt + tj) * TILE_ELEMS : nullptr;
-
-#pragma unroll 1
-    for (int rgi = 0; rgi < 2; ++rgi) {
-      const int row = 8 * (warp + 8 * rgi) + g;
-      const long grow = (long)ti * TB + row;
-#pragma unroll 1
-      for (int s = 0; s < NSLAB; ++s) {
-        const int c0 = s * KS + 4 * ch;
-        const int gc0 = tj * TB + c0;
-        Quad q;
-        bool need = true;
-        if (A.mode == CORR_ASSEMBLE) {
-          // skip the strictly-upper part of diagonal tiles and fully padded quads
-          if ((ti == tj && c0 > row) || grow >= A.n || gc0 >= A.n) need = false;
-        } else {
-          if (gc0 >= A.n) need = false;
-        }
-        if (need) {
-          if (FAST) q = corr_quad_gauss(d, th2, th2 + d, w0, As + row * lda, Bt + c0, TB);
-          else q = corr_quad(A.spec, cand, As + row * lda, Bt + c0, TB);
-        }
-        else q = quad_set(0.0);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          int gc = gc0 + e;
-          if (A.mode == CORR_ASSEMBLE) {
-            if (grow >= A.n || gc >= A.n) q.v[e] = (grow == gc) ? 1.0 : 0.0;   // identity padding
-            else if (grow == gc && A.add_eps) q.v[e] = __dadd_rn(q.v[e], eps); // Psi + eye*eps
-            else if (ti == tj && gc > grow) q.v[e] = 0.0;
-          } else {
-            if (gc >= A.n) q.v[e] = 0.0;
-          }
-        }
-        if (tile) {
-          double2* dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row * KS + ((ch ^ (row & 3)) << 2));
-          dst[0] = make_double2(q.v[0], q.v[1]);
-          dst[1] = make_double2(q.v[2], q.v[3]);
-        }
-        if (A.mode == CORR_PREDICT) {
-          double fa = 0.0, ua = 0.0;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            int gc = gc0 + e;   // alpha / w are zero padded to nt*TB
-            fa = fma(q.v[e], A.alpha[gc], fa);
-            if (A.wvec) ua = fma(q.v[e], A.wvec[gc], ua);
-          }
-          if (rgi == 0) { facc0 += fa; uacc0 += ua; } else { facc1 += fa; uacc1 += ua; }
-        }
-      }
+      interior = (tj + 1) * TB <= A.n;
     }
+    if (interior) corr_pair<FAST, MODE, true>(A, cand, th2, w0, eps, As, Bt, lda, ti, tj, tile, warp, g, ch, facc, uacc);
+    else corr_pair<FAST, MODE, false>(A, cand, th2, w0, eps, As, Bt, lda, ti, tj, tile, warp, g, ch, facc, uacc);
   }
-  if (A.mode == CORR_PREDICT) {
+  if (MODE == CORR_PREDICT) {
 #pragma unroll
     for (int rgi = 0; rgi < 2; ++rgi) {
-      double f = rgi ? facc1 : facc0, u = rgi ? uacc1 : uacc0;
+      double f = facc[rgi], u = uacc[rgi];
       f += __shfl_xor_sync(0xffffffffu, f, 1);
       f += __shfl_xor_sync(0xffffffffu, f, 2);
       u += __shfl_xor_sync(0xffffffffu, u, 1);
@@ -1806,15 +1827,25 @@ cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t 
   const int dev = cur_dev();
   if (sm > g_corr_attr[dev]) {
     const int want = (int)(sm > 48 * 1024 ? sm : 48 * 1024);
-    cudaError_t e = cudaFuncSetAttribute(corr_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    cudaError_t e = cudaFuncSetAttribute(corr_tile_kernel<false, CORR_ASSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(corr_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    e = cudaFuncSetAttribute(corr_tile_kernel<true, CORR_ASSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(corr_tile_kernel<false, CORR_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(corr_tile_kernel<true, CORR_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) return e;
     g_corr_attr[dev] = sm;
   }
   const bool fast = a.spec.nkernel == 1 && a.spec.kid[0] == K_GAUSS && !a.spec.kpls;
-  if (fast) corr_tile_kernel<true><<<dim3(grid_x, grid_y), CORR_THREADS, sm, st>>>(a);
-  else corr_tile_kernel<false><<<dim3(grid_x, grid_y), CORR_THREADS, sm, st>>>(a);
+  const dim3 grid(grid_x, grid_y);
+  if (a.mode == CORR_ASSEMBLE) {
+    if (fast) corr_tile_kernel<true, CORR_ASSEMBLE><<<grid, CORR_THREADS, sm, st>>>(a);
+    else corr_tile_kernel<false, CORR_ASSEMBLE><<<grid, CORR_THREADS, sm, st>>>(a);
+  } else {
+    if (fast) corr_tile_kernel<true, CORR_PREDICT><<<grid, CORR_THREADS, sm, st>>>(a);
+    else corr_tile_kernel<false, CORR_PREDICT><<<grid, CORR_THREADS, sm, st>>>(a);
+  }
   KB_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -336,6 +336,32 @@ def test_both_factorisation_paths_against_the_oracle(kb, half, monkeypatch):
     gm.close()
 
 
+def test_results_do_not_depend_on_workspace_chunking_or_stream_groups(kb, monkeypatch):
+    """Host-side scheduling must not change a bit: populations larger than the workspace are processed in
+    chunks (KB200_WORKSPACE_GB), candidates are split over stream groups (kb200_set_groups) -- every
+    candidate is an independent unit."""
+    from kadal_b200.model import GpuModel
+    w = ko.workload("C2", scale=0.3)
+    n = w["X"].shape[0]
+    pop = w["popB"][:150]
+    gm = GpuModel(w["X"], w["y"], np.ones((n, 1)), [0])
+    base, inf = gm.lik_batch(pop, False, -6.0)
+    assert not inf.any()
+    for g in (1, 4, 8):
+        gm.set_groups(g)
+        assert np.array_equal(gm.lik_batch(pop, False, -6.0)[0], base)
+    gm.close()
+    monkeypatch.setenv("KB200_WORKSPACE_GB", "0.01")          # clamped to 256 MiB: ~328 candidates of this size per chunk
+    per_mat = 6 * 131072 + 3 * 8192 + 2 * 384 * 8
+    gm = GpuModel(w["X"], w["y"], np.ones((n, 1)), [0])
+    big = np.vstack([pop, pop[::-1], pop[:77]])                # 377 candidates: two chunks (328 + 49)
+    assert len(big) * per_mat > 256 * 2 ** 20
+    out, inf = gm.lik_batch(big, False, -6.0)
+    assert not inf.any()
+    assert np.array_equal(out, np.r_[base, base[::-1], base[:77]])
+    gm.close()
+
+
 def test_kpls_plane_cache_is_bit_identical_to_on_the_fly_assembly(kb, monkeypatch):
     """KPLS distances sum_k g(dx_k) pls_kc do not depend on theta (kernelfunc.py:41-47, 58-64): the
     library caches the h planes per model and assembles every candidate's Psi from them.  Same
