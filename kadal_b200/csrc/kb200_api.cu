@@ -777,9 +777,14 @@ int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double
 
 // --------------------------------------------------------------------- prediction
 static long chunk_tiles_for(const kb200_model* m) {
-  // point tiles per variance chunk: a multiple of the SM count, chunk buffer ~ 64-160 MiB
-  long t = 148L * std::max(1L, 4L / m->nt);
-  return t;
+  // point tiles per variance chunk: a multiple of the SM count.  One wave per launch left a quarter of the
+  // time in launch gaps and tails (C4 pred+s: 17.8 ms at 1 wave, 15.4 at 8; with the half-SM panel kernel
+  // 14.2); 8 waves, capped so that the psi chunk stays below ~2.5 GB ($KB200_CHUNK_WAVES overrides).
+  static const long env_waves = getenv("KB200_CHUNK_WAVES") ? std::max(1L, atol(getenv("KB200_CHUNK_WAVES"))) : 0;
+  const long per_wave = 148L * std::max(1L, 4L / m->nt);
+  const long bytes_per_wave = per_wave * m->nt * (long)TILE_ELEMS * 8;
+  long waves = env_waves ? env_waves : std::max(1L, std::min(8L, (long)(2.5 * (1L << 30)) / bytes_per_wave));
+  return per_wave * waves;
 }
 
 static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long npts, int normtype,
@@ -843,7 +848,7 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     }
     return 0;
   }
-  const long ct = chunk_tiles_for(m);
+  const long ct = std::min(chunk_tiles_for(m), (npts + TB - 1) / TB);
   const long cpts = ct * TB;
   CK(sl.chunk.reserve((size_t)ct * m->nt * TILE_ELEMS * 8));
   CK(sl.udot.reserve((size_t)npts * 8));
@@ -864,7 +869,7 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     }
     for (int j = 0; j < m->nt; ++j) {
       Timed t(m, KB200_PROF_PREDSOLVE, st);
-      if (m->half_mode == 1 && !pa.naive) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // (no gain measured)
+      if (m->half_mode != 0 && !pa.naive) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // bit-identical to the full-SM kernel
       else CK(launch_chol_panel(pa, j, tiles, 1, st));
     }
     EpiArgs ee = e;
@@ -890,7 +895,7 @@ extern "C" int kb200_loocv(kb200_model* m, double* loo) {
   CK(cudaSetDevice(m->device));
   cudaStream_t st = m->stream;
   PredSlot& sl = m->slot[0];
-  const long ct = chunk_tiles_for(m);
+  const long ct = std::min<long>(chunk_tiles_for(m), m->nt);
   const long cpts = ct * TB;
   CK(sl.chunk.reserve((size_t)ct * m->nt * TILE_ELEMS * 8));
   CK(sl.ssq.reserve((size_t)cpts * 8));
@@ -906,7 +911,7 @@ extern "C" int kb200_loocv(kb200_model* m, double* loo) {
     m->launches++;
     for (int j = 0; j < m->nt; ++j) {
       Timed t(m, KB200_PROF_PREDSOLVE, st);
-      if (m->half_mode == 1 && !pa.naive) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // (no gain measured)
+      if (m->half_mode != 0 && !pa.naive) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // bit-identical to the full-SM kernel
       else CK(launch_chol_panel(pa, j, tiles, 1, st));
     }
     CK(launch_loo(m->R.d(), m->palpha.d(), m->pw.d(), sl.ssq.d(), m->pbtb, m->n, p0, (int)np, sl.out[0].d(), st));
