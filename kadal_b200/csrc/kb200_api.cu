@@ -90,7 +90,8 @@ struct kb200_model {
   // half-SM path: per group a side stream for the panel tiles below row j + 1, so that the diagonal
   // tile j + 1 (latency-bound POTF2) runs under them (factorize())
   cudaStream_t gside[MAXG] = {nullptr};
-  cudaEvent_t ev_d[MAXG] = {nullptr}, ev_p[MAXG] = {nullptr};
+  cudaEvent_t ev_d[MAXG] = {nullptr}, ev_p[MAXG] = {nullptr}, ev_asm[MAXG] = {nullptr};
+  bool stagger = false;     // measured: 8.35 vs 8.28 ms at two groups, worse with more ($KB200_STAGGER=1 to try)
   bool dual = false;        // measured: no gain over two candidate groups at P = 512 (8.32 ms both), kept as an option ($KB200_DUAL=1)
   int dual_env = -1;
   cudaEvent_t ev_fork = nullptr, ev_join[MAXG] = {nullptr};
@@ -219,6 +220,7 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
     for (int g = 0; g < m->ngroups; ++g) {
       MCK(cudaStreamCreateWithFlags(&m->gstream[g], cudaStreamNonBlocking));
       MCK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
+      MCK(cudaEventCreateWithFlags(&m->ev_asm[g], cudaEventDisableTiming));
     }
     MCK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   }
@@ -243,6 +245,8 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
     MCK(cudaMemcpy(m->pls2.p, p2.data(), p2.size() * 8, cudaMemcpyHostToDevice));
   }
   {
+    const char* es = getenv("KB200_STAGGER");
+    if (es) m->stagger = atoi(es) != 0;
     const char* ed = getenv("KB200_DUAL");
     if (ed) { m->dual_env = atoi(ed) != 0 ? 1 : 0; m->dual = m->dual_env == 1; }
     const char* eh = getenv("KB200_HALF");
@@ -283,6 +287,7 @@ void kb200_model_destroy(kb200_model* m) {
     if (m->gside[g]) cudaStreamDestroy(m->gside[g]);
     if (m->ev_d[g]) cudaEventDestroy(m->ev_d[g]);
     if (m->ev_p[g]) cudaEventDestroy(m->ev_p[g]);
+    if (m->ev_asm[g]) cudaEventDestroy(m->ev_asm[g]);
     if (m->ev_join[g]) cudaEventDestroy(m->ev_join[g]);
   }
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -533,8 +538,12 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
       double* W8 = m->W.d() + (size_t)o0 * m->nt * 1024;
       double* Z = m->Z.d() + (size_t)o0 * m->nq * m->npad;
       double* logdet = m->logdet.d() + o0;
+      // Optional stagger (off: no gain measured): group g assembles only after group g-1 has, so that the
+      // groups stay about one tile column apart.
+      if (G > 1 && g > 0 && m->stagger) CK(cudaStreamWaitEvent(sg, m->ev_asm[g - 1], 0));
       rc = assemble(m, cand, pg, tiles, 1, sg);
       if (rc) return rc;
+      if (G > 1 && m->stagger) CK(cudaEventRecord(m->ev_asm[g], sg));
       rc = factorize(m, pg, tiles, W8, Z, logdet, d_info + p0 + o0, sg, g);
       if (rc) return rc;
       FinArgs f;
@@ -1205,6 +1214,7 @@ int kb200_set_groups(kb200_model* m, int ngroups) {
   for (int g = 0; g < ngroups; ++g) {
     if (!m->gstream[g]) CK(cudaStreamCreateWithFlags(&m->gstream[g], cudaStreamNonBlocking));
     if (!m->ev_join[g]) CK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
+    if (!m->ev_asm[g]) CK(cudaEventCreateWithFlags(&m->ev_asm[g], cudaEventDisableTiming));
   }
   m->ngroups = ngroups;
   m->dual = m->dual_env == 1 && ngroups > 1;   // 1 group = everything serialised on one stream

@@ -1,3 +1,5 @@
+"""Stress test of the half-SM factorisation path: repeated 148..512-candidate C2 batches must be bit-identical
+from run to run and agree with the full-SM path (DBG_P, DBG_REPS, DBG_N; see profiles/r1k_half_race.md)."""
 import os, sys, numpy as np
 sys.path.insert(0, "/root/repo")
 import bench
