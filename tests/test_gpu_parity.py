@@ -438,6 +438,60 @@ def test_krigdemo_train_and_predict_drop_in(kb):
     assert np.max(np.abs(model.predict(X, ["pred"]) - y)) < 1e-3 * scale
 
 
+def test_trained_model_round_trips_through_pickle_and_believer_refit(kb, tmp_path):
+    """KADAL pickles trained Kriging objects (mobo_3d.py:244-248) and refits at
+    fixed theta after appending a sample (Kriging believer, MOBO.py:344-356; AK-MCS / SOBO updates).  The
+    drop-in keeps KrigInfo a plain dict and the device state outside it: a pickled / unpickled model
+    predicts the same values, and the believer refit with one more sample matches the oracle."""
+    import pickle
+    from kadal_b200 import Kriging
+    from kadal_b200.model import clear_cache
+    from kadal_b200.trendfunction import compute_regression_mat
+    rng = np.random.default_rng(23)
+    n, d = 60, 3
+    lb, ub = -np.ones(d), np.ones(d)
+    X = rng.uniform(-1, 1, (n, d))
+    y = (np.sin(2 * X[:, 0]) + X[:, 1] * X[:, 2])[:, None] + 2.0
+    K = {"X": X, "y": y, "lb": lb, "ub": ub, "nvar": d, "nugget": -6, "nrestart": 3, "kernel": ["gaussian"],
+         "optimizer": "lbfgsb"}
+    model = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+    model.train(disp=False)
+    xq = rng.uniform(-1, 1, (200, d))
+    before = model.predict(xq, ["pred", "s"])
+    blob = tmp_path / "krig.pkl"
+    with open(blob, "wb") as f:
+        pickle.dump(model, f)
+    clear_cache()                                   # as in a fresh process: no device state survives
+    with open(blob, "rb") as f:
+        again = pickle.load(f)
+    after = again.predict(xq, ["pred", "s"])
+    # (the reloaded predictor is rebuilt from KrigInfo['U'] / 'BE' instead of the device-resident fit:
+    #  same numbers to rounding, not the same bits)
+    assert relerr(after[0], before[0]) < 1e-10 and relerr(after[1], before[1], 1e-3 * float(np.max(before[1]))) < 1e-8
+    # Kriging believer: append the prediction at xnext as a pseudo-observation, refit at the same theta
+    xnext = rng.uniform(-1, 1, (1, d))
+    ynext = again.predict(xnext, ["pred"])
+    s_before = float(again.predict(xnext, ["s"]))
+    info = again.KrigInfo
+    info["X"] = np.vstack((info["X"], xnext))
+    info["y"] = np.vstack((info["y"], np.reshape(ynext, (1, 1))))
+    info["nsamp"] = n + 1
+    again.standardize()
+    info = again.KrigInfo
+    info["F"] = compute_regression_mat(info["idx"], info["X_norm"], np.vstack((-np.ones((1, d)), np.ones((1, d)))), np.ones(d))
+    ref = copy.deepcopy(info)
+    again.KrigInfo = kb.likelihood(info["Theta"], info, mode="all", trainvar=False)
+    ko.likelihood(np.array(ref["Theta"], dtype=float), ref, "all", False, check_pd=False)
+    cond = np.linalg.cond(ref["Psi"] + np.eye(n + 1) * 1e-6)
+    assert relerr(again.KrigInfo["NegLnLike"], ref["NegLnLike"]) < nll_tol(cond)
+    p2, r2 = again.predict(xq, ["pred", "s"]), ko.prediction(xq, ref, ["pred", "s"])
+    assert relerr(p2[0], r2[0]) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+    # the believer point is reproduced and carries (almost) no variance
+    assert abs(float(again.predict(xnext, ["pred"])) - float(ynext)) < 1e-6
+    s_after, s_ref = float(again.predict(xnext, ["s"])), float(ko.prediction(xnext, ref, ["s"]))
+    assert s_after < s_before and abs(s_after - s_ref) < max(TOL_VAR, 5 * cond * 2.0 ** -53) * max(s_ref, 1e-3)
+
+
 def test_kpls_class_cmaes_drop_in(kb):
     """KPLS (kpls_model.py): PLS rotations on the host (scikit-learn, as the reference), CMA-ES
     populations evaluated in GPU batches, prediction through the projected distances."""
