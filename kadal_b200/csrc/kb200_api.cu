@@ -76,6 +76,9 @@ struct kb200_model {
   int half_mode = -1;       // half-SM factorisation kernels (kb200_half.cu): -1 auto, 0 off, 1 on
   cudaStream_t stream = nullptr;
   // likelihood workspace
+  DevBuf Rw;
+  bool rl_lookahead = true;
+  int rl_mode = -1;          // right-looking factorisation for large matrices: -1 auto (nt > 16), 0 off, 1 on
   DevBuf tiles, W, Z, cand, xdev, nll, info, logdet, sigma2, beta, btb, resid, rhs2, sol2;
   // predictor state
   bool has_pred = false;
@@ -249,6 +252,10 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
     if (es) m->stagger = atoi(es) != 0;
     const char* ed = getenv("KB200_DUAL");
     if (ed) { m->dual_env = atoi(ed) != 0 ? 1 : 0; m->dual = m->dual_env == 1; }
+    const char* ela = getenv("KB200_RL_LOOKAHEAD");
+    if (ela) m->rl_lookahead = atoi(ela) != 0;
+    const char* erl = getenv("KB200_RL");
+    if (erl) m->rl_mode = atoi(erl) != 0 ? 1 : 0;
     const char* eh = getenv("KB200_HALF");
     if (eh) m->half_mode = atoi(eh) != 0 ? 1 : 0;
     const char* ek = getenv("KB200_KPLS_PLANES");
@@ -274,7 +281,7 @@ void kb200_model_destroy(kb200_model* m) {
                     &m->nll, &m->info, &m->logdet, &m->sigma2, &m->beta, &m->btb, &m->resid,
                     &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand,
                     &m->norm_a, &m->norm_b, &m->stats, &m->akpart,
-                    &m->sobB, &m->sobC, &m->sobY, &m->sobAcc, &m->sobPart, &m->sobMask};
+                    &m->Rw, &m->sobB, &m->sobC, &m->sobY, &m->sobAcc, &m->sobPart, &m->sobMask};
   for (DevBuf* b : bufs) b->release();
   for (int s = 0; s < 2; ++s) {
     PredSlot& sl = m->slot[s];
@@ -428,7 +435,85 @@ static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z
   // the diagonal work fused into the panel CTA are faster (C5, n = 4000, P = 16: 18.5 vs 21.1 ms,
   // profiles/r1k_half.md).  The choice depends on the model only, never on the batch size: any sub-batch
   // of a population is bit-identical to the full batch.  $KB200_HALF = 0 / 1 forces one path.
-  const bool use_half = !a.naive && (m->half_mode == 1 || (m->half_mode < 0 && m->nt <= 16));
+  const bool use_rl = !a.naive && m->half_mode != 0 && (m->rl_mode == 1 || (m->rl_mode < 0 && m->nt > 16));
+  const bool use_half = !a.naive && !use_rl && (m->half_mode == 1 || (m->half_mode < 0 && m->nt <= 16));
+  // Right-looking variant beyond 16 tiles per dimension: with few large matrices the left-looking paths
+  // are bound by the per-column chain of one CTA (GEMM of depth 128 j, solve, SYRK, POTF2); here every
+  // tile receives its updates column by column (C_ib -= L_ik L_bk^T, one tile of depth each), so the whole
+  // trailing matrix is parallel work and the chain per column is POTF2 + one solve.  Same kernels:
+  // chol_diag_half_kernel without its SYRK, chol_panel_half_kernel without its GEMM (T) or without its
+  // solve (U).  C5 (n = 4000, P = 16): profiles/r1n_right_looking.md.
+  if (use_rl) {
+    a.fuse_diag = 0;
+    a.Rw = m->Rw.d() + (Z - m->Z.d());
+    const int nt = m->nt;
+    a.rl_mode = 1;
+    CK(launch_rl_rhs_update(a, -1, Pb, st));
+    m->launches++;
+    // Look-ahead on two streams: after the solve of column k the main stream updates only the next column
+    // (tiles (i, k+1) and the RHS tile k+1) and goes on with POTF2 / solve of column k+1, while the side
+    // stream updates the rest of the trailing matrix.  U_a(k+1) touches tiles that U_b(k) also updates:
+    // the main stream waits for U_b(k) before it (ev_p); U_b(k) needs the solve of column k (ev_d).
+    if (!m->gside[g]) {
+      CK(cudaStreamCreateWithFlags(&m->gside[g], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&m->ev_d[g], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&m->ev_p[g], cudaEventDisableTiming));
+    }
+    cudaStream_t side = m->gside[g];
+    const bool look = m->rl_lookahead;
+    for (int k = 0; k < nt; ++k) {
+      {
+        Timed t(m, KB200_PROF_DIAG, st);
+        a.rl_mode = 1;
+        a.i0 = 0;
+        CK(launch_chol_diag_half(a, k, Pb, st));
+      }
+      const int M = nt - 1 - k;
+      if (M <= 0) break;
+      {
+        Timed t(m, KB200_PROF_PANEL, st);
+        a.rl_mode = 1;
+        CK(launch_chol_panel_half(a, k, 2 * M, Pb, st));
+      }
+      if (!look) {
+        {
+          Timed t(m, KB200_PROF_PANEL, st);
+          a.rl_mode = 2;
+          CK(launch_chol_panel_half(a, k, M * (M + 1), Pb, st));
+        }
+        CK(launch_rl_rhs_update(a, k, Pb, st));
+        m->launches++;
+        continue;
+      }
+      // U_a(k) and the main-stream RHS update touch what U_b(k-1) also updates: wait for it here (this wait
+      // is enqueued before ev_p is re-recorded below, so it refers to U_b(k-1))
+      if (k > 0) CK(cudaStreamWaitEvent(st, m->ev_p[g], 0));
+      CK(cudaEventRecord(m->ev_d[g], st));                       // column k solved
+      if (M > 1) {                                               // U_b(k): pairs from row / column k + 2 on
+        CK(cudaStreamWaitEvent(side, m->ev_d[g], 0));
+        CholArgs b = a;
+        b.rl_mode = 2;
+        b.i0 = 1;
+        {
+          Timed t(m, KB200_PROF_PANEL, side);
+          CK(launch_chol_panel_half(b, k, (M - 1) * M, Pb, side));
+        }
+        CK(launch_rl_rhs_update(b, k, Pb, side));                // RHS tiles k + 2 ..
+        m->launches++;
+      }
+      {                                                          // U_a(k): the strip b = k + 1, RHS tile k + 1
+        Timed t(m, KB200_PROF_PANEL, st);
+        a.rl_mode = 3;
+        a.i0 = 0;
+        CK(launch_chol_panel_half(a, k, 2 * M, Pb, st));
+      }
+      CK(launch_rl_rhs_update(a, k, Pb, st, 1));
+      m->launches++;
+      CK(cudaEventRecord(m->ev_p[g], side));                     // (an empty record when M == 1)
+    }
+    if (look && nt > 1) CK(cudaStreamWaitEvent(st, m->ev_p[g], 0));   // join
+    return 0;
+  }
   if (use_half) {
     a.fuse_diag = 0;
     const int nt = m->nt;
@@ -505,6 +590,7 @@ static int reserve_lik(kb200_model* m, long P, int Pb) {
   CK(m->tiles.reserve((size_t)Pb * m->tiles_per_mat * TILE_ELEMS * 8));
   CK(m->W.reserve((size_t)Pb * m->nt * 1024 * 8));
   CK(m->Z.reserve((size_t)Pb * m->nq * m->npad * 8));
+  CK(m->Rw.reserve((size_t)Pb * m->nq * m->npad * 8));
   CK(m->cand.reserve((size_t)P * m->cstride * 8));
   CK(m->logdet.reserve((size_t)Pb * 8));
   return 0;

@@ -339,7 +339,7 @@ chol_diag_half_kernel(CholArgs A, int j) {
   for (int q = 0; q < MAXQ; ++q) tacc[q] = 0.0;
   const int rr = tid >> 1, hh = tid & 1;     // RHS hook: row rr, columns 8 hh .. 8 hh + 7 of every slab
 
-  const int nslab = NSLAB * j;
+  const int nslab = A.rl_mode ? 0 : NSLAB * j;      // right-looking: tile (j, j) and the RHS are already updated
   auto issue = [&](int q) {
     const int st = q % DNST, use = q / DNST;
     if (use > 0) mbar_wait(&empty[st], (uint32_t)((use - 1) & 1));
@@ -441,7 +441,9 @@ chol_diag_half_kernel(CholArgs A, int j) {
     if (qq < nq) {
       double s = tacc[qq];
       s += __shfl_xor_sync(FULLMASK, s, 1);
-      if (hh == 0) trow[qq * TLD + rr] = A.R[(size_t)qq * A.npad + j * TB + rr] - s;
+      const double base = A.rl_mode ? A.Rw[((size_t)m * A.nq + qq) * A.npad + j * TB + rr]
+                                    : A.R[(size_t)qq * A.npad + j * TB + rr];
+      if (hh == 0) trow[qq * TLD + rr] = base - s;
     }
   }
   __syncthreads();
@@ -529,6 +531,29 @@ chol_panel_half_kernel(CholArgs A, int j) {
     Ljj = A.L + (size_t)tri_index(j, j) * TILE_ELEMS;
     W8j = A.W8 + (size_t)j * 1024;
     ssq_base = pt * TB + hr * HROWS;
+  } else if (A.rl_mode >= 2) {
+    // right-looking trailing update after column k = j: C_ib -= L_ik L_bk^T for k < b <= i.
+    // mode 2: all pairs from row/column k + 1 + i0 on: blockIdx.x >> 1 = a (a + 1) / 2 + c enumerates
+    //         (i, b) = (k + 1 + i0 + a, k + 1 + i0 + c), c <= a;  mode 3: the strip b = k + 1 only (look-ahead)
+    const int t = blockIdx.x >> 1;
+    int a, c;
+    if (A.rl_mode == 3) {
+      a = t;
+      c = 0;
+    } else {
+      a = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+      while ((a + 1) * (a + 2) / 2 <= t) ++a;
+      while (a * (a + 1) / 2 > t) --a;
+      c = t - a * (a + 1) / 2;
+    }
+    const int i = j + 1 + A.i0 + a, b = j + 1 + A.i0 + c;
+    const long m = blockIdx.y;
+    double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+    rowA = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;       // the 8 slabs of tile (i, k)
+    rowB = tiles + (size_t)tri_index(b, j) * TILE_ELEMS;       // the 8 slabs of tile (b, k)
+    Cij = tiles + (size_t)tri_index(i, b) * TILE_ELEMS;
+    Ljj = tiles;                                               // unused
+    W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;                // fetched, unused
   } else {
     const int i = j + 1 + A.i0 + (blockIdx.x >> 1);
     const long m = blockIdx.y;
@@ -557,7 +582,8 @@ chol_panel_half_kernel(CholArgs A, int j) {
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
   // ---- GEMM: acc = A(64 x 128 j) B(128 x 128 j)^T, operands streamed slab by slab
-  const int nslab = NSLAB * j;
+  // (right-looking variant: no accumulation before the solve (T), one tile of depth for the update (U))
+  const int nslab = A.rl_mode == 1 ? 0 : (A.rl_mode >= 2 ? NSLAB : NSLAB * j);
   auto issue = [&](int q) {
     const int st = q % HNST, use = q / HNST;
     if (use > 0) mbar_wait(&empty[st], (uint32_t)((use - 1) & 1));
@@ -585,6 +611,18 @@ chol_panel_half_kernel(CholArgs A, int j) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[(q - 1) % HNST]);
     }
+  }
+  if (A.rl_mode >= 2) {   // trailing update: C -= acc in place, nothing to solve
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
+        double2* p = reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + r, c));
+        const double2 v = *p;
+        *p = make_double2(v.x - acc[mt][nt][0], v.y - acc[mt][nt][1]);
+      }
+    return;
   }
   fence_proxy_async();
   __syncthreads();       // ring drained: Cs and the first two L_jj slabs may overwrite it
@@ -673,6 +711,50 @@ chol_panel_half_kernel(CholArgs A, int j) {
       *dst = (j == 0 ? 0.0 : *dst) + rs;
     }
   }
+}
+
+// right-looking RHS update after column k: rw_i -= L_ik z_k for the tiles i > k (nq right-hand sides);
+// one CTA per (i, candidate), thread = row; column k == -1 initialises rw = R
+__global__ void __launch_bounds__(TB)
+rl_rhs_update_kernel(CholArgs A, int k) {
+  const long m = blockIdx.y;
+  double* rw = A.Rw + (size_t)m * A.nq * A.npad;
+  if (k < 0) {
+    for (int idx = blockIdx.x * TB + threadIdx.x; idx < A.nq * A.npad; idx += gridDim.x * TB) rw[idx] = A.R[idx];
+    return;
+  }
+  __shared__ double z[MAXQ][TB];
+  const int i = k + 1 + A.i0 + blockIdx.x, r = threadIdx.x;
+  const double* zk = A.Z + (size_t)m * A.nq * A.npad;
+  for (int q = 0; q < A.nq; ++q) z[q][r] = zk[(size_t)q * A.npad + k * TB + r];
+  __syncthreads();
+  const double* T = A.L + ((size_t)m * A.tiles_per_mat + tri_index(i, k)) * TILE_ELEMS;
+  double acc[MAXQ];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) acc[q] = 0.0;
+  for (int c4 = 0; c4 < TB / 4; ++c4) {
+    const int s = c4 >> 2, ch = c4 & 3;
+    const double2* lp = reinterpret_cast<const double2*>(T + s * SLAB_ELEMS + r * KS + ((ch ^ (r & 3)) << 2));
+    const double2 l01 = lp[0], l23 = lp[1];
+    const int c = 4 * c4;
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+      if (q < A.nq) {
+        double v = acc[q];
+        v = fma(l01.x, z[q][c], v); v = fma(l01.y, z[q][c + 1], v);
+        v = fma(l23.x, z[q][c + 2], v); v = fma(l23.y, z[q][c + 3], v);
+        acc[q] = v;
+      }
+    }
+  }
+  for (int q = 0; q < A.nq; ++q) rw[(size_t)q * A.npad + i * TB + r] -= acc[q];
+}
+
+cudaError_t launch_rl_rhs_update(const CholArgs& a, int k, int nmat, cudaStream_t st, int ntiles) {
+  const int gx = k < 0 ? 8 : (ntiles >= 0 ? ntiles : a.nt - 1 - k - a.i0);
+  if (gx <= 0) return cudaSuccess;
+  rl_rhs_update_kernel<<<dim3(gx, nmat), TB, 0, st>>>(a, k);
+  return cudaGetLastError();
 }
 
 // ====================================================================== launchers

@@ -44,6 +44,8 @@ struct CholArgs {
   int* info;             // [P]
   int naive;             // debug: plain-FMA GEMM instead of the DMMA pipeline
   int i0;                // half-SM panel: first tile row of this launch is j + 1 + i0
+  int rl_mode;           // right-looking variant (large matrices): 0 off, 1 solve-only (T), 2 trailing update (U)
+  double* Rw;            // [P][nq][npad] working right-hand sides of the right-looking variant
   int fuse_diag;         // panel CTA (j+1, j) also finishes diagonal tile j+1 (no diag launches for j >= 1)
   // prediction-as-extra-rows
   int pred_mode;
@@ -167,6 +169,7 @@ cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, 
 // half-SM variants (kb200_half.cu): two CTAs per SM
 cudaError_t launch_chol_diag_half(const CholArgs& a, int j, int nmat, cudaStream_t st);
 cudaError_t launch_chol_panel_half(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);
+cudaError_t launch_rl_rhs_update(const CholArgs& a, int k, int nmat, cudaStream_t st, int ntiles = -1);
 cudaError_t launch_w8_from_tiles(const CholArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_finalize(const FinArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_backsolve(const BackArgs& a, cudaStream_t st);
