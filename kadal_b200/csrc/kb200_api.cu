@@ -427,22 +427,24 @@ static int assemble(kb200_model* m, const double* d_cand, int Pb, double* tiles,
 }
 
 static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z, double* logdet,
-                     int* info, cudaStream_t st, int g = 0) {
+                     int* info, cudaStream_t st, int g = 0, long Ptotal = 1) {
   CholArgs a = chol_args(m, tiles, W, Z, logdet, info);
   a.fuse_diag = a.naive ? 0 : 1;
-  // Half-SM kernels (kb200_half.cu, two CTAs per SM) up to 16 tiles per dimension; for larger matrices the
-  // per-candidate critical path (one half-SM CTA per diagonal tile) decides and the full-SM kernels with
-  // the diagonal work fused into the panel CTA are faster (C5, n = 4000, P = 16: 18.5 vs 21.1 ms,
-  // profiles/r1k_half.md).  The choice depends on the model only, never on the batch size: any sub-batch
-  // of a population is bit-identical to the full batch.  $KB200_HALF = 0 / 1 forces one path.
-  const bool use_rl = !a.naive && m->half_mode != 0 && (m->rl_mode == 1 || (m->rl_mode < 0 && m->nt > 16));
-  const bool use_half = !a.naive && !use_rl && (m->half_mode == 1 || (m->half_mode < 0 && m->nt <= 16));
-  // Right-looking variant beyond 16 tiles per dimension: with few large matrices the left-looking paths
-  // are bound by the per-column chain of one CTA (GEMM of depth 128 j, solve, SYRK, POTF2); here every
-  // tile receives its updates column by column (C_ib -= L_ik L_bk^T, one tile of depth each), so the whole
-  // trailing matrix is parallel work and the chain per column is POTF2 + one solve.  Same kernels:
-  // chol_diag_half_kernel without its SYRK, chol_panel_half_kernel without its GEMM (T) or without its
-  // solve (U).  C5 (n = 4000, P = 16): profiles/r1n_right_looking.md.
+  // Two schedules on the half-SM kernels (kb200_half.cu, two CTAs per SM), chosen by the amount of parallel
+  // work of the CALL (candidates of the whole batch x tiles per dimension), not of the chunk or stream group:
+  //  * left-looking (one diagonal + one panel launch per tile column, GEMM of depth 128 j per tile): least
+  //    HBM traffic, best when the batch fills the machine (C2, P = 512: 8.3 ms vs 9.6 right-looking);
+  //  * right-looking (every trailing tile updated per column, one tile of depth each): with few matrices the
+  //    left-looking chain of one CTA per candidate and column (GEMM, solve, SYRK, POTF2) is the bound, here
+  //    the chain is POTF2 + one solve and the trailing matrix is parallel work (n = 1000, P = 16: 0.86 vs
+  //    1.14 ms; n = 2048, P = 8: 2.1 vs 3.9; C5 n = 4000, P = 16: 15.7 vs 18.9; tools/sweep_paths.py).
+  // Cross-over measured at about 32 candidates / P x nt ~ 512 (no gain below 3 tiles per dimension).  The two schedules round differently (NLL agrees to ~1e-10
+  // relative); within one schedule results are bit-identical for any batch composition, chunking or grouping.
+  // $KB200_RL = 0 / 1 and $KB200_HALF = 0 (full-SM kernels of the first design) force a path.
+  const bool use_rl = !a.naive && m->half_mode != 0 &&
+                      (m->rl_mode == 1 ||
+                       (m->rl_mode < 0 && m->nt >= 3 && (Ptotal <= 32 || (long)Ptotal * m->nt < 512)));
+  const bool use_half = !a.naive && !use_rl && m->half_mode != 0;
   if (use_rl) {
     a.fuse_diag = 0;
     a.Rw = m->Rw.d() + (Z - m->Z.d());
@@ -630,7 +632,7 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
       rc = assemble(m, cand, pg, tiles, 1, sg);
       if (rc) return rc;
       if (G > 1 && m->stagger) CK(cudaEventRecord(m->ev_asm[g], sg));
-      rc = factorize(m, pg, tiles, W8, Z, logdet, d_info + p0 + o0, sg, g);
+      rc = factorize(m, pg, tiles, W8, Z, logdet, d_info + p0 + o0, sg, g, P);
       if (rc) return rc;
       FinArgs f;
       memset(&f, 0, sizeof(f));
