@@ -281,6 +281,19 @@ __device__ void potf2_blocked_t(double* S, double* trow, double* dinv, double* W
   }
 }
 
+// accumulators of warp W of the diagonal kernel = minus its 17 tiles of Psi_jj (row blocks 15 - W and W)
+template <int W>
+__device__ __forceinline__ void syrk_acc_init(double (&acc)[17][2], const double* Cjj, int g, int t) {
+  constexpr int NHI = 16 - W;
+#pragma unroll
+  for (int u = 0; u < 17; ++u) {
+    const int R = u < NHI ? 15 - W : W, C = u < NHI ? u : u - NHI;
+    const double2 p = *reinterpret_cast<const double2*>(Cjj + tile_off(8 * R + g, 8 * C + 2 * t));
+    acc[u][0] = -p.x;
+    acc[u][1] = -p.y;
+  }
+}
+
 }  // namespace
 
 // ============================================================================ diagonal tile
@@ -331,13 +344,30 @@ chol_diag_half_kernel(CholArgs A, int j) {
   // ---- SYRK: warp w owns the 8-row blocks hiR = 15 - w (tiles C = 0..hiR) and loR = w (C = 0..w):
   //      17 of the 136 lower 8x8 tiles each.  acc[u]: u < nhi -> (hiR, u), else (loR, u - nhi).
   const int hiR = 15 - warp, loR = warp, nhi = hiR + 1;
+  // The accumulators start at -Psi_jj (and -R_j), not at zero: the partial sums then walk from the entry down
+  // to the (much smaller) Schur complement exactly as a right-looking update would, and every rounding is
+  // relative to the current partial value instead of to the O(1) products that cancel at the end.  On
+  // candidates with cond ~ 7e8 this takes the ln-likelihood error from 2e-7 to 2e-9 relative
+  // (profiles/r1o_accumulate_from_c.md).
   double acc[17][2];
-#pragma unroll
-  for (int u = 0; u < 17; ++u) acc[u][0] = acc[u][1] = 0.0;
+  switch (warp) {     // (a select between the two row blocks inside one unrolled loop crashes ptxas 12.9)
+    case 0: syrk_acc_init<0>(acc, Cjj, g, t); break;
+    case 1: syrk_acc_init<1>(acc, Cjj, g, t); break;
+    case 2: syrk_acc_init<2>(acc, Cjj, g, t); break;
+    case 3: syrk_acc_init<3>(acc, Cjj, g, t); break;
+    case 4: syrk_acc_init<4>(acc, Cjj, g, t); break;
+    case 5: syrk_acc_init<5>(acc, Cjj, g, t); break;
+    case 6: syrk_acc_init<6>(acc, Cjj, g, t); break;
+    default: syrk_acc_init<7>(acc, Cjj, g, t); break;
+  }
+  const int rr = tid >> 1, hh = tid & 1;     // RHS hook: row rr, columns 8 hh .. 8 hh + 7 of every slab
   double tacc[MAXQ];
 #pragma unroll
-  for (int q = 0; q < MAXQ; ++q) tacc[q] = 0.0;
-  const int rr = tid >> 1, hh = tid & 1;     // RHS hook: row rr, columns 8 hh .. 8 hh + 7 of every slab
+  for (int q = 0; q < MAXQ; ++q) {
+    tacc[q] = 0.0;
+    if (q < nq && hh == 0)
+      tacc[q] = -(A.rl_mode ? A.Rw[((size_t)m * A.nq + q) * A.npad + j * TB + rr] : A.R[(size_t)q * A.npad + j * TB + rr]);
+  }
 
   const int nslab = A.rl_mode ? 0 : NSLAB * j;      // right-looking: tile (j, j) and the RHS are already updated
   auto issue = [&](int q) {
@@ -425,15 +455,14 @@ chol_diag_half_kernel(CholArgs A, int j) {
   }
   __syncthreads();        // every warp is done with the ring: S may overwrite it
 
-  // ---- S = Psi_jj - acc (packed lower triangle), t = R_j - tacc
+  // ---- S = -acc = Psi_jj - sum (packed lower triangle), t = -tacc = R_j - sum
   for (int idx = tid; idx < 8 * TLD; idx += HT) trow[idx] = 0.0;
 #pragma unroll
   for (int u = 0; u < 17; ++u) {
     const int R = u < nhi ? hiR : loR, C = u < nhi ? u : u - nhi;
     const int r = 8 * R + g, c = 8 * C + 2 * t;
-    const double2 p = *reinterpret_cast<const double2*>(Cjj + tile_off(r, c));
-    if (c <= r) S[tri(r) + c] = p.x - acc[u][0];
-    if (c + 1 <= r) S[tri(r) + c + 1] = p.y - acc[u][1];
+    if (c <= r) S[tri(r) + c] = -acc[u][0];
+    if (c + 1 <= r) S[tri(r) + c + 1] = -acc[u][1];
   }
   __syncthreads();
 #pragma unroll
@@ -441,9 +470,7 @@ chol_diag_half_kernel(CholArgs A, int j) {
     if (qq < nq) {
       double s = tacc[qq];
       s += __shfl_xor_sync(FULLMASK, s, 1);
-      const double base = A.rl_mode ? A.Rw[((size_t)m * A.nq + qq) * A.npad + j * TB + rr]
-                                    : A.R[(size_t)qq * A.npad + j * TB + rr];
-      if (hh == 0) trow[qq * TLD + rr] = base - s;
+      if (hh == 0) trow[qq * TLD + rr] = -s;
     }
   }
   __syncthreads();
@@ -575,13 +602,19 @@ chol_panel_half_kernel(CholArgs A, int j) {
   }
   __syncthreads();
 
+  // acc starts at -C_ij (see chol_diag_half_kernel: rounding relative to the shrinking partial value)
   double acc[4][4][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
+      const double2 p = *reinterpret_cast<const double2*>(Cij + tile_off(HROWS * hr + r, c));
+      acc[mt][nt][0] = -p.x;
+      acc[mt][nt][1] = -p.y;
+    }
 
-  // ---- GEMM: acc = A(64 x 128 j) B(128 x 128 j)^T, operands streamed slab by slab
+  // ---- GEMM: acc = -C + A(64 x 128 j) B(128 x 128 j)^T, operands streamed slab by slab
   // (right-looking variant: no accumulation before the solve (T), one tile of depth for the update (U))
   const int nslab = A.rl_mode == 1 ? 0 : (A.rl_mode >= 2 ? NSLAB : NSLAB * j);
   auto issue = [&](int q) {
@@ -618,9 +651,7 @@ chol_panel_half_kernel(CholArgs A, int j) {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
-        double2* p = reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + r, c));
-        const double2 v = *p;
-        *p = make_double2(v.x - acc[mt][nt][0], v.y - acc[mt][nt][1]);
+        *reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
       }
     return;
   }
@@ -633,14 +664,13 @@ chol_panel_half_kernel(CholArgs A, int j) {
       bulk_g2s(stages + P_WS01 + s * SLAB_ELEMS, Ljj + (size_t)s * SLAB_ELEMS, SLAB_BYTES, &wbar[s]);
     }
   }
-  // ---- C = Psi_ij - acc -> Cs
+  // ---- C = -acc = Psi_ij - sum -> Cs
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
-      const double2 p = *reinterpret_cast<const double2*>(Cij + tile_off(HROWS * hr + r, c));
-      *reinterpret_cast<double2*>(Cs + half_off(r, c)) = make_double2(p.x - acc[mt][nt][0], p.y - acc[mt][nt][1]);
+      *reinterpret_cast<double2*>(Cs + half_off(r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
     }
   __syncthreads();
   // ---- every warp takes 8 complete rows (C-fragment layout, 16 column tiles) and solves them

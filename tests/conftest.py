@@ -38,6 +38,16 @@ def golden_c2():
     return load_golden("c2_anchor.npz")
 
 
+@pytest.fixture(scope="session")
+def golden_c2_full():
+    return load_golden("c2_full.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_c2_truth():
+    return load_golden("c2_truth.npz")
+
+
 def relerr(a, b, floor=1.0):
     a = np.asarray(a, dtype=float)
     b = np.asarray(b, dtype=float)

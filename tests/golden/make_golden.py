@@ -122,6 +122,38 @@ def c2_anchor(ref):
     print("c2_anchor.npz KAT", repr(kat))
 
 
+def _c2_full_worker(args):
+    name, lo, hi = args
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "2"
+    ref = ref_loader.load()
+    w = ko.workload("C2")
+    info = ko.make_kriginfo(w["X"], w["y"])
+    n = w["X"].shape[0]
+    nll, cond = np.empty(hi - lo), np.empty(hi - lo)
+    for k, i in enumerate(range(lo, hi)):
+        A = copy.deepcopy(info)
+        ref.likelihood(w[name][i].copy(), A, "all", False)
+        nll[k] = A["NegLnLike"]
+        ev = np.linalg.eigvalsh(A["Psi"] + np.eye(n) * 1e-6)
+        cond[k] = ev[-1] / ev[0]
+    return name, lo, nll, cond
+
+
+def c2_full():
+    """n=1000, d=10 (BASELINE config 2): the live reference on EVERY candidate of both 512-candidate
+    populations, with cond(Psi + eps I) for the tolerance model of SURVEY.md Appendix E."""
+    from multiprocessing import get_context
+    jobs = [(name, lo, lo + 32) for name in ("popA", "popB") for lo in range(0, 512, 32)]
+    out = dict(nll_popA=np.empty(512), nll_popB=np.empty(512), cond_popA=np.empty(512), cond_popB=np.empty(512))
+    with get_context("spawn").Pool(4) as pool:
+        for name, lo, nll, cond in pool.imap_unordered(_c2_full_worker, jobs):
+            out["nll_" + name][lo:lo + 32] = nll
+            out["cond_" + name][lo:lo + 32] = cond
+            print(name, lo, "done", flush=True)
+    np.savez_compressed(os.path.join(HERE, "c2_full.npz"), **out)
+    print("c2_full.npz", out["nll_popB"].min(), out["cond_popB"].max(), out["cond_popA"].max())
+
+
 def ehvi_fronts():
     """Deterministic Pareto fronts + candidates of the EHVI goldens (shared with the tests)."""
     rng = np.random.default_rng(2024)
@@ -156,6 +188,9 @@ def ehvi2d():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ehvi":
         ehvi2d()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c2full":
+        c2_full()
         sys.exit(0)
     ref = ref_loader.load()
     appendix_c(ref)

@@ -64,6 +64,29 @@ def test_oracle_c2_known_answer(golden_c2):
     assert abs(v - float(golden_c2["kat_nll"])) < 1e-9 * 346
 
 
+def test_oracle_c2_full_population_golden(golden_c2_full, golden_c2):
+    """c2_full.npz holds the live reference on all 2 x 512 candidates; spot-check the oracle on a few of each
+    population (a full pass is 20 CPU-minutes) and the file against the older anchors."""
+    g = golden_c2_full
+    w = ko.workload("C2")
+    info = ko.make_kriginfo(w["X"], w["y"])
+    assert relerr(g["nll_popB"][golden_c2["idxB"]], golden_c2["nllB"]) < 1e-13
+    assert relerr(g["nll_popA"][golden_c2["idxA"]], golden_c2["nllA"]) < 1e-13
+    for pop, idx in (("popA", [100, 316]), ("popB", [114, 178, 476])):
+        v = ko.likelihood_population(w[pop][idx], copy.deepcopy(info), False, check_pd=False)
+        assert relerr(v, g["nll_" + pop][idx]) < 1e-12
+    assert int(np.argmin(g["nll_popB"])) == 178 and g["cond_popB"].max() > 9e8
+
+
+def test_c2_truth_fixture(golden_c2_truth, golden_c2_full):
+    """The reference's float64 result against the long-double value of its own formula: the reference itself
+    is 0.01 .. 1.4 cond ulp away from exact -- the scale of any parity bound at cond ~ 1e9."""
+    t = golden_c2_truth
+    assert np.array_equal(t["ref"], golden_c2_full["nll_popB"][t["idx"]]) or relerr(t["ref"], golden_c2_full["nll_popB"][t["idx"]]) < 1e-13
+    e = np.abs(t["ref"] - t["truth"]) / np.maximum(1, np.abs(t["truth"])) / (t["cond"] * 2.0 ** -53)
+    assert 114 in t["idx"] and e.max() < 2.0 and e.max() > 0.05
+
+
 def test_oracle_errors():
     info = ko.make_kriginfo(np.zeros((4, 2)), np.zeros((4, 1)))
     with pytest.raises(np.linalg.LinAlgError):  # duplicate rows + 0 nugget-free? keep nugget tiny
