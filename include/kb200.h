@@ -140,6 +140,29 @@ int kb200_ehvi2d_dev(int device, const double* d_pareto, int k, const double* re
                      const double* d_mu0, const double* d_mu1, const double* d_s0, const double* d_s1,
                      long long inc, long long npop, double sign, double* d_out, void* stream);
 
+/* 3-objective expected hyper-volume improvement of npop candidates: replaces the reference's C++ extension
+ * kmac.ehvi3d_sliceupdate_multi(y_par, ref_point, mean_vector, std_dev)
+ * (kadal/extern/HDYE_3D_Update/kmac_wrapper.cpp:73-118 -> ehvi_multi.cc:113-341) as called by
+ * optim_tools/ehvi/EHVIcomputation.py:235.  MAXIMISATION convention like KMAC (the caller negates, :235):
+ * front is [k][3] row-major, ref the lower corner, candidate i has means mean[3 i + c] and spreads
+ * sdev[3 i + c].  As in the wrapper (:24-34) the front is fed point by point and a new point drops the
+ * earlier points it dominates or equals.  out[i] = sign * EHVI_i.
+ * mode 0 reproduces the reference exactly, including ehvi_multi.cc:296-308 leaving the candidate loop with
+ * `break` once one candidate's partial improvement in a cell is below 1e-15 (later candidates of the batch
+ * lose that cell: results depend on the order of the batch, and the reference's own test_multi.py pins it);
+ * mode 1 evaluates every candidate as if it were alone.  k <= 1000 (the reference's static tables).
+ * Host pointers.  No model handle. */
+#define KB200_EHVI3D_REFERENCE 0
+#define KB200_EHVI3D_INDEPENDENT 1
+int kb200_ehvi3d(int device, const double* front, int k, const double* ref, const double* mean,
+                 const double* sdev, long long npop, int mode, double sign, double* out);
+/* Same with device pointers: candidate i, objective c at d_mean[i * inc + c * cinc] (inc = 3, cinc = 1 for
+ * [npop][3]; inc = 1, cinc = npop for one plane per objective); d_front must already be mutually
+ * non-dominated (no filter); runs on `stream`. */
+int kb200_ehvi3d_dev(int device, const double* d_front, int k, const double* ref, const double* d_mean,
+                     const double* d_sdev, long long inc, long long cinc, long long npop, int mode, double sign,
+                     double* d_out, void* stream);
+
 /* Leave-one-out predictions of the installed fit: loo[i] = prediction at sample i of the model
  * refitted without it at the same hyper-parameters (beta re-estimated) -- what
  * supports/krigloocv2.py:7-34 computes with n refits -- in closed form from the factor. */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libkb200.so")
-SOURCES = ["kb200_kernels.cu", "kb200_api.cu", "kb200_kpls.cu", "kb200_ehvi.cu", "kb200_sobol.cu", "kb200_half.cu"]
+SOURCES = ["kb200_kernels.cu", "kb200_api.cu", "kb200_kpls.cu", "kb200_ehvi.cu", "kb200_ehvi3d.cu", "kb200_sobol.cu", "kb200_half.cu"]
 HEADERS = ["kb200_common.cuh", "kb200_corr.cuh", "kb200_kernels.h", os.path.join("..", "..", "include", "kb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -64,6 +64,11 @@ SIGNATURES = {
     "kb200_ehvi2d_dev": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_double, c_void_p,
                                         c_void_p]),
+    "kb200_ehvi3d": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p,
+                                    ctypes.c_longlong, ctypes.c_int, ctypes.c_double, c_void_p]),
+    "kb200_ehvi3d_dev": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p,
+                                        ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
+                                        ctypes.c_double, c_void_p, c_void_p]),
     "kb200_debug_tiles": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p]),
     "kb200_debug_psi": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        ctypes.c_int, c_void_p]),

@@ -1285,6 +1285,99 @@ int kb200_ehvi2d(int device, const double* pareto, int k, const double* ref, con
   return rc;
 }
 
+// ---------------------------------------------------------------- 3-objective EHVI (KMAC replacement)
+static int ehvi3_core(const double* d_front, int n, const double* ref, const double* d_mean, const double* d_sdev,
+                      long inc, long cinc, long npop, int mode, double sign, double* d_out, cudaStream_t st) {
+  if (n < 0 || n > 1000) return fail_arg("kb200_ehvi3d: 0 <= k <= 1000 front points supported (the reference's static tables)");
+  if (mode != 0 && mode != 1) return fail_arg("kb200_ehvi3d: mode must be 0 (reference) or 1 (independent)");
+  const size_t nn = (size_t)n * n, n1 = (size_t)n + 1, np = (size_t)npop;
+  // doubles: coord 3n | xlim nn | ylim nn | slice n1 nn | chunk n1 nn | E, G, EX 3 n1 np each | partial n1 np
+  // then longs first 3 n1, ints rank 3n | hd nn
+  const size_t nd = 3 * (size_t)n + 2 * nn + 2 * n1 * nn + 10 * n1 * np;
+  const size_t bytes = nd * 8 + 3 * n1 * 8 + (3 * (size_t)n + nn) * 4 + 64;
+  unsigned char* ws = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&ws, bytes, st);
+  if (e != cudaSuccess) return fail("kb200_ehvi3d workspace", e);
+  Ehvi3Args a;
+  a.n = n; a.npop = npop; a.mode = mode; a.r0 = ref[0]; a.r1 = ref[1]; a.r2 = ref[2];
+  a.front = d_front;
+  double* p = reinterpret_cast<double*>(ws);
+  a.coord = p; p += 3 * (size_t)n;
+  a.xlim = p; p += nn;
+  a.ylim = p; p += nn;
+  a.slice = p; p += n1 * nn;
+  a.chunk = p; p += n1 * nn;
+  a.E = p; p += 3 * n1 * np;
+  a.G = p; p += 3 * n1 * np;
+  a.EX = p; p += 3 * n1 * np;
+  a.partial = p; p += n1 * np;
+  a.first = reinterpret_cast<long*>(p);
+  a.rank = reinterpret_cast<int*>(a.first + 3 * n1);
+  a.hd = a.rank + 3 * (size_t)n;
+  a.mean = d_mean; a.sdev = d_sdev; a.inc = inc; a.cinc = cinc; a.sign = sign; a.out = d_out;
+  int rc = 0;
+  e = launch_ehvi3(a, st);
+  if (e != cudaSuccess) rc = fail("ehvi3d", e);
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+int kb200_ehvi3d_dev(int device, const double* d_front, int k, const double* ref, const double* d_mean,
+                     const double* d_sdev, long long inc, long long cinc, long long npop, int mode, double sign,
+                     double* d_out, void* stream) {
+  if (!ref || !d_mean || !d_sdev || !d_out || (k > 0 && !d_front)) return fail_arg("kb200_ehvi3d_dev: null argument");
+  if (npop < 1) return 0;
+  CK(cudaSetDevice(device));
+  return ehvi3_core(d_front, k, ref, d_mean, d_sdev, (long)inc, (long)cinc, (long)npop, mode, sign, d_out,
+                    (cudaStream_t)stream);
+}
+
+int kb200_ehvi3d(int device, const double* front, int k, const double* ref, const double* mean, const double* sdev,
+                 long long npop, int mode, double sign, double* out) {
+  if (!ref || !mean || !sdev || !out || (k > 0 && !front)) return fail_arg("kb200_ehvi3d: null argument");
+  if (k < 0) return fail_arg("kb200_ehvi3d: k < 0");
+  if (npop < 1) return 0;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return fail_arg("kb200: no CUDA device (there is no CPU fallback)");
+  // the wrapper's marshalling (kmac_wrapper.cpp:24-34, 80-91): a new point drops the earlier points it dominates or equals
+  std::vector<double> nd;
+  nd.reserve(3 * (size_t)k);
+  for (int i = 0; i < k; ++i) {
+    const double* q = front + 3 * (size_t)i;
+    size_t w = 0;
+    for (size_t j = 0; j < nd.size(); j += 3) {
+      const bool drop = q[0] >= nd[j] && q[1] >= nd[j + 1] && q[2] >= nd[j + 2];
+      if (!drop) { nd[w] = nd[j]; nd[w + 1] = nd[j + 1]; nd[w + 2] = nd[j + 2]; w += 3; }
+    }
+    nd.resize(w);
+    nd.insert(nd.end(), q, q + 3);
+  }
+  const int n = (int)(nd.size() / 3);
+  CK(cudaSetDevice(device));
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const size_t np = (size_t)npop;
+  double* buf = nullptr;    // front [3n] | mean [3 npop] | sdev [3 npop] | out [npop]
+  cudaError_t e = cudaMalloc((void**)&buf, (3 * (size_t)n + 3 + 7 * np) * 8);
+  if (e != cudaSuccess) { cudaStreamDestroy(st); return fail("cudaMalloc", e); }
+  double* d_front = buf;
+  double* d_mean = buf + 3 * (size_t)n + 3;
+  double* d_sdev = d_mean + 3 * np;
+  double* d_out = d_sdev + 3 * np;
+  int rc = 0;
+  auto CKL = [&](cudaError_t err, const char* what) { if (err != cudaSuccess && !rc) rc = fail(what, err); };
+  if (n > 0) CKL(cudaMemcpyAsync(d_front, nd.data(), 3 * (size_t)n * 8, cudaMemcpyHostToDevice, st), "H2D front");
+  CKL(cudaMemcpyAsync(d_mean, mean, 3 * np * 8, cudaMemcpyHostToDevice, st), "H2D mean");
+  CKL(cudaMemcpyAsync(d_sdev, sdev, 3 * np * 8, cudaMemcpyHostToDevice, st), "H2D sdev");
+  if (!rc) rc = ehvi3_core(d_front, n, ref, d_mean, d_sdev, 3, 1, (long)npop, mode, sign, d_out, st);
+  if (!rc) CKL(cudaMemcpyAsync(out, d_out, np * 8, cudaMemcpyDeviceToHost, st), "D2H out");
+  CKL(cudaStreamSynchronize(st), "sync");
+  cudaFree(buf);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
 // debug: raw tile storage of candidate `cand` of the last likelihood batch (tiles_per_mat * 16384 doubles)
 int kb200_debug_tiles(kb200_model* m, int cand, double* out) {
   if (!m || !out) return fail_arg("kb200_debug_tiles: null argument");

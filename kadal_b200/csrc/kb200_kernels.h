@@ -148,6 +148,28 @@ cudaError_t launch_ehvi_tables(const double* P, int k, double r0, double r1, dou
                                cudaStream_t st);
 cudaError_t launch_ehvi_score(const EhviArgs& a, long npop, cudaStream_t st);
 
+// 3-objective EHVI (kb200_ehvi3d.cu); maximisation convention of the reference's KMAC extension
+struct Ehvi3Args {
+  int n;                       // front points (mutually non-dominated)
+  long npop;                   // candidates
+  int mode;                    // 0: reference semantics (order-dependent `break`), 1: every candidate on its own
+  double r0, r1, r2;           // reference point (lower corner)
+  const double* front;         // [n][3]
+  int* rank;                   // [3][n] rank of point i per axis
+  double* coord;               // [3][n] sorted coordinates per axis
+  int* hd;                     // [n][n] highest dominator of node (x, y)
+  double *xlim, *ylim;         // [n][n]
+  double *slice, *chunk;       // [n + 1][n][n]
+  const double *mean, *sdev;   // candidate i, objective c at [i * inc + c * cinc]
+  long inc, cinc;
+  double *E, *G, *EX;          // [3][n + 1][npop]
+  long* first;                 // [3][n + 1]
+  double* partial;             // [n + 1][npop]
+  double sign;
+  double* out;                 // [npop]
+};
+cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st);
+
 // Saltelli sums (kb200_sobol.cu)
 constexpr int SOBOL_BLOCKS = 296;       // 2 x 148
 cudaError_t launch_sobol_compose(const double* A, const double* B, const unsigned char* from_a, long n, int d, double* C,

@@ -7,7 +7,11 @@ the whole population instead of n_pop x n_obj Python calls), the expected improv
 candidate from ``kb200_ehvi2d``.  Like the reference, the kriging *variance* is handed to exi2d
 where a standard deviation is meant (EHVIcomputation.py:57,176) — parity, not a fix.
 
-The 3-objective KMAC path (EHVIcomputation.py:189-251, a C++ extension of its own) is out of scope.
+``ehvi3d_sliceupdate_multi(y_par, ref_point, mean_vector, std_dev)`` stands in for the reference's C++
+extension ``kmac`` (kadal/extern/HDYE_3D_Update/kmac_wrapper.cpp:73-118), ``ehvicalc_kmac3d`` mirrors
+EHVIcomputation.py:189-251 on top of it (``kb200_ehvi3d``).  ``mode="reference"`` (default) reproduces
+KMAC's multi slice-update bit of behaviour for bit of behaviour, including its order-dependent early exit
+(include/kb200.h); ``mode="independent"`` scores every candidate as if it were alone.
 """
 import numpy as np
 
@@ -41,6 +45,43 @@ def exi2d(P, r, mu, s):
     return exi2d_batch(P, r, np.asarray(mu, dtype=float).reshape(1, 2), np.asarray(s, dtype=float).reshape(1, 2))[0]
 
 
+_EHVI3D_MODES = {"reference": 0, "independent": 1, 0: 0, 1: 1}
+
+
+def ehvi3d_sliceupdate_multi(y_par, ref_point, mean_vector, std_dev, mode="reference", sign=1.0):
+    """kmac.ehvi3d_sliceupdate_multi (maximisation): EHVI of every row of mean_vector / std_dev [n_pop, 3] over
+    the front y_par [n_par, 3] with lower corner ref_point."""
+    lib, dev = _device()
+    if mode not in _EHVI3D_MODES:
+        raise ValueError("ehvi3d mode must be 'reference' or 'independent'")
+    P = as_f64(np.asarray(y_par, dtype=float).reshape(-1, 3))
+    r = as_f64(np.asarray(ref_point, dtype=float).reshape(-1))
+    MU = as_f64(np.atleast_2d(mean_vector))
+    S = as_f64(np.atleast_2d(std_dev))
+    if r.shape[0] != 3 or MU.shape[1] != 3 or S.shape != MU.shape:
+        raise ValueError("ehvi3d: three objectives expected (ref (3,), mean (n,3), std (n,3))")
+    out = np.empty(MU.shape[0])
+    check(lib.kb200_ehvi3d(dev, ptr(P), P.shape[0], ptr(r), ptr(MU), ptr(S), MU.shape[0], _EHVI3D_MODES[mode],
+                           float(sign), ptr(out)))
+    return out
+
+
+def ehvicalc_kmac3d(x, y_par, moboInfo, kriglist, pool=None, mode="reference"):
+    """EHVIcomputation.py:189-251: -EHVI (KMAC, 3 objectives) for a population x [n_pop, n_dv]; a float for a
+    1-D x.  Like the reference the kriging variance SSqr is handed over where KMAC expects a standard
+    deviation (:235), and the inputs are negated because KMAC maximises.  ``pool`` is ignored."""
+    x = np.asarray(x, dtype=float)
+    reshape = x.ndim == 1
+    if reshape:
+        x = x.reshape(1, -1)
+    if len(kriglist) != 3:
+        raise ValueError("ehvicalc_kmac3d needs three objectives")
+    pred, SSqr = _pred_ssqr(x, kriglist)
+    ref_point = np.asarray(moboInfo["refpoint"], dtype=float)
+    hv = ehvi3d_sliceupdate_multi(-np.asarray(y_par, dtype=float), -ref_point, -pred, SSqr, mode=mode, sign=-1.0)
+    return hv[0] if reshape else hv
+
+
 def _pred_ssqr(x, kriglist):
     from .prediction import predict_arrays
     n_pop = x.shape[0]
@@ -62,8 +103,8 @@ def ehvicalc_vec(x, y_par, moboInfo, kriglist, pool=None):
     if reshape:
         x = x.reshape(1, -1)
     if len(kriglist) != 2:
-        raise NotImplementedError("kadal_b200: EHVI for %d objectives is not supported (2-D exi2d only; the "
-                                  "3-D path is the KMAC C++ extension)" % len(kriglist))
+        raise NotImplementedError("kadal_b200: ehvicalc_vec is the 2-objective exi2d path (EHVIcomputation.py:129); "
+                                  "use ehvicalc_kmac3d for three objectives")
     pred, SSqr = _pred_ssqr(x, kriglist)
     hv = exi2d_batch(y_par, moboInfo["refpoint"], pred, SSqr, sign=-1.0)
     return hv[0] if reshape else hv
