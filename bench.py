@@ -553,7 +553,50 @@ def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
     out["c5_kpls_score"] = {"workload": "C5: pred + SSqr (EHVI inputs) over %d candidates per GPU" % nc, "pts_per_s_per_gpu": pts,
                             "ms": ms, "fp64_tflops_algorithmic": pts * (n * n + n * (3 * d + 6 * h + 20)) / 1e12}
     m.close()
+    out["c5_ehvi3d"] = ehvi3d_bench(rank, local_rank, world, torch, timed, dev)
     return out
+
+
+def ehvi3d_bench(rank, local_rank, world, torch, timed, dev):
+    """C5's 3-objective scoring step: kb200_ehvi3d over 1000 candidates and a 100-point front (the largest batch
+    the reference's static tables hold), both batch semantics, device-resident inputs; at N=1 the reference's own
+    C++ (oracle/_ref/libkmac_ref.so, built from /root/reference in the build container) is timed beside it."""
+    import ctypes
+    from kadal_b200 import _capi
+    lib = _capi.load()
+    rng = np.random.default_rng(5)
+    k, npop = 100, 1000
+    v = np.abs(rng.standard_normal((k, 3)))
+    P = -10 + 9.5 * v / np.linalg.norm(v, axis=1, keepdims=True)
+    mu, sd = rng.uniform(-10.2, -0.5, (npop, 3)), rng.uniform(0.3, 2.5, (npop, 3))
+    ref = np.array([-10.0, -10.0, -10.0])
+    dP, dmu, dsd = (torch.from_numpy(a).to(dev) for a in (P, mu, sd))
+    o = torch.empty(npop, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    res = {"workload": "C5 scoring: 3-objective EHVI (KMAC) of %d candidates over a %d-point front per GPU" % (npop, k)}
+    for mode, name in ((0, "reference_semantics"), (1, "independent")):
+        def run():
+            _capi.check(lib.kb200_ehvi3d_dev(local_rank, dP.data_ptr(), k, _capi.ptr(ref), dmu.data_ptr(), dsd.data_ptr(),
+                                             3, 1, npop, mode, 1.0, o.data_ptr(), ctypes.c_void_p(stream)))
+        ms = timed(run, 5)
+        res[name] = {"ms": ms, "candidates_per_s_per_gpu": npop / (ms * 1e-3), "positive": int((o > 0).sum().item())}
+    if rank == 0 and world == 1:
+        try:
+            from oracle import kmac_ref_loader as kr   # checker / CPU baseline only
+            if kr.available():
+                t0 = time.perf_counter()
+                kr.ehvi3d_multi(P, ref, mu, sd)
+                t_batch = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                for i in range(20):
+                    kr.ehvi3d_multi(P, ref, mu[i:i + 1], sd[i:i + 1])
+                t_one = (time.perf_counter() - t0) / 20
+                res["cpu_reference"] = {"kind": "reference", "cores": 1, "batch_ms": t_batch * 1e3,
+                                        "one_candidate_alone_ms": t_one * 1e3,
+                                        "sample": "the batch once (its early exit skips most of the work); 20 candidates one by one"}
+        except Exception as exc:   # the baseline is optional
+            res["cpu_reference"] = {"unavailable": str(exc)[:100]}
+    return res
 
 
 def main():
