@@ -194,7 +194,7 @@ def run_reference(args, rank):
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(budget_s=14.0):
@@ -229,9 +229,8 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and WARN: main() has pointed fd 1 at
+        # stderr, the JSON line goes to the saved descriptor)
         dist.init_process_group("nccl", device_id=dev)
 
     X, y, pop = population(rank)
@@ -411,7 +410,7 @@ def run_ours(args, rank, local_rank, world):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -599,7 +598,26 @@ def ehvi3d_bench(rank, local_rank, world, torch, timed, dev):
     return res
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line, on the process's real stdout."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries write to fd 1 behind Python's back (NCCL's version banner, torchrun notices): point fd 1 at stderr
+    # for the whole run and keep the real stdout for the JSON line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -619,7 +637,7 @@ def main():
         # launched without torchrun: re-exec under torch.distributed.run
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))   # the child gets the real stdout as its fd 1
     run_ours(args, rank, local_rank, world)
 
 

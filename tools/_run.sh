@@ -1,4 +1,10 @@
 O=gpurun_out; mkdir -p $O
-python -m pytest tests/test_ehvi3d.py tests/test_ehvi.py -m gpu -q -x 2>&1 | tail -15 | tee $O/pytest_e3.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python -m pytest tests -m gpu -q -x > $O/pytest_r1p.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_r1p.log; tail -5 $O/pytest_r1p.log
+python bench.py --steps 10 --warmup 3 > $O/bench_r1p.json 2> $O/bench_r1p.err; echo "bench rc=$?"; python - <<'PY'
+import json
+j=json.load(open('gpurun_out/bench_r1p.json'))
+print(j['value'], j['ms_per_step'], j['e2e']['value'], j['roofline']['frac'], j['clocks'])
+print(json.dumps(j['other_configs']['c5_ehvi3d'], indent=1))
+print(j['cpu_baseline'])
+PY
+tail -3 $O/bench_r1p.err
+python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -2
