@@ -14,6 +14,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python tools/prof_run.py pred 2 > $O/plain_pred.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_pred_$TAG.csv python tools/prof_run.py pred 2 > $O/ncu_pred.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'chol_diag|chol_panel|corr_tile|lik_finalize' -s 17 -c 17 -f -o $O/prof_lik_$TAG python tools/prof_run.py lik 2 > $O/ncu_full_lik.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'chol_panel|corr_tile|predict_epi' -s 4 -c 4 -f -o $O/prof_pred_$TAG python tools/prof_run.py pred 2 > $O/ncu_full_pred.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'predict_small|chol_panel|corr_tile|predict_epi' -s 2 -c 3 -f -o $O/prof_pred_$TAG python tools/prof_run.py pred 2 > $O/ncu_full_pred.log 2>&1
 ls -la $O
 fi
