@@ -94,6 +94,12 @@ struct kb200_model {
   // tile j + 1 (latency-bound POTF2) runs under them (factorize())
   cudaStream_t gside[MAXG] = {nullptr};
   cudaEvent_t ev_d[MAXG] = {nullptr}, ev_p[MAXG] = {nullptr}, ev_asm[MAXG] = {nullptr};
+  // $KB200_PRIO: 1 = the diagonal kernels of every group run on a high-priority stream of their own (their CTAs
+  // are placed as soon as a slot frees instead of behind the other group's queued panel CTAs); 2 = the group
+  // streams themselves get descending priorities (group 0 never waits for group 1)
+  int prio = 0;
+  cudaStream_t gprio[MAXG] = {nullptr};
+  cudaEvent_t ev_q[MAXG] = {nullptr}, ev_r[MAXG] = {nullptr};
   bool stagger = false;     // measured: 8.35 vs 8.28 ms at two groups, worse with more ($KB200_STAGGER=1 to try)
   bool dual = false;        // measured: no gain over two candidate groups at P = 512 (8.32 ms both), kept as an option ($KB200_DUAL=1)
   int dual_env = -1;
@@ -220,8 +226,17 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
     if (eg) m->ngroups = std::max(1, std::min((int)kb200_model::MAXG, atoi(eg)));
     const char* em = getenv("KB200_GROUP_MIN");
     if (em) m->group_min = std::max(1, atoi(em));
+    {
+      const char* ep = getenv("KB200_PRIO");
+      if (ep) m->prio = atoi(ep);
+    }
+    int prio_least = 0, prio_greatest = 0;
+    MCK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     for (int g = 0; g < m->ngroups; ++g) {
-      MCK(cudaStreamCreateWithFlags(&m->gstream[g], cudaStreamNonBlocking));
+      if (m->prio == 2)
+        MCK(cudaStreamCreateWithPriority(&m->gstream[g], cudaStreamNonBlocking, std::min(prio_least, prio_greatest + g)));
+      else
+        MCK(cudaStreamCreateWithFlags(&m->gstream[g], cudaStreamNonBlocking));
       MCK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
       MCK(cudaEventCreateWithFlags(&m->ev_asm[g], cudaEventDisableTiming));
     }
@@ -292,6 +307,9 @@ void kb200_model_destroy(kb200_model* m) {
   for (int g = 0; g < kb200_model::MAXG; ++g) {
     if (m->gstream[g]) cudaStreamDestroy(m->gstream[g]);
     if (m->gside[g]) cudaStreamDestroy(m->gside[g]);
+    if (m->gprio[g]) cudaStreamDestroy(m->gprio[g]);
+    if (m->ev_q[g]) cudaEventDestroy(m->ev_q[g]);
+    if (m->ev_r[g]) cudaEventDestroy(m->ev_r[g]);
     if (m->ev_d[g]) cudaEventDestroy(m->ev_d[g]);
     if (m->ev_p[g]) cudaEventDestroy(m->ev_p[g]);
     if (m->ev_asm[g]) cudaEventDestroy(m->ev_asm[g]);
@@ -520,8 +538,25 @@ static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z
     a.fuse_diag = 0;
     const int nt = m->nt;
     if (!m->dual || nt < 3) {
+      const bool hp = m->prio == 1 && nt >= 2;
+      if (hp && !m->gprio[g]) {
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&m->gprio[g], cudaStreamNonBlocking, greatest));
+        CK(cudaEventCreateWithFlags(&m->ev_q[g], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&m->ev_r[g], cudaEventDisableTiming));
+      }
       for (int j = 0; j < nt; ++j) {
-        {
+        if (hp) {
+          CK(cudaEventRecord(m->ev_q[g], st));
+          CK(cudaStreamWaitEvent(m->gprio[g], m->ev_q[g], 0));
+          {
+            Timed t(m, KB200_PROF_DIAG, m->gprio[g]);
+            CK(launch_chol_diag_half(a, j, Pb, m->gprio[g]));
+          }
+          CK(cudaEventRecord(m->ev_r[g], m->gprio[g]));
+          CK(cudaStreamWaitEvent(st, m->ev_r[g], 0));
+        } else {
           Timed t(m, KB200_PROF_DIAG, st);
           CK(launch_chol_diag_half(a, j, Pb, st));
         }

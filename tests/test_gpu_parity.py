@@ -271,6 +271,17 @@ def test_return_types_and_errors(kb, golden_c):
         kb.likelihood(np.zeros(9), info, "default", tv)                   # nuggetset: no such layout
 
 
+def test_empty_population_and_empty_point_set(kb, golden_c):
+    info, x, tv = cases.appendix_c_info(golden_c, "gaussian")
+    nll, inf = kb.likelihood_batch(np.zeros((0, len(x))), info, tv)
+    assert nll.shape == (0,) and inf.shape == (0,)
+    kb.likelihood(x.copy(), info, "all", tv)
+    res = kb.predict_arrays(np.zeros((0, 4)), info, ("pred", "ssqr"))
+    assert res["pred"].shape == (0,) and res["ssqr"].shape == (0,)
+    from kadal_b200 import ehvi
+    assert ehvi.ehvi3d_sliceupdate_multi(np.zeros((0, 3)), [0.0, 0, 0], np.zeros((0, 3)), np.zeros((0, 3))).shape == (0,)
+
+
 def test_not_positive_definite_is_reported_per_candidate(kb):
     # KPLS-exponential with signed coefficients gives "distances" of either sign, hence
     # correlations > 1: an indefinite Psi, robustly -- unlike an exactly

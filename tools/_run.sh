@@ -1,10 +1,4 @@
-O=gpurun_out; mkdir -p $O
-python bench.py --steps 10 --warmup 3 > $O/bench_r1p.json 2> $O/bench_r1p.err; echo "bench rc=$?"; python - <<'PY'
-import json
-j=json.load(open('gpurun_out/bench_r1p.json'))
-print(j['value'], j['ms_per_step'], j['e2e']['value'], j['roofline']['frac'], j['clocks'])
-print(json.dumps(j['other_configs']['c5_ehvi3d'], indent=1))
-print(j['cpu_baseline'])
-PY
-tail -3 $O/bench_r1p.err
-python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -2
+O=gpurun_out
+python tools/sanitize_small.py > $O/sanitize_plain.log 2>&1; echo "plain rc=$?"; tail -3 $O/sanitize_plain.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_small.py > $O/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -c "Invalid\|out of bounds" $O/sanitize_memcheck.log; tail -4 $O/sanitize_memcheck.log
+timeout 900 compute-sanitizer --tool initcheck --error-exitcode 7 python tools/sanitize_small.py > $O/sanitize_initcheck.log 2>&1; echo "initcheck rc=$?"; tail -4 $O/sanitize_initcheck.log
