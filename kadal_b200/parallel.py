@@ -28,6 +28,18 @@ def _world(group=None):
     return dist.get_world_size(group), dist.get_rank(group)
 
 
+def comm_device(group=None):
+    """Where tensors of a collective are staged: the rank's own GPU for NCCL -- chosen by the same rule as the
+    compute path ($KADAL_B200_DEVICE, else $LOCAL_RANK), not torch's current device, which is cuda:0 on every
+    rank unless the caller has set it -- and the host for gloo."""
+    import os
+    import torch
+    if _dist().get_backend(group) == "nccl":
+        k = int(os.environ.get("KADAL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        return "cuda:%d" % (k % max(1, torch.cuda.device_count()))
+    return "cpu"
+
+
 def all_gather_rows(local, n_total, group=None, device=None):
     """Gather the per-rank slices (``shard_bounds`` order) of a 1-D / 2-D float64 or int32 array
     into the full array on every rank.  Uses the group's backend: tensors are staged on
@@ -39,7 +51,7 @@ def all_gather_rows(local, n_total, group=None, device=None):
     if world == 1:
         return local
     if device is None:
-        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        device = comm_device(group)
     counts = [shard_bounds(n_total, world, r) for r in range(world)]
     width = int(np.prod(local.shape[1:])) if local.ndim > 1 else 1
     maxc = max(hi - lo for lo, hi in counts)

@@ -29,7 +29,7 @@ def akmcs_reductions(init_samp, KrigInfo, group=None):
     if world > 1:
         import torch
         import torch.distributed as dist
-        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        dev = parallel.comm_device(group)
         sizes = torch.zeros(world, dtype=torch.int64, device=dev)
         sizes[rank] = nmc
         dist.all_reduce(sizes, group=group)

@@ -45,7 +45,7 @@ def sobol_sums(A, B, KrigInfo, column_sets, group=None):
     if world > 1:
         import torch
         import torch.distributed as dist
-        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        dev = parallel.comm_device(group)
         t = torch.from_numpy(np.concatenate([base, yayc, ybyc])).to(dev)
         dist.all_reduce(t, group=group)
         v = t.cpu().numpy()
