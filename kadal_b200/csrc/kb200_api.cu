@@ -1326,9 +1326,10 @@ static int ehvi3_core(const double* d_front, int n, const double* ref, const dou
   if (n < 0 || n > 1000) return fail_arg("kb200_ehvi3d: 0 <= k <= 1000 front points supported (the reference's static tables)");
   if (mode != 0 && mode != 1) return fail_arg("kb200_ehvi3d: mode must be 0 (reference) or 1 (independent)");
   const size_t nn = (size_t)n * n, n1 = (size_t)n + 1, np = (size_t)npop;
-  // doubles: coord 3n | xlim nn | ylim nn | slice n1 nn | chunk n1 nn | E, G, EX 3 n1 np each | partial n1 np
+  // doubles: coord 3n | xlim nn | ylim nn | slice n1 nn | chunk n1 nn | E, G, EX 3 n1 np each | partial ysplit n1 np
   // then longs first 3 n1, ints rank 3n | hd nn
-  const size_t nd = 3 * (size_t)n + 2 * nn + 2 * n1 * nn + 10 * n1 * np;
+  const int ysplit = ehvi3_ysplit(n, npop);
+  const size_t nd = 3 * (size_t)n + 2 * nn + 2 * n1 * nn + (9 + (size_t)ysplit) * n1 * np;
   const size_t bytes = nd * 8 + 3 * n1 * 8 + (3 * (size_t)n + nn) * 4 + 64;
   unsigned char* ws = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&ws, bytes, st);
@@ -1345,7 +1346,8 @@ static int ehvi3_core(const double* d_front, int n, const double* ref, const dou
   a.E = p; p += 3 * n1 * np;
   a.G = p; p += 3 * n1 * np;
   a.EX = p; p += 3 * n1 * np;
-  a.partial = p; p += n1 * np;
+  a.partial = p; p += (size_t)ysplit * n1 * np;
+  a.ysplit = ysplit;
   a.first = reinterpret_cast<long*>(p);
   a.rank = reinterpret_cast<int*>(a.first + 3 * n1);
   a.hd = a.rank + 3 * (size_t)n;

@@ -90,15 +90,22 @@ __global__ void ehvi3_slice_kernel(Ehvi3Args A) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z > n) return;
   double* sl = A.slice + (size_t)z * n * n;
-  const double* X = A.coord;
-  const double* Y = A.coord + n;
+  const double* __restrict__ X = A.coord;
+  const double* __restrict__ Y = A.coord + n;
+  const int* __restrict__ hd = A.hd;
   for (int y = 0; y < n; ++y) {
     const double wy = __dsub_rn(Y[y], A.r1);
+    // rows do not overlap: `restrict` lets the loads of the row above run ahead of the stores of this row
+    // (the chain through `left` is a few cycles per node, an un-hoisted load is an L2 round trip per node)
+    const double* __restrict__ prev = sl + (size_t)(y > 0 ? y - 1 : 0) * n;
+    double* __restrict__ cur = sl + (size_t)y * n;
+    const int* __restrict__ hrow = hd + (size_t)y * n;
     double left = 0.0, upleft = 0.0;
+#pragma unroll 8
     for (int x = 0; x < n; ++x) {
-      const double up = y > 0 ? sl[x + (y - 1) * n] : 0.0;
+      const double up = y > 0 ? prev[x] : 0.0;
       double v;
-      if (A.hd[x + y * n] < z) {
+      if (hrow[x] < z) {
         if (x > 0 && y > 0) v = __dadd_rn(__dsub_rn(up, upleft), left);
         else if (y > 0) v = up;
         else if (x > 0) v = left;
@@ -106,7 +113,7 @@ __global__ void ehvi3_slice_kernel(Ehvi3Args A) {
       } else {
         v = __dmul_rn(__dsub_rn(X[x], A.r0), wy);
       }
-      sl[x + y * n] = v;
+      cur[x] = v;
       left = v;
       upleft = up;
     }
@@ -171,6 +178,8 @@ __global__ void __launch_bounds__(E3_THREADS)
 ehvi3_score_kernel(Ehvi3Args A) {
   extern __shared__ double sm[];
   const int n = A.n, n1 = n + 1, z = blockIdx.y;
+  const int ys = blockIdx.z, nys = gridDim.z;            // this CTA's share of the grid rows of level z
+  const int y_lo = (int)((long)n1 * ys / nys), y_hi = (int)((long)n1 * (ys + 1) / nys);
   double* c_sm = sm;             // [n1]
   double* c_s0 = c_sm + n1;
   double* c_s1 = c_s0 + n1;
@@ -194,7 +203,7 @@ ehvi3_score_kernel(Ehvi3Args A) {
     e3 = A.E[o]; g3 = A.G[o]; ex3 = A.EX[o];
   }
   double acc = 0.0;
-  for (int y = 0; y <= n; ++y) {
+  for (int y = y_lo; y < y_hi; ++y) {
     const double cl1 = y == 0 ? A.r1 : Y[y - 1], cu1 = y == n ? INFINITY : Y[y];
     const double len1 = __dsub_rn(cu1, cl1);
     const long fyz = min(fz, A.first[n1 + y]);
@@ -249,13 +258,13 @@ ehvi3_score_kernel(Ehvi3Args A) {
       if (t > 0.0) acc = __dadd_rn(acc, t);
     }
   }
-  if (mine) A.partial[(size_t)z * np + i] = acc;
+  if (mine) A.partial[((size_t)z * nys + ys) * np + i] = acc;
 }
 
 __global__ void ehvi3_sum_kernel(Ehvi3Args A) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.npop; i += (long)gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (int z = 0; z <= A.n; ++z) s = __dadd_rn(s, A.partial[(size_t)z * A.npop + i]);
+    for (int q = 0; q < (A.n + 1) * A.ysplit; ++q) s = __dadd_rn(s, A.partial[(size_t)q * A.npop + i]);
     A.out[i] = A.sign * s;
   }
 }
@@ -263,6 +272,14 @@ __global__ void ehvi3_sum_kernel(Ehvi3Args A) {
 }  // namespace
 
 size_t ehvi3_smem_bytes(int n) { return (size_t)(n + 1) * 8 * sizeof(double); }
+
+// grid rows of a z level are split over `ysplit` CTAs so that a small population still fills the machine
+// (about eight 128-thread CTAs per SM); every split re-reads the level's tables from L2, so no more than that
+int ehvi3_ysplit(int n, long npop) {
+  const long ctas = ((npop + E3_THREADS - 1) / E3_THREADS) * (n + 1);
+  long want = (148L * 8 + ctas - 1) / ctas;
+  return (int)max(1L, min(want, min((long)(n + 1), 16L)));
+}
 
 cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st) {
   const int n = a.n, n1 = n + 1;
@@ -288,7 +305,7 @@ cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(ehvi3_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
   }
-  ehvi3_score_kernel<<<dim3((unsigned)((a.npop + E3_THREADS - 1) / E3_THREADS), n1), E3_THREADS, sm, st>>>(a);
+  ehvi3_score_kernel<<<dim3((unsigned)((a.npop + E3_THREADS - 1) / E3_THREADS), n1, a.ysplit), E3_THREADS, sm, st>>>(a);
   E3_CHECK();
   ehvi3_sum_kernel<<<blocks(a.npop, 128), 128, 0, st>>>(a);
   E3_CHECK();

@@ -164,11 +164,13 @@ struct Ehvi3Args {
   long inc, cinc;
   double *E, *G, *EX;          // [3][n + 1][npop]
   long* first;                 // [3][n + 1]
-  double* partial;             // [n + 1][npop]
+  int ysplit;                  // CTAs per z level along y (ehvi3_ysplit)
+  double* partial;             // [(n + 1) * ysplit][npop]
   double sign;
   double* out;                 // [npop]
 };
 cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st);
+int ehvi3_ysplit(int n, long npop);
 
 // Saltelli sums (kb200_sobol.cu)
 constexpr int SOBOL_BLOCKS = 296;       // 2 x 148
