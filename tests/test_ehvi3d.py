@@ -96,6 +96,40 @@ def test_cuda_ehvi3d_matches_reference_golden_and_known_answers():
         ehvi.ehvi3d_sliceupdate_multi(mk.KAT_MULTI_FRONT, mk.KAT_REF[:2], mk.KAT_MULTI_MEAN, np.zeros((3, 3)))
 
 
+def tied_front(rng, k):
+    """Integer-valued objectives: many equal coordinates (zero-length cells, ties in the three sort orders)."""
+    P = rng.integers(-9, 0, (40, 3)).astype(float)
+    nd = [i for i in range(len(P)) if not any((P[j] >= P[i]).all() and (P[j] > P[i]).any() for j in range(len(P)))]
+    P = np.unique(P[nd], axis=0)[:k]
+    return P[rng.permutation(len(P))]
+
+
+@pytest.mark.skipif(not kr.available(), reason="oracle/_ref/libkmac_ref.so not built")
+def test_oracle_matches_the_compiled_reference_on_tied_coordinates():
+    rng = np.random.default_rng(11)
+    r = np.array([-10.0, -10.0, -10.0])
+    for _ in range(6):
+        P = tied_front(rng, int(rng.integers(2, 12)))
+        mu, s = rng.uniform(-10, -1, (15, 3)), rng.uniform(0.2, 2, (15, 3))
+        assert err(eo.ehvi3d_multi(P, r, mu, s), kr.ehvi3d_multi(P, r, mu, s), P, r) < TOL
+
+
+@pytest.mark.gpu
+def test_cuda_ehvi3d_tied_coordinates():
+    from kadal_b200 import ehvi
+    rng = np.random.default_rng(12)
+    r = np.array([-10.0, -10.0, -10.0])
+    for _ in range(6):
+        P = tied_front(rng, int(rng.integers(2, 12)))
+        mu, s = rng.uniform(-10, -1, (33, 3)), rng.uniform(0.2, 2, (33, 3))
+        mu[4] = P[0]                                   # a mean exactly on a (tied) grid line
+        for mode, indep in (("reference", False), ("independent", True)):
+            got = ehvi.ehvi3d_sliceupdate_multi(P, r, mu, s, mode=mode)
+            assert err(got, eo.ehvi3d_multi(P, r, mu, s, independent=indep), P, r) < TOL
+            if kr.available() and not indep:
+                assert err(got, kr.ehvi3d_multi(P, r, mu, s), P, r) < TOL
+
+
 @pytest.mark.gpu
 def test_cuda_ehvi3d_large_front_and_population():
     """BASELINE config 5's scoring shape: 1500 candidates (more than the reference's static tables hold: 1000)
