@@ -160,6 +160,16 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------ reference arm (CPU)
+def all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is entitled to all host threads."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=os.cpu_count())
+        return max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        return None
+
+
 def run_reference(args, rank):
     """The reference's own CPU implementation of the path, timed on this box's host cores.
     KADAL is pure Python (numpy/scipy) and /root/reference does not travel to the GPU box, so
@@ -167,6 +177,7 @@ def run_reference(args, rank):
     tests/test_oracle.py pins bit-for-bit to the live reference (kind = "port")."""
     if rank != 0:
         return
+    all_host_threads()
     from oracle import kriging_oracle as ko
     X, y, pop = c2_data()
     info = ko.make_kriginfo(X, y)
@@ -198,6 +209,7 @@ def run_reference(args, rank):
 
 
 def cpu_baseline(budget_s=14.0):
+    all_host_threads()
     from oracle import kriging_oracle as ko
     X, y, pop = c2_data()
     info = ko.make_kriginfo(X, y)
