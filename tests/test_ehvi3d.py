@@ -4,8 +4,9 @@ CPU: oracle/ehvi3d_oracle.py against the reference's own known answers (test_sin
 against tests/golden/ehvi3d.npz (outputs of the reference's C++ compiled by oracle/kmac_ref/Makefile) and, when
 oracle/_ref/libkmac_ref.so is present, against that library live.  GPU: kb200_ehvi3d through the C ABI against the
 same.  KMAC is not covered by the north star's tolerances; the CUDA terms differ from the reference's only through
-the last ulp of erf / exp, the bound used is 1e-11 relative to max(|ref|, 1e-6 x the volume of the box between the
-reference point and the front's upper corner)."""
+the last ulp of erf / exp, the bound used is 1e-11 relative to max(|ref|, 1e-3 x the volume of the box between the
+reference point and the front's upper corner) -- a cell is a difference of terms of the size of that box, so this
+is a few hundred ulps of them, the same convention as the 2-objective tests."""
 import importlib.util
 import os
 
@@ -29,7 +30,7 @@ def golden_cases():
 
 def err(got, ref, P, r):
     box = np.prod((P.max(axis=0) if len(P) else r + 10.0) - r)
-    return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6 * box)))
+    return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3 * box)))
 
 
 def test_oracle_reproduces_the_references_known_answers():

@@ -1,7 +1,5 @@
-python -m pytest tests/test_ehvi3d.py -m gpu -q -x 2>&1 | tail -3
-python tools/prof_ehvi3d.py 100 1000 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_ehvi3d.csv python tools/prof_ehvi3d.py 100 1000 > /dev/null 2>&1
-python - <<'PY'
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/launches_ehvi3d.csv')) if len(r)>10 and r[0].isdigit()]
-for r in rows[-8:]: print(r[4][:40], r[7], r[8], r[-1])
-PY
+O=gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python -m pytest tests -m gpu -q > $O/pytest_r1q.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_r1q.log
+python bench.py --steps 10 --warmup 3 > $O/bench_r1q.json 2> $O/bench_r1q.err; echo "bench rc=$?"; wc -l $O/bench_r1q.json; python -c "
+import json; j=json.load(open('gpurun_out/bench_r1q.json')); print(j['value'], j['e2e']['value'], j['predict']['value'], j['other_configs']['c5_ehvi3d']['independent'], j['cpu_baseline']['value'])"
