@@ -101,21 +101,37 @@ __global__ void ehvi3_slice_kernel(Ehvi3Args A) {
     double* __restrict__ cur = sl + (size_t)y * n;
     const int* __restrict__ hrow = hd + (size_t)y * n;
     double left = 0.0, upleft = 0.0;
-#pragma unroll 8
-    for (int x = 0; x < n; ++x) {
-      const double up = y > 0 ? prev[x] : 0.0;
-      double v;
-      if (hrow[x] < z) {
-        if (x > 0 && y > 0) v = __dadd_rn(__dsub_rn(up, upleft), left);
-        else if (y > 0) v = up;
-        else if (x > 0) v = left;
-        else v = 0.0;
-      } else {
-        v = __dmul_rn(__dsub_rn(X[x], A.r0), wy);
+    for (int x0 = 0; x0 < n; x0 += 8) {
+      // eight nodes per trip: their loads are issued together (one L2 round trip per eight nodes instead of
+      // one per node: the chain through `left` is only a few cycles long)
+      double upv[8], xv[8];
+      int hv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int x = min(x0 + u, n - 1);
+        upv[u] = y > 0 ? prev[x] : 0.0;
+        hv[u] = hrow[x];
+        xv[u] = X[x];
       }
-      cur[x] = v;
-      left = v;
-      upleft = up;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int x = x0 + u;
+        if (x < n) {
+          const double up = upv[u];
+          double v;
+          if (hv[u] < z) {
+            if (x > 0 && y > 0) v = __dadd_rn(__dsub_rn(up, upleft), left);
+            else if (y > 0) v = up;
+            else if (x > 0) v = left;
+            else v = 0.0;
+          } else {
+            v = __dmul_rn(__dsub_rn(xv[u], A.r0), wy);
+          }
+          cur[x] = v;
+          left = v;
+          upleft = up;
+        }
+      }
     }
   }
 }
@@ -207,6 +223,8 @@ ehvi3_score_kernel(Ehvi3Args A) {
     const double cl1 = y == 0 ? A.r1 : Y[y - 1], cu1 = y == n ? INFINITY : Y[y];
     const double len1 = __dsub_rn(cu1, cl1);
     const long fyz = min(fz, A.first[n1 + y]);
+    // reference semantics: an early exit in front of every candidate of this CTA empties the whole grid row
+    if ((long)blockIdx.x * E3_THREADS >= fyz) continue;        // (uniform: depends on the CTA, y and z only)
     __syncthreads();
     for (int x = threadIdx.x; x <= n; x += E3_THREADS) {        // ehvi_multi.cc:241-282
       const double cl0 = x == 0 ? A.r0 : X[x - 1], cu0 = x == n ? INFINITY : X[x];
