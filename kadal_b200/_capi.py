@@ -82,7 +82,8 @@ class Kb200Error(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB
+    # $KB200_LIB: an alternative build of the same sources (A/B tools only, e.g. tools/ab_predict_div.py)
+    return os.environ.get("KB200_LIB") or _build.LIB
 
 
 def load():

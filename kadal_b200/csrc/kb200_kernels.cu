@@ -25,6 +25,11 @@ namespace kb200 {
 // (prediction).  256 threads; lane -> (row = lane/4, 32-byte chunk = lane%4), so a warp
 // writes 8 consecutive 128-byte lines of a slab (1 KiB contiguous).
 constexpr int CORR_THREADS = 256;
+// 1: the prediction kernels divide by theta^2 exactly like the likelihood assembly (the first design);
+// 0: they multiply by the correctly rounded reciprocal (kb200_corr.cuh:gauss_term)
+#ifndef KB200_PREDICT_EXACT_DIV
+#define KB200_PREDICT_EXACT_DIV 0
+#endif
 #ifndef KB200_CORR_FAST_BLOCKS
 #define KB200_CORR_FAST_BLOCKS 3
 #endif
@@ -67,7 +72,7 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
         }
       }
       if (need) {
-        if (FAST) q = corr_quad_gauss(d, th2, th2 + d, w0, As + row * lda, Bt + c0, TB);
+        if (FAST) q = corr_quad_gauss<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV>(d, th2, th2 + d, w0, As + row * lda, Bt + c0, TB);
         else q = corr_quad(A.spec, cand, As + row * lda, Bt + c0, TB);
       } else {
         q = quad_set(0.0);
@@ -1474,8 +1479,13 @@ __device__ __forceinline__ void gauss_pair_sum(int d, const double* th2, const d
     const double2 b = *reinterpret_cast<const double2*>(bt2 + k * 256);
     const double t2 = th2[k], r2 = th2[PS_MAXD + k];
     const double d0 = __dsub_rn(ak, b.x), d1 = __dsub_rn(ak, b.y);
-    t0 = div_by_rcp(__dmul_rn(d0, d0), t2, r2);
-    t1 = div_by_rcp(__dmul_rn(d1, d1), t2, r2);
+    if (KB200_PREDICT_EXACT_DIV) {
+      t0 = div_by_rcp(__dmul_rn(d0, d0), t2, r2);
+      t1 = div_by_rcp(__dmul_rn(d1, d1), t2, r2);
+    } else {            // prediction: d^2 * RN(1/theta^2), see gauss_term
+      t0 = __dmul_rn(__dmul_rn(d0, d0), r2);
+      t1 = __dmul_rn(__dmul_rn(d1, d1), r2);
+    }
   };
   if (d < 8) {
     S0 = 0.0; S1 = 0.0;
