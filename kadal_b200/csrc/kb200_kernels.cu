@@ -73,7 +73,7 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
       }
       if (need) {
         if (FAST) q = corr_quad_gauss<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV>(d, th2, th2 + d, w0, As + row * lda, Bt + c0, TB);
-        else q = corr_quad(A.spec, cand, As + row * lda, Bt + c0, TB);
+        else q = corr_quad<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV>(A.spec, cand, As + row * lda, Bt + c0, TB);
       } else {
         q = quad_set(0.0);
       }
