@@ -84,6 +84,19 @@ int kb200_fit_state(kb200_model* m, const double* x, int nbhyp, int trainvar,
                     double* nll, int* info, double* theta_log10, double* nugget_out,
                     double* wgkf);
 
+/* The same call after ONE sample was stacked under X, y and F -- what the Kriging believer of
+ * optim_tools/MOBO.py:344-356 and the sequential updates of reliability_analysis/akmcs.py:127-139 and
+ * optim_tools/SOBO.py:137-145 do when they re-run likelihood(KrigInfo['Theta'], KrigInfo, mode='all') at unchanged
+ * hyper-parameters.  `next` is a model of n + 1 samples whose first n rows are the samples of `prev` (the caller
+ * checks that), `prev` holds the fit of the same x (kb200_fit_state or kb200_fit_append).  The factor of the bordered
+ * matrix is the old factor plus one row (O(n^2): one triangular solve with the old factor) instead of a new O(n^3)
+ * factorisation; outputs, installed predictor and error reporting are those of kb200_fit_state on `next`.
+ * Fails (< 0, nothing installed) if the hyper-parameters decoded from x differ from those of prev's fit or the two
+ * models do not match; the caller then runs kb200_fit_state. */
+int kb200_fit_append(kb200_model* next, kb200_model* prev, const double* x, int nbhyp, int trainvar,
+                     double nugget_log10, double* U, double* Psi, double* BE, double* sigma2,
+                     double* nll, int* info, double* theta_log10, double* nugget_out, double* wgkf);
+
 /* Install a predictor from an existing KrigInfo (Theta, wgkf, U, BE, SigmaSqr), as
  * prediction() reads them (prediction.py:148-154).  U is n x n row-major upper. */
 int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double* wgkf,

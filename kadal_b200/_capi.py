@@ -39,6 +39,9 @@ SIGNATURES = {
     "kb200_fit_state": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        c_void_p, c_void_p, c_void_p, c_double_p, c_double_p, c_int_p,
                                        c_void_p, c_double_p, c_void_p]),
+    "kb200_fit_append": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                        c_void_p, c_void_p, c_void_p, c_double_p, c_double_p, c_int_p,
+                                        c_void_p, c_double_p, c_void_p]),
     "kb200_predictor_load": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double]),
     "kb200_predict": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
                                      ctypes.c_uint, ctypes.c_double, ctypes.c_double, ctypes.c_int,

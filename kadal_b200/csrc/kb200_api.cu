@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include "../../include/kb200.h"
 #include "kb200_kernels.h"
 
@@ -29,28 +30,96 @@ static int fail_arg(const std::string& msg) {
     if (e__ != cudaSuccess) return fail(#call, e__); \
   } while (0)
 
+// Device allocations are recycled through a small process-wide pool: the sequential flows of KADAL (Kriging believer,
+// AK-MCS, SOBO) build a new model of n + 1 samples for every update, and ~25 cudaMalloc / cudaFree pairs per model cost
+// more than the refit itself.  A buffer goes back to the pool only after the device is idle (what cudaFree would
+// have waited for as well); the pool is bounded and emptied when an allocation fails.
+struct DevPool {
+  struct Item { void* p; size_t cap; int dev; };
+  std::mutex mu;
+  std::vector<Item> items;
+  size_t bytes = 0;
+  static constexpr size_t MAX_BYTES = (size_t)8 << 30;
+  static constexpr size_t MAX_ITEMS = 256;
+  void* take(size_t want, int dev, size_t* cap) {
+    std::lock_guard<std::mutex> g(mu);
+    int best = -1;
+    for (int i = 0; i < (int)items.size(); ++i)
+      if (items[i].dev == dev && items[i].cap >= want && items[i].cap <= 2 * want + 4096 &&
+          (best < 0 || items[i].cap < items[best].cap))
+        best = i;
+    if (best < 0) return nullptr;
+    void* p = items[best].p;
+    *cap = items[best].cap;
+    bytes -= items[best].cap;
+    items.erase(items.begin() + best);
+    return p;
+  }
+  bool give(void* p, size_t cap, int dev) {   // caller guarantees the device is idle
+    std::lock_guard<std::mutex> g(mu);
+    if (items.size() >= MAX_ITEMS || bytes + cap > MAX_BYTES) return false;
+    items.push_back({p, cap, dev});
+    bytes += cap;
+    return true;
+  }
+  void flush(int dev) {
+    std::lock_guard<std::mutex> g(mu);
+    for (size_t i = 0; i < items.size();) {
+      if (items[i].dev == dev) {
+        cudaFree(items[i].p);
+        bytes -= items[i].cap;
+        items.erase(items.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+  }
+};
+static DevPool g_pool;
+static const bool g_pool_on = !(getenv("KB200_NO_POOL") && atoi(getenv("KB200_NO_POOL")) != 0);
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+  void drop(bool idle) {
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_pool_on) {
+      if (!idle) cudaDeviceSynchronize();
+      if (!g_pool.give(p, cap, dev)) cudaFree(p);
+    } else {
+      cudaFree(p);
+    }
     p = nullptr;
     cap = 0;
+  }
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    drop(false);
+    int dev = 0;
+    cudaGetDevice(&dev);
     size_t want = bytes + bytes / 8;
+    if (g_pool_on) {
+      size_t got = 0;
+      if (void* q = g_pool.take(bytes, dev, &got)) {
+        p = q;
+        cap = got;
+        return cudaSuccess;
+      }
+    }
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
+      cudaGetLastError();
+      g_pool.flush(dev);
       e = cudaMalloc(&p, bytes);
       want = bytes;
     }
     if (e == cudaSuccess) cap = want;
+    else p = nullptr;
     return e;
   }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
+  void release(bool idle = false) { drop(idle); }
   double* d() const { return static_cast<double*>(p); }
 };
 
@@ -84,6 +153,10 @@ struct kb200_model {
   bool has_pred = false;
   DevBuf pL, pW, palpha, pw, pcand;
   double pbeta = 0, psigma2 = 0, pbtb = 0;
+  // state of the last kb200_fit_state / kb200_fit_append that a one-sample append continues from:
+  // Z = L^-1 [y F] ([nq][npad]) and sum ln L_ii
+  bool has_fit = false;
+  DevBuf pZ, plogdet, appdiag, appvec, trwork;
   PredSlot slot[2];
   // candidate groups of one likelihood batch run on their own streams so that the tail of one
   // group's launch (partially filled last wave, long "next diagonal" CTAs) overlaps the other's
@@ -294,14 +367,15 @@ void kb200_model_destroy(kb200_model* m) {
   cudaSetDevice(m->device);
   DevBuf* bufs[] = {&m->X, &m->R, &m->pls, &m->pls2, &m->kplanes_sq, &m->kplanes_abs, &m->tiles, &m->W, &m->Z, &m->cand, &m->xdev,
                     &m->nll, &m->info, &m->logdet, &m->sigma2, &m->beta, &m->btb, &m->resid,
-                    &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand,
+                    &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand, &m->pZ, &m->plogdet, &m->appdiag, &m->appvec, &m->trwork,
                     &m->norm_a, &m->norm_b, &m->stats, &m->akpart,
                     &m->Rw, &m->sobB, &m->sobC, &m->sobY, &m->sobAcc, &m->sobPart, &m->sobMask};
-  for (DevBuf* b : bufs) b->release();
+  cudaDeviceSynchronize();   // nothing of this model is in flight when its buffers go back to the pool
+  for (DevBuf* b : bufs) b->release(true);
   for (int s = 0; s < 2; ++s) {
     PredSlot& sl = m->slot[s];
-    sl.x.release(); sl.chunk.release(); sl.fdot.release(); sl.udot.release(); sl.ssq.release();
-    for (auto& o : sl.out) o.release();
+    sl.x.release(true); sl.chunk.release(true); sl.fdot.release(true); sl.udot.release(true); sl.ssq.release(true);
+    for (auto& o : sl.out) o.release(true);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
   for (int g = 0; g < kb200_model::MAXG; ++g) {
@@ -746,10 +820,12 @@ static int install_predictor(kb200_model* m, const double* tiles, const double* 
   CK(cudaMemcpyAsync(m->rhs2.d(), d_resid, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(m->rhs2.d() + m->npad, d_b, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   BackArgs b;
-  b.L = m->pL.d(); b.nt = m->nt; b.npad = m->npad; b.nq = 2;
+  b.L = m->pL.d(); b.W8 = m->pW.d(); b.nt = m->nt; b.npad = m->npad; b.nq = 2;
   b.rhs = m->rhs2.d(); b.out = m->sol2.d();
+  CK(m->trwork.reserve((size_t)MAXQ * m->npad * 8));
+  b.work = m->trwork.d();
   CK(launch_backsolve(b, st));
-  m->launches++;
+  m->launches += trsv_launches(m->nt);
   CK(cudaMemcpyAsync(m->palpha.p, m->sol2.d(), (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(m->pw.p, m->sol2.d() + m->npad, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   m->pbeta = beta; m->psigma2 = sigma2; m->pbtb = btb;
@@ -757,10 +833,39 @@ static int install_predictor(kb200_model* m, const double* tiles, const double* 
   return 0;
 }
 
-int kb200_fit_state(kb200_model* m, const double* x, int nbhyp, int trainvar,
-                    double nugget_log10, double* U, double* Psi, double* BE, double* sigma2,
-                    double* nll, int* info, double* theta_log10, double* nugget_out,
-                    double* wgkf) {
+// One-sample append: m's bordered matrix Psi + eps I is already assembled in m->tiles;
+// prev holds the factor of its leading (n - 1) x (n - 1) block.  Leaves in m->tiles / W / Z / logdet / info what
+// factorize() would leave, at O(n^2) instead of O(n^3) work.
+static int append_factor(kb200_model* m, kb200_model* prev, cudaStream_t st) {
+  const int np = prev->n;
+  // appvec: [0, npad_prev) the new row of Psi, [npad_prev, 2 npad_prev) v = L^-1 psi
+  CK(m->appvec.reserve((size_t)2 * prev->npad * 8));
+  CK(m->appdiag.reserve(8));
+  CK(m->trwork.reserve((size_t)MAXQ * m->npad * 8));
+  CK(launch_append_extract(m->tiles.d(), np, prev->nt, m->appvec.d(), m->appdiag.d(), st));
+  m->launches++;
+  // the old factor is a prefix of the new tile storage (tile (ti, tj) at ti (ti + 1) / 2 + tj); the new row is
+  // rewritten below, the rest of a new tile row keeps the assembly's identity padding
+  CK(cudaMemcpyAsync(m->tiles.p, prev->pL.p, (size_t)prev->tiles_per_mat * TILE_ELEMS * 8, cudaMemcpyDeviceToDevice, st));
+  BackArgs f;
+  f.L = prev->pL.d(); f.W8 = prev->pW.d(); f.nt = prev->nt; f.npad = prev->npad; f.nq = 1;
+  f.rhs = m->appvec.d(); f.out = m->appvec.d() + prev->npad; f.work = m->trwork.d();
+  CK(launch_forwardsolve(f, st));
+  m->launches += trsv_launches(prev->nt);
+  CK(launch_append_row(m->tiles.d(), m->appvec.d() + prev->npad, np, prev->nt, m->nq, prev->npad, m->npad, prev->pZ.d(),
+                       m->R.d(), m->Z.d(), prev->plogdet.d(), m->logdet.d(), static_cast<int*>(m->info.p),
+                       m->appdiag.d(), st));
+  m->launches++;
+  CholArgs ca = chol_args(m, m->tiles.d(), m->W.d(), nullptr, nullptr, nullptr);
+  CK(launch_w8_from_tiles(ca, 1, st));
+  m->launches++;
+  return 0;
+}
+
+static int fit_state_impl(kb200_model* m, kb200_model* prev, const double* x, int nbhyp, int trainvar,
+                          double nugget_log10, double* U, double* Psi, double* BE, double* sigma2,
+                          double* nll, int* info, double* theta_log10, double* nugget_out,
+                          double* wgkf) {
   if (!m || !x) return fail_arg("kb200_fit_state: null argument");
   CK(cudaSetDevice(m->device));
   cudaStream_t st = m->stream;
@@ -789,7 +894,18 @@ int kb200_fit_state(kb200_model* m, const double* x, int nbhyp, int trainvar,
   }
   CK(launch_add_diag(m->tiles.d(), m->n, m->cand.d() + 4 * m->ntheta + m->nkernel, st));
   m->launches++;
-  rc = factorize(m, 1, m->tiles.d(), m->W.d(), m->Z.d(), m->logdet.d(), static_cast<int*>(m->info.p), st);
+  if (prev) {
+    // the two fits must share every hyper-parameter: compare the decoded parameter rows bit for bit
+    std::vector<double> a(m->cstride), b(m->cstride);
+    CK(cudaMemcpyAsync(a.data(), m->cand.p, (size_t)m->cstride * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(b.data(), prev->pcand.p, (size_t)m->cstride * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (memcmp(a.data(), b.data(), (size_t)(m->cstride - 1) * 8) != 0)   // last entry: sigma2 of trainvar, not in Psi
+      return fail_arg("kb200_fit_append: hyper-parameters differ from the fit installed in `prev`");
+    rc = append_factor(m, prev, st);
+  } else {
+    rc = factorize(m, 1, m->tiles.d(), m->W.d(), m->Z.d(), m->logdet.d(), static_cast<int*>(m->info.p), st);
+  }
   if (rc) return rc;
   FinArgs f;
   memset(&f, 0, sizeof(f));
@@ -832,11 +948,41 @@ int kb200_fit_state(kb200_model* m, const double* x, int nbhyp, int trainvar,
     rc = install_predictor(m, m->tiles.d(), m->W.d(), m->resid.d(), m->Z.d() + m->npad,
                            m->cand.d(), hbeta[0], h_s2, h_btb, st);
     if (rc) return rc;
+    // what a later one-sample append continues from
+    CK(m->pZ.reserve((size_t)m->nq * m->npad * 8));
+    CK(m->plogdet.reserve(8));
+    CK(cudaMemcpyAsync(m->pZ.p, m->Z.p, (size_t)m->nq * m->npad * 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(m->plogdet.p, m->logdet.p, 8, cudaMemcpyDeviceToDevice, st));
+    m->has_fit = true;
     CK(cudaStreamSynchronize(st));
   } else {
     m->has_pred = false;
+    m->has_fit = false;
   }
   return 0;
+}
+
+int kb200_fit_state(kb200_model* m, const double* x, int nbhyp, int trainvar,
+                    double nugget_log10, double* U, double* Psi, double* BE, double* sigma2,
+                    double* nll, int* info, double* theta_log10, double* nugget_out,
+                    double* wgkf) {
+  return fit_state_impl(m, nullptr, x, nbhyp, trainvar, nugget_log10, U, Psi, BE, sigma2, nll, info, theta_log10,
+                        nugget_out, wgkf);
+}
+
+int kb200_fit_append(kb200_model* next, kb200_model* prev, const double* x, int nbhyp, int trainvar,
+                     double nugget_log10, double* U, double* Psi, double* BE, double* sigma2,
+                     double* nll, int* info, double* theta_log10, double* nugget_out, double* wgkf) {
+  if (!next || !prev || !x) return fail_arg("kb200_fit_append: null argument");
+  if (!prev->has_fit || !prev->has_pred)
+    return fail_arg("kb200_fit_append: `prev` holds no fit (call kb200_fit_state or kb200_fit_append on it first)");
+  if (next->n != prev->n + 1 || next->d != prev->d || next->p != prev->p || next->h != prev->h ||
+      next->nkernel != prev->nkernel || next->device != prev->device ||
+      ((next->flags ^ prev->flags) & KB200_FLAG_ISO) || memcmp(next->kid, prev->kid, sizeof(int) * next->nkernel) != 0)
+    return fail_arg("kb200_fit_append: `next` must be `prev` with exactly one more sample (same d, trend, kernels, device)");
+  if (next->p != 1) return fail_arg("kb200_fit_append: ordinary Kriging only (TrendOrder 0)");
+  return fit_state_impl(next, prev, x, nbhyp, trainvar, nugget_log10, U, Psi, BE, sigma2, nll, info, theta_log10,
+                        nugget_out, wgkf);
 }
 
 int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double* wgkf,
@@ -885,10 +1031,12 @@ int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double
   CK(cudaMemcpyAsync(m->rhs2.p, rhs.data(), rhs.size() * 8, cudaMemcpyHostToDevice, st));
   CK(m->Z.reserve((size_t)2 * m->npad * 8));
   BackArgs f;
-  f.L = m->pL.d(); f.nt = m->nt; f.npad = m->npad; f.nq = 2;
+  f.L = m->pL.d(); f.W8 = m->pW.d(); f.nt = m->nt; f.npad = m->npad; f.nq = 2;
   f.rhs = m->rhs2.d(); f.out = m->Z.d();
+  CK(m->trwork.reserve((size_t)MAXQ * m->npad * 8));
+  f.work = m->trwork.d();
   CK(launch_forwardsolve(f, st));
-  m->launches++;
+  m->launches += trsv_launches(m->nt);
   std::vector<double> hb(m->npad);
   CK(cudaMemcpyAsync(hb.data(), m->Z.d() + m->npad, (size_t)m->npad * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -898,6 +1046,7 @@ int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double
   CK(cudaMemcpyAsync(m->resid.p, m->Z.d(), (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   CK(m->beta.reserve((size_t)m->npad * 8));
   CK(cudaMemcpyAsync(m->beta.p, m->Z.d() + m->npad, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
+  m->has_fit = false;
   int rc = install_predictor(m, m->pL.d(), m->pW.d(), m->resid.d(), m->beta.d(), m->pcand.d(), BE[0],
                              sigma2, btb, st);
   if (rc) return rc;

@@ -7,7 +7,7 @@
 //                            GEMM with the inverted diagonal block.  Prediction points are
 //                            "extra rows" of the factorisation and reuse this kernel.
 //   lik_finalize_kernel  K4  GLS beta, sigma^2, concentrated / trainvar ln-likelihood
-//   backsolve_kernel         alpha = L^-T r, w = L^-T b (predictor state, once per fit)
+//   trsv_diag / trsv_update  alpha = L^-T r, w = L^-T b (predictor state, once per fit), forward solves
 //   predict_epilogue_kernel  mean / SSqr / s / EI / PoI / PoF / U-function
 //   import / export kernels  row-major U, Psi  <->  tile layout
 //
@@ -1222,112 +1222,136 @@ lik_finalize_kernel(FinArgs A) {
 }
 
 // ================================================================== backsolve (fit)
-// X_j = L_jj^-T (RHS_j - sum_{k>j} L_kj^T X_k), j = nt-1 .. 0, nq columns; one CTA.
+// X_j = L_jj^-T (RHS_j - sum_{k>j} L_kj^T X_k), j = nt-1 .. 0 (and the forward counterpart), nq columns.
 // (once per fit: alpha = L^-T r, w = L^-T b of the predictor, prediction.py:233-235, 245-249)
 // The in-tile solve is a column-oriented substitution in shared memory: thread (r, q-group).
-__device__ __forceinline__ void tile_substitute(const double* __restrict__ T, double* tv, double* out_base,
-                                                int npad, int nq, bool transposed) {
+// The diagonal tile is staged in shared memory first (it used to be read from global memory inside the 128
+// strictly sequential steps, ~2 us per step: 8 of the 10 ms of a fit at n = 4000) and the pivots' reciprocals
+// are formed once, off the chain.
+constexpr size_t SOLVE_SMEM = (size_t)(TILE_ELEMS + 1024 + 8 * MAXQ) * 8;
+// Blocked by the 8x8 diagonal blocks whose inverses W8 the factorisation keeps anyway: x_b = W_b t_b (or W_b^T t_b),
+// then the block is taken out of the rows still to be solved -- 16 block steps of two barriers per tile instead of
+// 128 pivots of one (41 -> 15 us per tile).
+__device__ __forceinline__ void tile_substitute(const double* __restrict__ T, const double* __restrict__ W8, double* Ts,
+                                                double* tv, double* out_base, int npad, int nq, bool transposed) {
   // forward (transposed = false): solve L x = t;  backward (true): solve L^T x = t
   const int tid = threadIdx.x, r = tid & (TB - 1), part = tid >> 7;
-  for (int step = 0; step < TB; ++step) {
-    const int c = transposed ? TB - 1 - step : step;
-    const double dcc = T[tile_off(c, c)];
-    const double lrc = transposed ? (r < c ? T[tile_off(c, r)] : 0.0) : (r > c ? T[tile_off(r, c)] : 0.0);
-    for (int q = part; q < nq; q += 4) {
-      const double xc = tv[c * MAXQ + q] / dcc;
-      if (r == c) out_base[(size_t)q * npad + r] = xc;
-      else tv[r * MAXQ + q] = fma(-lrc, xc, tv[r * MAXQ + q]);
+  double* Ws = Ts + TILE_ELEMS;          // [16][8][8]
+  double* xb = Ws + 1024;                // [8][MAXQ]
+  {
+    const double2* src = reinterpret_cast<const double2*>(T);
+    double2* dst = reinterpret_cast<double2*>(Ts);
+    for (int idx = tid; idx < TILE_ELEMS / 2; idx += CH_THREADS) dst[idx] = src[idx];
+    for (int idx = tid; idx < 1024; idx += CH_THREADS) Ws[idx] = W8[idx];
+  }
+  __syncthreads();
+  for (int step = 0; step < TB / 8; ++step) {
+    const int b = transposed ? TB / 8 - 1 - step : step;
+    if (r < 8) {
+      for (int q = part; q < nq; q += 4) {
+        double x = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const double w = transposed ? Ws[b * 64 + k * 8 + r] : Ws[b * 64 + r * 8 + k];
+          x = fma(w, tv[(8 * b + k) * MAXQ + q], x);
+        }
+        xb[r * MAXQ + q] = x;
+        out_base[(size_t)q * npad + 8 * b + r] = x;
+      }
+    }
+    __syncthreads();
+    const bool mine = transposed ? (r < 8 * b) : (r >= 8 * b + 8);
+    if (mine) {
+      double l[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) l[k] = transposed ? Ts[tile_off(8 * b + k, r)] : Ts[tile_off(r, 8 * b + k)];
+      for (int q = part; q < nq; q += 4) {
+        double t = tv[r * MAXQ + q];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t = fma(-l[k], xb[k * MAXQ + q], t);
+        tv[r * MAXQ + q] = t;
+      }
     }
     __syncthreads();
   }
 }
 
+// Right-looking over tile columns, two launches per column: trsv_diag_kernel solves the diagonal tile for the nq
+// columns (one CTA, 128 sequential pivots in shared memory), trsv_update_kernel takes that block out of every
+// remaining right-hand-side block (one CTA per tile, all in parallel).  The first version was ONE CTA walking the
+// whole triangle (6 ms of the 8 ms of a fit at n = 4000, ncu launch list r1r).
 __global__ void __launch_bounds__(CH_THREADS, 1)
-backsolve_kernel(BackArgs A) {
-  __shared__ double xs[TB * MAXQ];       // X_k block (broadcast reads); reused as t
-  __shared__ double part[4][TB][MAXQ];
-  double* tv = xs;
-  const int tid = threadIdx.x, r = tid & (TB - 1), part_id = tid >> 7;
-  const int nq = A.nq, npad = A.npad, nt = A.nt;
-  for (int j = nt - 1; j >= 0; --j) {
-    double acc[MAXQ];
-#pragma unroll
-    for (int q = 0; q < MAXQ; ++q) acc[q] = 0.0;
-    for (int k = j + 1; k < nt; ++k) {
-      __syncthreads();
-      for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
-        int c = idx / nq, q = idx - c * nq;
-        xs[c * MAXQ + q] = A.out[(size_t)q * npad + k * TB + c];
-      }
-      __syncthreads();
-      const double* T = A.L + (size_t)tri_index(k, j) * TILE_ELEMS;
-      for (int c = 32 * part_id; c < 32 * part_id + 32; ++c) {
-        const double l = T[tile_off(c, r)];
-#pragma unroll
-        for (int q = 0; q < MAXQ; ++q)
-          if (q < nq) acc[q] = fma(l, xs[c * MAXQ + q], acc[q]);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < MAXQ; ++q)
-      if (q < nq) part[part_id][r][q] = acc[q];
-    __syncthreads();
-    if (tid < TB) {
-      for (int q = 0; q < nq; ++q) {
-        double s = ((part[0][r][q] + part[1][r][q]) + part[2][r][q]) + part[3][r][q];
-        tv[r * MAXQ + q] = A.rhs[(size_t)q * npad + j * TB + r] - s;
-      }
-    }
-    __syncthreads();
-    tile_substitute(A.L + (size_t)tri_index(j, j) * TILE_ELEMS, tv, A.out + j * TB, npad, nq, true);
-    __threadfence_block();
-    __syncthreads();
+trsv_diag_kernel(BackArgs A, int j, int transposed) {
+  extern __shared__ __align__(16) double solve_tile[];   // diagonal tile + reciprocal pivots (SOLVE_SMEM)
+  __shared__ double tv[TB * MAXQ];
+  const int nq = A.nq, npad = A.npad;
+  for (int idx = threadIdx.x; idx < TB * nq; idx += CH_THREADS) {
+    const int c = idx / nq, q = idx - c * nq;
+    tv[c * MAXQ + q] = A.work[(size_t)q * npad + j * TB + c];
   }
+  __syncthreads();
+  tile_substitute(A.L + (size_t)tri_index(j, j) * TILE_ELEMS, A.W8 + (size_t)j * 1024, solve_tile, tv, A.out + j * TB, npad,
+                  nq, transposed != 0);
 }
 
-// ================================================================ forward solve (load)
-// X_j = L_jj^-1 (RHS_j - sum_{k<j} L_jk X_k), j = 0 .. nt-1, nq columns; one CTA.
-// Used when a factor is imported from KrigInfo['U'] (prediction.py:233-235, 245-246).
-__global__ void __launch_bounds__(CH_THREADS, 1)
-forwardsolve_kernel(BackArgs A) {
+// forward:  work_i -= L_ij   x_j, i = j + 1 + blockIdx.x   (tile (i, j), rows of the tile)
+// backward: work_i -= L_ji^T x_j, i = blockIdx.x < j       (tile (j, i), columns of the tile)
+__global__ void __launch_bounds__(CH_THREADS)
+trsv_update_kernel(BackArgs A, int j, int transposed) {
   __shared__ double xs[TB * MAXQ];
   __shared__ double part[4][TB][MAXQ];
-  double* tv = xs;
   const int tid = threadIdx.x, r = tid & (TB - 1), part_id = tid >> 7;
-  const int nq = A.nq, npad = A.npad, nt = A.nt;
-  for (int j = 0; j < nt; ++j) {
-    double acc[MAXQ];
+  const int nq = A.nq, npad = A.npad;
+  const int i = transposed ? (int)blockIdx.x : j + 1 + (int)blockIdx.x;
+  for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
+    const int c = idx / nq, q = idx - c * nq;
+    xs[c * MAXQ + q] = A.out[(size_t)q * npad + j * TB + c];
+  }
+  __syncthreads();
+  const double* T = A.L + (size_t)(transposed ? tri_index(j, i) : tri_index(i, j)) * TILE_ELEMS;
+  double acc[MAXQ];
 #pragma unroll
-    for (int q = 0; q < MAXQ; ++q) acc[q] = 0.0;
-    for (int k = 0; k < j; ++k) {
-      __syncthreads();
-      for (int idx = tid; idx < TB * nq; idx += CH_THREADS) {
-        int c = idx / nq, q = idx - c * nq;
-        xs[c * MAXQ + q] = A.out[(size_t)q * npad + k * TB + c];
+  for (int q = 0; q < MAXQ; ++q) acc[q] = 0.0;
+  if (transposed) {
+    // out index r = column of the tile: row c of the tile is contiguous over r
+#pragma unroll 8
+    for (int c = 32 * part_id; c < 32 * part_id + 32; ++c) {
+      const double l = T[tile_off(c, r)];
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q)
+        if (q < nq) acc[q] = fma(l, xs[c * MAXQ + q], acc[q]);
+    }
+  } else {
+    // out index r = row of the tile: this thread reads the two 128-byte lines (slabs 2 part, 2 part + 1) of its row
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int slab = 2 * part_id + sl;
+      const double2* line = reinterpret_cast<const double2*>(T + (size_t)slab * SLAB_ELEMS + r * KS);
+      double v[KS];
+#pragma unroll
+      for (int h = 0; h < KS / 2; ++h) {
+        const double2 t = line[h];
+        v[2 * h] = t.x;
+        v[2 * h + 1] = t.y;
       }
-      __syncthreads();
-      const double* T = A.L + (size_t)tri_index(j, k) * TILE_ELEMS;
-      for (int c = 32 * part_id; c < 32 * part_id + 32; ++c) {
-        const double l = T[tile_off(r, c)];
+#pragma unroll
+      for (int pp = 0; pp < KS; ++pp) {
+        const int c = slab * KS + ((((pp >> 2) ^ (r & 3)) << 2) | (pp & 3));   // inverse of slab_off's swizzle
 #pragma unroll
         for (int q = 0; q < MAXQ; ++q)
-          if (q < nq) acc[q] = fma(l, xs[c * MAXQ + q], acc[q]);
+          if (q < nq) acc[q] = fma(v[pp], xs[c * MAXQ + q], acc[q]);
       }
     }
+  }
 #pragma unroll
-    for (int q = 0; q < MAXQ; ++q)
-      if (q < nq) part[part_id][r][q] = acc[q];
-    __syncthreads();
-    if (tid < TB) {
-      for (int q = 0; q < nq; ++q) {
-        double s = ((part[0][r][q] + part[1][r][q]) + part[2][r][q]) + part[3][r][q];
-        tv[r * MAXQ + q] = A.rhs[(size_t)q * npad + j * TB + r] - s;
-      }
+  for (int q = 0; q < MAXQ; ++q)
+    if (q < nq) part[part_id][r][q] = acc[q];
+  __syncthreads();
+  if (tid < TB) {
+    for (int q = 0; q < nq; ++q) {
+      const double sum = ((part[0][r][q] + part[1][r][q]) + part[2][r][q]) + part[3][r][q];
+      A.work[(size_t)q * npad + i * TB + r] -= sum;
     }
-    __syncthreads();
-    tile_substitute(A.L + (size_t)tri_index(j, j) * TILE_ELEMS, tv, A.out + j * TB, npad, nq, false);
-    __threadfence_block();
-    __syncthreads();
   }
 }
 
@@ -1803,6 +1827,103 @@ cudaError_t launch_akmcs_reduce(const double* G, const double* S, long n, long b
   return cudaSuccess;
 }
 
+// ===================================== one-sample append to a factor
+// Kriging believer (optim_tools/MOBO.py:344-356) and the sequential updates of AK-MCS / SOBO
+// (reliability_analysis/akmcs.py:127-139, optim_tools/SOBO.py:137-145) call likelihood(Theta, KrigInfo, 'all')
+// again after ONE sample was stacked under X and y: the Cholesky factor of the bordered matrix is the old
+// factor with one more row  [v^T, l],  v = L^-1 psi_new,  l = sqrt(psi_nn + eps - v.v): one forward solve
+// (trsv kernels above; the panel kernel in prediction mode took 5 ms for a single point at n = 4000).
+//
+// append_extract_kernel: row `n_prev` of the freshly assembled bordered matrix (tile row ti_new, local row
+// r_new) as a plain zero-padded vector of length nt_prev * 128, and its diagonal entry; one CTA per tile.
+__global__ void __launch_bounds__(TB)
+append_extract_kernel(const double* __restrict__ tiles, int n_prev, int nt_prev, double* __restrict__ vec,
+                      double* __restrict__ dnn) {
+  const int tj = blockIdx.x, ti_new = n_prev / TB, r_new = n_prev % TB, c = threadIdx.x;
+  // psi_nn + eps exactly as the assembly wrote it (the old factor is copied over this tile next)
+  if (tj == 0 && c == 0) *dnn = tiles[(size_t)tri_index(ti_new, ti_new) * TILE_ELEMS + tile_off(r_new, r_new)];
+  const double* S = tiles + (size_t)tri_index(ti_new, tj) * TILE_ELEMS;
+  vec[tj * TB + c] = (tj * TB + c < n_prev) ? S[tile_off(r_new, c)] : 0.0;
+}
+
+// append_row_kernel: one CTA.  `tiles` already holds the old factor (copied over the assembled matrix except
+// for its new diagonal entry, kept aside by append_extract_kernel).
+struct AppendArgs {
+  double* tiles;           // bordered matrix / new factor, tile storage
+  const double* v;         // [nt_prev * 128]  L^-1 psi_new
+  int n_prev, nt_prev;
+  int nq, npad_prev, npad;
+  const double* Zprev;     // [nq][npad_prev]  L^-1 [y F] of the old fit
+  const double* R;         // [nq][npad]       [y F]^T of the bordered model
+  double* Z;               // [nq][npad]
+  const double* logdet_prev;
+  double* logdet;
+  int* info;
+  const double* dnn;       // diagonal entry of the bordered matrix
+};
+__global__ void __launch_bounds__(256)
+append_row_kernel(AppendArgs A) {
+  __shared__ double red[8];
+  __shared__ double s_l;
+  const int n = A.n_prev, ti = n / TB, r = n % TB;
+  double* D = A.tiles + (size_t)tri_index(ti, ti) * TILE_ELEMS;
+  const double dnn = *A.dnn;
+  double ss = 0.0;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const double v = A.v[c];
+    ss = fma(v, v, ss);
+  }
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0) {
+    const double piv = dnn - ss;
+    double l = 1.0;
+    if (piv > 0.0) l = sqrt(piv);
+    else *A.info = n + 1;                        // first non-positive pivot, 1-based (as the factorisation reports)
+    s_l = l;
+    D[tile_off(r, r)] = l;
+    *A.logdet = *A.logdet_prev + log(l);
+  }
+  __syncthreads();
+  const double l = s_l;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const double v = A.v[c];
+    A.tiles[(size_t)tri_index(ti, c / TB) * TILE_ELEMS + tile_off(r, c % TB)] = v;
+  }
+  // z_new = ([y F]_new - v . Z_prev) / l   (forward substitution of likelihood_func.py:183-193, last row)
+  for (int q = 0; q < A.nq; ++q) {
+    const double* zp = A.Zprev + (size_t)q * A.npad_prev;
+    double* zn = A.Z + (size_t)q * A.npad;
+    double dot = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+      const double v = A.v[c];
+      const double z = zp[c];
+      dot = fma(v, z, dot);
+      zn[c] = z;
+    }
+    dot = block_sum(dot, red);
+    for (int c = n + 1 + threadIdx.x; c < A.npad; c += blockDim.x) zn[c] = 0.0;
+    if (threadIdx.x == 0) zn[n] = (A.R[(size_t)q * A.npad + n] - dot) / l;
+  }
+}
+
+cudaError_t launch_append_extract(const double* tiles, int n_prev, int nt_prev, double* vec, double* dnn,
+                                  cudaStream_t st) {
+  append_extract_kernel<<<nt_prev, TB, 0, st>>>(tiles, n_prev, nt_prev, vec, dnn);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t launch_append_row(double* tiles, const double* v, int n_prev, int nt_prev, int nq, int npad_prev,
+                              int npad, const double* Zprev, const double* R, double* Z, const double* logdet_prev,
+                              double* logdet, int* info, const double* dnn, cudaStream_t st) {
+  AppendArgs a;
+  a.dnn = dnn;
+  a.tiles = tiles; a.v = v; a.n_prev = n_prev; a.nt_prev = nt_prev; a.nq = nq; a.npad_prev = npad_prev;
+  a.npad = npad; a.Zprev = Zprev; a.R = R; a.Z = Z; a.logdet_prev = logdet_prev; a.logdet = logdet; a.info = info;
+  append_row_kernel<<<1, 256, 0, st>>>(a);
+  KB_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
 cudaError_t launch_identity_chunk(double* chunk, int tiles, int nt, long pt0, cudaStream_t st) {
   identity_chunk_kernel<<<dim3(tiles, nt), 256, 0, st>>>(chunk, nt, pt0);
   KB_LAUNCH_CHECK();
@@ -1907,17 +2028,36 @@ cudaError_t launch_finalize(const FinArgs& a, int nmat, cudaStream_t st) {
   return cudaSuccess;
 }
 
-cudaError_t launch_backsolve(const BackArgs& a, cudaStream_t st) {
-  backsolve_kernel<<<1, CH_THREADS, 0, st>>>(a);
-  KB_LAUNCH_CHECK();
+static bool g_solve_attr[64] = {false};
+static cudaError_t solve_attrs() {
+  const int dev = cur_dev();
+  if (g_solve_attr[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM);
+  if (e != cudaSuccess) return e;
+  g_solve_attr[dev] = true;
   return cudaSuccess;
 }
 
-cudaError_t launch_forwardsolve(const BackArgs& a, cudaStream_t st) {
-  forwardsolve_kernel<<<1, CH_THREADS, 0, st>>>(a);
-  KB_LAUNCH_CHECK();
+static cudaError_t launch_trsv(const BackArgs& a, bool transposed, cudaStream_t st) {
+  cudaError_t e = solve_attrs();
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(a.work, a.rhs, (size_t)a.nq * a.npad * 8, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return e;
+  for (int s = 0; s < a.nt; ++s) {
+    const int j = transposed ? a.nt - 1 - s : s;
+    trsv_diag_kernel<<<1, CH_THREADS, SOLVE_SMEM, st>>>(a, j, transposed ? 1 : 0);
+    KB_LAUNCH_CHECK();
+    const int rest = transposed ? j : a.nt - 1 - j;
+    if (rest > 0) {
+      trsv_update_kernel<<<rest, CH_THREADS, 0, st>>>(a, j, transposed ? 1 : 0);
+      KB_LAUNCH_CHECK();
+    }
+  }
   return cudaSuccess;
 }
+
+cudaError_t launch_backsolve(const BackArgs& a, cudaStream_t st) { return launch_trsv(a, true, st); }
+cudaError_t launch_forwardsolve(const BackArgs& a, cudaStream_t st) { return launch_trsv(a, false, st); }
 
 cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t st) {
   decode_kernel<<<(int)((a.P + 127) / 128), 128, 0, st>>>(a);

@@ -71,10 +71,13 @@ struct FinArgs {
 
 struct BackArgs {
   const double* L;       // tiles of one matrix
+  const double* W8;      // [nt][16][64] inverses of its 8x8 diagonal blocks
   int nt, npad, nq;
   const double* rhs;     // [nq][npad]
   double* out;           // [nq][npad]
+  double* work;          // [nq][npad] scratch: the right-hand sides as the solve consumes them
 };
+inline int trsv_launches(int nt) { return 2 * nt - 1; }
 
 struct DecodeArgs {
   const double* x;       // [P][nbhyp]
@@ -184,6 +187,12 @@ constexpr int AK_BLOCKS = 592;          // 4 x 148
 constexpr int AK_PARTIAL_BYTES = 40;    // {double min_u; long long arg; unsigned long long c0, cm, cp;}
 cudaError_t launch_akmcs_reduce(const double* G, const double* S, long n, long base, void* out, int nblocks, cudaStream_t st);
 cudaError_t launch_identity_chunk(double* chunk, int tiles, int nt, long pt0, cudaStream_t st);
+// one-sample append to a factor (believer / sequential refits)
+cudaError_t launch_append_extract(const double* tiles, int n_prev, int nt_prev, double* vec, double* dnn,
+                                  cudaStream_t st);
+cudaError_t launch_append_row(double* tiles, const double* v, int n_prev, int nt_prev, int nq, int npad_prev,
+                              int npad, const double* Zprev, const double* R, double* Z, const double* logdet_prev,
+                              double* logdet, int* info, const double* dnn, cudaStream_t st);
 cudaError_t launch_loo(const double* y, const double* alpha, const double* w, const double* ssq, double btb, int n,
                        long p0, int np, double* out, cudaStream_t st);
 cudaError_t launch_predict_small(const PredSmallArgs& a, int sm_count, cudaStream_t st);

@@ -7,7 +7,7 @@ All arithmetic runs in the CUDA library (``kb200_lik_batch`` / ``kb200_fit_state
 """
 import numpy as np
 
-from .model import model_for
+from .model import model_for, append_source
 
 
 def _fixed_nugget(KrigInfo):
@@ -94,7 +94,8 @@ def likelihood(x, KrigInfo, mode="default", trainvar=True):
             raise np.linalg.LinAlgError("Matrix is not positive definite")
         KrigInfo["NegLnLike"] = nll[0]
         return nll[0]
-    st = m.fit_state(xv, tv, nug_fixed)
+    # one more sample under the same hyper-parameters (believer / sequential updates): extend the cached factor
+    st = m.fit_state(xv, tv, nug_fixed, append_to=append_source(m, xv, tv, nug_fixed))
     if st["info"] != 0:
         raise np.linalg.LinAlgError("Matrix is not positive definite")
     KrigInfo["U"] = st["U"]

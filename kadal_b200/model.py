@@ -58,6 +58,7 @@ class GpuModel:
             self.h = pls.shape[1]
         self.ntheta = self.h if self.h else self.d
         self.nkernel = len(kernels)
+        self.kernels = tuple(int(k) for k in kernels)
         self.iso = bool(iso)
         if device is None:
             device = int(os.environ.get("KADAL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
@@ -75,6 +76,7 @@ class GpuModel:
         self.ymin = float(np.min(y))
         self.pred_token = None
         self._keep = None
+        self.fit_key = None       # (x bytes, trainvar, nugget) of the fit an append may continue from
 
     def close(self):
         if getattr(self, "handle", None):
@@ -102,7 +104,10 @@ class GpuModel:
                                            float(nugget_log10), c_void_p(nll_ptr), c_void_p(info_ptr),
                                            c_void_p(stream)))
 
-    def fit_state(self, x, trainvar, nugget_log10, want_U=True, want_Psi=True):
+    def fit_state(self, x, trainvar, nugget_log10, want_U=True, want_Psi=True, append_to=None):
+        """likelihood(x, KrigInfo, 'all') on the device.  ``append_to``: a GpuModel holding the fit of the same
+        ``x`` on this model's samples minus the last one -- the factor is then extended by one row
+        (``kb200_fit_append``) instead of being recomputed."""
         x = as_f64(np.asarray(x).reshape(-1))
         n = self.n
         U = np.empty((n, n)) if want_U else None
@@ -112,9 +117,15 @@ class GpuModel:
         wgkf = np.empty(self.nkernel)
         s2, nll, nug = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         info = ctypes.c_int()
-        check(self.lib.kb200_fit_state(self.handle, ptr(x), x.shape[0], int(bool(trainvar)), float(nugget_log10),
-                                       ptr(U), ptr(Psi), ptr(BE), ctypes.byref(s2), ctypes.byref(nll),
-                                       ctypes.byref(info), ptr(theta), ctypes.byref(nug), ptr(wgkf)))
+        tail = (ptr(x), x.shape[0], int(bool(trainvar)), float(nugget_log10),
+                ptr(U), ptr(Psi), ptr(BE), ctypes.byref(s2), ctypes.byref(nll),
+                ctypes.byref(info), ptr(theta), ctypes.byref(nug), ptr(wgkf))
+        if append_to is not None:
+            check(self.lib.kb200_fit_append(self.handle, append_to.handle, *tail))
+        else:
+            check(self.lib.kb200_fit_state(self.handle, *tail))
+        self.fit_key = (x.tobytes(), bool(trainvar), float(nugget_log10)) if info.value == 0 and self.p == 1 else None
+        self.last_fit_appended = append_to is not None
         return dict(U=U, Psi=Psi, BE=BE, sigma2=s2.value, nll=nll.value, info=info.value, theta=theta,
                     nugget=nug.value, wgkf=wgkf)
 
@@ -127,6 +138,7 @@ class GpuModel:
 
     # ------------------------------------------------------------------ prediction
     def predictor_load(self, theta_log10, wgkf, U, BE, sigma2):
+        self.fit_key = None
         theta_log10 = as_f64(np.asarray(theta_log10).reshape(-1))
         wgkf = as_f64(np.asarray(wgkf, dtype=float).reshape(-1))
         U = as_f64(U)
@@ -243,6 +255,32 @@ def model_for(KrigInfo):
         _, old = _CACHE.popitem(last=False)
         old.close()
     return m
+
+
+def append_source(m, x, trainvar, nugget_log10):
+    """A cached model that ``m`` extends by exactly one sample and that holds the fit of the same
+    hyper-parameters (Kriging believer, MOBO.py:344-356; AK-MCS / SOBO sequential updates), or None.
+    ``$KB200_NO_APPEND=1`` always answers None (every 'all' call refactorises)."""
+    if os.environ.get("KB200_NO_APPEND", "0") == "1" or m.p != 1 or m._keep is None or m.n < 2:
+        return None
+    x = as_f64(np.asarray(x).reshape(-1))
+    want = (x.tobytes(), bool(trainvar), float(nugget_log10))
+    X, y, F, pls = m._keep
+    for prev in reversed(list(_CACHE.values())):
+        if prev is m or prev.handle is None or prev.fit_key != want or prev._keep is None:
+            continue
+        if (prev.n != m.n - 1 or prev.d != m.d or prev.p != m.p or prev.h != m.h or prev.iso != m.iso
+                or prev.device != m.device or prev.kernels != m.kernels):
+            continue
+        pX, py, pF, ppls = prev._keep
+        n = prev.n
+        if not (np.array_equal(np.asarray(X)[:n], pX) and np.array_equal(np.asarray(y).reshape(-1)[:n], np.asarray(py).reshape(-1))
+                and np.array_equal(np.asarray(F)[:n], pF)):
+            continue
+        if (pls is None) != (ppls is None) or (pls is not None and not np.array_equal(pls, ppls)):
+            continue
+        return prev
+    return None
 
 
 def clear_cache():

@@ -541,6 +541,90 @@ def test_trained_model_round_trips_through_pickle_and_believer_refit(kb, tmp_pat
     assert s_after < s_before and abs(s_after - s_ref) < max(TOL_VAR, 5 * cond * 2.0 ** -53) * max(s_ref, 1e-3)
 
 
+def _believer_step(kb, info, xnew_norm, ynew):
+    """What MOBO.py:344-356 does to a KrigInfo between two likelihood(..., 'all') calls (standardisation off here:
+    X_norm of the old rows does not change under 'default' standardisation either)."""
+    info["X"] = np.vstack((info["X"], xnew_norm))
+    info["X_norm"] = info["X"]
+    info["y"] = np.vstack((info["y"], np.reshape(ynew, (1, 1))))
+    info["nsamp"] = info["X"].shape[0]
+    info["F"] = np.ones((info["nsamp"], 1))
+    return info
+
+
+@pytest.mark.parametrize("kernel,n0", [(["gaussian"], 125), (["matern52"], 60), (["gaussian", "exponential"], 254)])
+def test_one_sample_append_matches_refactorisation_and_oracle(kb, monkeypatch, kernel, n0):
+    """likelihood(Theta, KrigInfo, 'all') after one stacked sample extends the cached
+    factor by a row (kb200_fit_append, O(n^2)) -- six appends in a row, across a 128-tile boundary, each checked
+    against the oracle and against the full refactorisation ($KB200_NO_APPEND=1) of the same KrigInfo."""
+    from kadal_b200.model import model_for, clear_cache
+    clear_cache()
+    rng = np.random.default_rng(31)
+    d = 4
+    X = rng.uniform(-1, 1, (n0, d))
+    f = lambda Z: np.sin(Z.sum(1)) + 0.3 * Z[:, 0] ** 2 + 3.0
+    info = ko.make_kriginfo(X, f(X)[:, None], kernel=kernel, nugget=-6)
+    x = np.array([0.1, -0.2, 0.3, 0.0])
+    if len(kernel) > 1:
+        x = np.concatenate((x, [0.7, 0.4]))           # kernel weights ride along in x (nuggetset)
+    kb.likelihood(x.copy(), info, "all", False)
+    assert model_for(info).last_fit_appended is False
+    xq = rng.uniform(-1, 1, (300, d))
+    for step in range(6):
+        xn = rng.uniform(-1, 1, (1, d))
+        yn = kb.prediction(xn, info, ["pred"]) if step % 2 == 0 else f(xn)     # believer / true observation
+        info = _believer_step(kb, info, xn, yn)
+        ref, full = copy.deepcopy(info), copy.deepcopy(info)
+        kb.likelihood(x.copy(), info, "all", False)
+        assert model_for(info).last_fit_appended is True
+        n = info["X"].shape[0]
+        ko.likelihood(x.copy(), ref, "all", False, check_pd=False)
+        cond = np.linalg.cond(ref["Psi"] + np.eye(n) * 1e-6)
+        assert np.array_equal(info["Psi"], ref["Psi"]) or relerr(info["Psi"], ref["Psi"]) < 1e-15
+        assert relerr(info["NegLnLike"], ref["NegLnLike"]) < nll_tol(cond)
+        assert relerr(info["BE"], ref["BE"]) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+        assert relerr(info["SigmaSqr"], ref["SigmaSqr"]) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+        assert relerr(info["U"], ref["U"], 1.0) < max(1e-10, 0.5 * cond * 2.0 ** -53)
+        assert np.all(np.tril(info["U"], -1) == 0.0)
+        got, want = kb.prediction(xq, info, ["pred", "SSqr"]), ko.prediction(xq, ref, ["pred", "SSqr"])
+        assert relerr(got[0], want[0]) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+        s2 = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
+        assert relerr(got[1], want[1], 1e-6 * s2) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
+        # the same KrigInfo refactorised from scratch on the device
+        monkeypatch.setenv("KB200_NO_APPEND", "1")
+        clear_cache_keep = model_for(full)            # a second model for the copied arrays
+        kb.likelihood(x.copy(), full, "all", False)
+        assert clear_cache_keep.last_fit_appended is False
+        monkeypatch.delenv("KB200_NO_APPEND")
+        assert relerr(info["NegLnLike"], full["NegLnLike"]) < max(1e-11, 0.05 * cond * 2.0 ** -53)
+        assert relerr(info["U"], full["U"], 1.0) < max(1e-12, 0.05 * cond * 2.0 ** -53)
+    clear_cache()
+
+
+def test_append_refuses_other_hyperparameters_and_falls_back_to_full_fit(kb):
+    """kb200_fit_append fails loudly when the hyper-parameters differ; the host layer only appends when the cached
+    fit is the fit of the same x (otherwise likelihood(..., 'all') refactorises on the device)."""
+    from kadal_b200 import _capi
+    from kadal_b200.model import model_for, clear_cache
+    clear_cache()
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, (40, 3))
+    info = ko.make_kriginfo(X, np.sin(X.sum(1))[:, None] + 2.0, kernel=["gaussian"], nugget=-6)
+    x = np.array([0.0, 0.1, -0.1])
+    kb.likelihood(x.copy(), info, "all", False)
+    prev = model_for(info)
+    info = _believer_step(kb, info, rng.uniform(-1, 1, (1, 3)), np.array([2.0]))
+    nxt = model_for(info)
+    with pytest.raises(_capi.Kb200Error):
+        nxt.fit_state(x + 0.01, False, -6.0, append_to=prev)
+    ref = copy.deepcopy(info)
+    kb.likelihood(x + 0.01, info, "all", False)                 # other theta: full fit, no append
+    assert nxt.last_fit_appended is False
+    ko.likelihood(x + 0.01, ref, "all", False, check_pd=False)
+    assert relerr(info["NegLnLike"], ref["NegLnLike"]) < 1e-9
+    clear_cache()
+
+
 def test_kpls_class_cmaes_drop_in(kb):
     """KPLS (kpls_model.py): PLS rotations on the host (scikit-learn, as the reference), CMA-ES
     populations evaluated in GPU batches, prediction through the projected distances."""
