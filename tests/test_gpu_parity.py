@@ -601,6 +601,35 @@ def test_one_sample_append_matches_refactorisation_and_oracle(kb, monkeypatch, k
     clear_cache()
 
 
+def test_one_sample_append_kpls_and_trainvar(kb):
+    """The append under KPLS-projected distances (the theta-independent planes of the bordered model are rebuilt, the
+    factor is extended) and with trainvar=True (sigma^2 rides in x and does not enter Psi)."""
+    from kadal_b200.model import model_for, clear_cache
+    clear_cache()
+    rng = np.random.default_rng(77)
+    n0, d, h = 127, 6, 2
+    X = rng.uniform(-1, 1, (n0, d))
+    f = lambda Z: (Z[:, :3].sum(1)) ** 2 + 0.5 * Z[:, 4] + 3.0
+    pls = rng.standard_normal((d, h)) / 3.0
+    for tv, x in ((False, np.array([0.2, -0.1])), (True, np.array([0.2, -0.1, 0.3]))):
+        info = ko.make_kriginfo(X, f(X)[:, None], kernel=["gaussian"], nugget=-6, pls=pls, n_princomp=h)
+        kb.likelihood(x.copy(), info, "all", tv)
+        for step in range(3):
+            xn = rng.uniform(-1, 1, (1, d))
+            info = _believer_step(kb, info, xn, f(xn))
+            ref = copy.deepcopy(info)
+            kb.likelihood(x.copy(), info, "all", tv)
+            assert model_for(info).last_fit_appended is True
+            ko.likelihood(x.copy(), ref, "all", tv, check_pd=False)
+            n = info["X"].shape[0]
+            cond = np.linalg.cond(ref["Psi"] + np.eye(n) * 1e-6)
+            assert relerr(info["NegLnLike"], ref["NegLnLike"]) < nll_tol(cond)
+            assert relerr(info["U"], ref["U"], 1.0) < max(1e-10, 0.5 * cond * 2.0 ** -53)
+            xq = rng.uniform(-1, 1, (100, d))
+            assert relerr(kb.prediction(xq, info, ["pred"]), ko.prediction(xq, ref, ["pred"])) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+    clear_cache()
+
+
 def test_append_refuses_other_hyperparameters_and_falls_back_to_full_fit(kb):
     """kb200_fit_append fails loudly when the hyper-parameters differ; the host layer only appends when the cached
     fit is the fit of the same x (otherwise likelihood(..., 'all') refactorises on the device)."""
