@@ -152,3 +152,66 @@ def pinned_free(arr):
     p = _PINNED.pop(arr.__array_interface__["data"][0], None)
     if p:
         load().kb200_host_free(p)
+
+
+# ---------------------------------------------------------------- pinned result arrays
+# likelihood(x, KrigInfo, 'all') hands U and Psi (n x n each) back to the host: into pageable numpy memory that copy
+# is 5 of the 6 ms of the call at n = 1000 (56 of 60 ms at n = 4000).  Result arrays therefore live in recycled pinned
+# buffers: a buffer goes back to the free list when the last numpy view of it dies, pinning new pages (slow) is
+# needed only while the working set grows.  Bounded: beyond $KB200_PINNED_MB (default 2048) of live + free pinned
+# memory results fall back to ordinary numpy arrays (same values, slower copy).
+import threading
+import weakref
+
+_RES_LOCK = threading.Lock()
+_RES_FREE = []            # (capacity, pointer)
+_RES_BYTES = [0]          # live + free
+_RES_LIMIT = int(float(os.environ.get("KB200_PINNED_MB", "2048")) * (1 << 20))
+
+
+def _res_release(p, cap):
+    with _RES_LOCK:
+        if len(_RES_FREE) < 16:
+            _RES_FREE.append((cap, p))
+            return
+        _RES_BYTES[0] -= cap
+    try:
+        load().kb200_host_free(c_void_p(p))
+    except Exception:
+        pass
+
+
+def result_empty(shape):
+    """float64 array for a device->host result, pinned when the budget allows."""
+    count = int(np.prod(shape))
+    need = max(count * 8, 8)
+    if _RES_LIMIT <= 0 or need < (1 << 16):
+        return np.empty(shape)
+    p, drop = None, []
+    with _RES_LOCK:
+        fits = [i for i, (c, _) in enumerate(_RES_FREE) if need <= c <= 2 * need]
+        if fits:
+            cap, p = _RES_FREE.pop(min(fits, key=lambda i: _RES_FREE[i][0]))
+        else:
+            cap = need + need // 8
+            if _RES_BYTES[0] + cap > _RES_LIMIT:      # make room: the free buffers did not fit anyway
+                drop, _RES_FREE[:] = list(_RES_FREE), []
+                _RES_BYTES[0] -= sum(c for c, _ in drop)
+            if _RES_BYTES[0] + cap > _RES_LIMIT:
+                cap = None
+            else:
+                _RES_BYTES[0] += cap
+    lib = require_gpu()
+    for _, q in drop:
+        lib.kb200_host_free(c_void_p(q))
+    if cap is None:
+        return np.empty(shape)
+    if p is None:
+        p = lib.kb200_host_alloc(cap)
+        if not p:
+            with _RES_LOCK:
+                _RES_BYTES[0] -= cap
+            return np.empty(shape)
+    buf = (ctypes.c_char * cap).from_address(p)
+    weakref.finalize(buf, _res_release, p, cap).atexit = False
+    return np.frombuffer(buf, dtype=np.float64, count=count).reshape(shape)

@@ -110,8 +110,8 @@ class GpuModel:
         (``kb200_fit_append``) instead of being recomputed."""
         x = as_f64(np.asarray(x).reshape(-1))
         n = self.n
-        U = np.empty((n, n)) if want_U else None
-        Psi = np.empty((n, n)) if want_Psi else None
+        U = _capi.result_empty((n, n)) if want_U else None
+        Psi = _capi.result_empty((n, n)) if want_Psi else None
         BE = np.empty(self.p)
         theta = np.empty(self.ntheta)
         wgkf = np.empty(self.nkernel)

@@ -62,3 +62,58 @@ def test_append_source_rules(cache, monkeypatch):
     prev.fit_key = (x.tobytes(), False, -6.0)
     prev.close()
     assert M.append_source(nxt, x, False, -6.0) is None
+
+
+def test_pinned_result_arrays_are_recycled(monkeypatch):
+    """U / Psi of a mode='all' call live in recycled pinned buffers (kadal_b200/_capi.py:result_empty): a buffer
+    returns to the free list when its last numpy view dies, is reused for a slightly larger result, survives
+    deepcopy / pickle as an ordinary array, and the budget falls back to pageable memory -- on a stand-in
+    allocator, no device."""
+    import copy
+    import ctypes
+    import gc
+    import pickle
+    from kadal_b200 import _capi
+
+    class FakeLib:
+        def __init__(self):
+            self.live = {}
+
+        def kb200_host_alloc(self, n):
+            b = (ctypes.c_char * n)()
+            self.live[ctypes.addressof(b)] = b
+            return ctypes.addressof(b)
+
+        def kb200_host_free(self, p):
+            del self.live[p.value]
+
+    fl = FakeLib()
+    monkeypatch.setattr(_capi, "require_gpu", lambda: fl)
+    monkeypatch.setattr(_capi, "load", lambda: fl)
+    monkeypatch.setattr(_capi, "_RES_FREE", [])
+    monkeypatch.setattr(_capi, "_RES_BYTES", [0])
+    monkeypatch.setattr(_capi, "_RES_LIMIT", 4 << 20)
+    a = _capi.result_empty((300, 300))
+    a[:] = 2.0
+    addr = a.__array_interface__["data"][0]
+    assert len(fl.live) == 1 and _capi._RES_BYTES[0] >= 720000
+    view = a[:5]
+    del a
+    gc.collect()
+    assert _capi._RES_FREE == []                       # a view still holds the buffer
+    del view
+    gc.collect()
+    assert len(_capi._RES_FREE) == 1
+    b = _capi.result_empty((301, 301))                 # the next model of a believer sequence
+    assert b.__array_interface__["data"][0] == addr and len(fl.live) == 1
+    b[:] = 3.0
+    assert copy.deepcopy(b).sum() == b.sum() and pickle.loads(pickle.dumps(b)).shape == (301, 301)
+    assert _capi.result_empty((4, 4)).base is None      # small results stay ordinary arrays
+    big = _capi.result_empty((1000, 1000))              # over the budget: pageable
+    assert big.base is None and len(fl.live) == 1
+    c = _capi.result_empty((500, 500))                  # fits next to b
+    assert len(fl.live) == 2
+    del b, c
+    gc.collect()
+    d = _capi.result_empty((600, 600))                  # needs the room of the two free buffers
+    assert d.base is not None and len(fl.live) == 1
