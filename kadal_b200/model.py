@@ -158,7 +158,7 @@ class GpuModel:
         ptrs = []
         for i, nm in enumerate(names):
             if want & (1 << i):
-                arr = out[nm] if out is not None and nm in out else np.empty(npred)
+                arr = out[nm] if out is not None and nm in out else _capi.result_empty((npred,))
                 outs[nm] = arr
                 ptrs.append(ptr(arr))
             else:
