@@ -8,6 +8,7 @@
 #include <vector>
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include "../../include/kb200.h"
 #include "kb200_kernels.h"
 
@@ -1056,6 +1057,95 @@ int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double
 
 }  // extern "C"
 
+// ------------------------------------------------------- bulk host -> device copies
+// KADAL's callers hold their 10^7-point populations in ordinary (pageable) numpy arrays.  cudaMemcpyAsync from
+// pageable memory is staged by the driver on the calling thread at ~10 GB/s (320 MB of C4 points: 31 ms against 13 ms
+// of prediction kernels).  Large pageable sources are therefore copied by a few host threads into a small ring of
+// pinned buffers and sent from there, so the copy of the next chunk proceeds at several times that rate while the
+// kernels of the current one run.  Pinned sources and small copies go straight to cudaMemcpyAsync.
+// $KB200_STAGE_THREADS (default 4, 0 = always the driver's path).
+struct HostStager {
+  static constexpr int RING = 3;
+  static constexpr size_t SLOT = (size_t)32 << 20;
+  void* buf[RING] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[RING] = {nullptr, nullptr, nullptr};
+  bool used[RING] = {false, false, false};
+  int next = 0, dev = -1, threads = 4;
+  bool failed = false;
+  std::mutex mu;
+  bool init(int device) {
+    if (failed) return false;
+    if (buf[0]) return dev == device;        // one ring per process (events belong to its device)
+    const char* e = getenv("KB200_STAGE_THREADS");
+    if (e) threads = atoi(e);
+    if (threads <= 0) { failed = true; return false; }
+    threads = std::min(threads, 16);
+    for (int i = 0; i < RING; ++i) {
+      if (cudaHostAlloc(&buf[i], SLOT, cudaHostAllocDefault) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        for (int k = 0; k <= i; ++k) {
+          if (buf[k]) cudaFreeHost(buf[k]);
+          if (ev[k]) cudaEventDestroy(ev[k]);
+          buf[k] = nullptr; ev[k] = nullptr;
+        }
+        failed = true;
+        return false;
+      }
+    }
+    dev = device;
+    return true;
+  }
+};
+static HostStager g_stager;
+
+static void parallel_memcpy(char* dst, const char* src, size_t bytes, int threads) {
+  if (threads <= 1 || bytes < ((size_t)4 << 20)) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t per = ((bytes / threads) + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; ++t) {
+    const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+    if (hi > lo) th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+  }
+  memcpy(dst, src, std::min(bytes, per));
+  for (auto& t : th) t.join();
+}
+
+static cudaError_t h2d_bulk(void* dst, const void* src, size_t bytes, int device, cudaStream_t st) {
+  bool staged = bytes >= ((size_t)16 << 20);
+  if (staged) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) != cudaSuccess) {
+      cudaGetLastError();
+      staged = false;
+    } else if (at.type != cudaMemoryTypeUnregistered) {
+      staged = false;                         // already pinned (or managed): the DMA engine reads it directly
+    }
+  }
+  if (!staged) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  std::lock_guard<std::mutex> g(g_stager.mu);
+  if (!g_stager.init(device)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  for (size_t off = 0; off < bytes; off += HostStager::SLOT) {
+    const size_t len = std::min(HostStager::SLOT, bytes - off);
+    const int k = g_stager.next;
+    g_stager.next = (k + 1) % HostStager::RING;
+    if (g_stager.used[k]) {
+      cudaError_t e = cudaEventSynchronize(g_stager.ev[k]);
+      if (e != cudaSuccess) return e;
+    }
+    parallel_memcpy(static_cast<char*>(g_stager.buf[k]), static_cast<const char*>(src) + off, len, g_stager.threads);
+    cudaError_t e = cudaMemcpyAsync(static_cast<char*>(dst) + off, g_stager.buf[k], len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(g_stager.ev[k], st);
+    if (e != cudaSuccess) return e;
+    g_stager.used[k] = true;
+  }
+  return cudaSuccess;
+}
+
 // --------------------------------------------------------------------- prediction
 static long chunk_tiles_for(const kb200_model* m) {
   // point tiles per variance chunk: a multiple of the SM count.  One wave per launch left a quarter of the
@@ -1270,7 +1360,7 @@ int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int nor
     cudaStream_t st = sl.stream;
     const long np = std::min<long>(sc, npred - p0);
     CK(sl.x.reserve((size_t)std::min<long>(sc, npred) * m->d * 8));
-    CK(cudaMemcpyAsync(sl.x.p, x + (size_t)p0 * m->d, (size_t)np * m->d * 8, cudaMemcpyHostToDevice, st));
+    CK(h2d_bulk(sl.x.p, x + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
     double* outs[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     CK(sl.out[0].reserve((size_t)std::min<long>(sc, npred) * 8));
     CK(sl.out[2].reserve((size_t)std::min<long>(sc, npred) * 8));
@@ -1323,7 +1413,7 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
     cudaStream_t st = sl.stream;
     const long np = std::min<long>(sc, npred - p0);
     CK(sl.x.reserve((size_t)std::min<long>(sc, npred) * m->d * 8));
-    CK(cudaMemcpyAsync(sl.x.p, x + (size_t)p0 * m->d, (size_t)np * m->d * 8, cudaMemcpyHostToDevice, st));
+    CK(h2d_bulk(sl.x.p, x + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
     double* outs[7];
     for (int i = 0; i < 7; ++i) {
       outs[i] = nullptr;
@@ -1375,8 +1465,8 @@ int kb200_sobol_sums(kb200_model* m, const double* A, const double* B, long long
   const unsigned char* masks = static_cast<const unsigned char*>(m->sobMask.p);
   for (long p0 = 0; p0 < N; p0 += sc) {
     const long np = std::min<long>(sc, (long)N - p0);
-    CK(cudaMemcpyAsync(sl.x.p, A + (size_t)p0 * m->d, (size_t)np * m->d * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(m->sobB.p, B + (size_t)p0 * m->d, (size_t)np * m->d * 8, cudaMemcpyHostToDevice, st));
+    CK(h2d_bulk(sl.x.p, A + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
+    CK(h2d_bulk(m->sobB.p, B + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
     double* outs[7] = {ya, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     rc = predict_core(m, sl, sl.x.d(), np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
     if (rc) return rc;
