@@ -1100,7 +1100,8 @@ struct HostStager {
 static HostStager g_stager;
 
 static void parallel_memcpy(char* dst, const char* src, size_t bytes, int threads) {
-  if (threads <= 1 || bytes < ((size_t)4 << 20)) {
+  threads = (int)std::min<size_t>((size_t)threads, bytes >> 21);   // at least 2 MiB per thread
+  if (threads <= 1) {
     memcpy(dst, src, bytes);
     return;
   }
@@ -1115,7 +1116,7 @@ static void parallel_memcpy(char* dst, const char* src, size_t bytes, int thread
 }
 
 static cudaError_t h2d_bulk(void* dst, const void* src, size_t bytes, int device, cudaStream_t st) {
-  bool staged = bytes >= ((size_t)16 << 20);
+  bool staged = bytes >= ((size_t)4 << 20);
   if (staged) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, src) != cudaSuccess) {
@@ -1408,10 +1409,11 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
   // for true overlap; pageable memory still works, staged by the driver).
   const long ct = chunk_tiles_for(m) * TB;
   long sc = std::max<long>(ct, (1L << 19) / ct * ct);
-  for (long p0 = 0, it = 0; p0 < npred; p0 += sc, ++it) {
+  // the first super-chunk is a single kernel chunk: the device starts after 1/3 .. 1/4 of the copy-in latency
+  for (long p0 = 0, it = 0, np = 0; p0 < npred; p0 += np, ++it) {
     PredSlot& sl = m->slot[it & 1];
     cudaStream_t st = sl.stream;
-    const long np = std::min<long>(sc, npred - p0);
+    np = std::min<long>(it == 0 ? ct : sc, npred - p0);
     CK(sl.x.reserve((size_t)std::min<long>(sc, npred) * m->d * 8));
     CK(h2d_bulk(sl.x.p, x + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
     double* outs[7];

@@ -29,5 +29,17 @@ for name, n, d, npts, want in (("c3", 200, 6, 4_000_000, 1 | 4), ("c4", 800, 20,
         chk = float(r["pred"][::1000].sum())
         del r
     out[name] = {"npts": npts, "ms_best": min(ts[1:]) * 1e3, "pts_per_s": npts / min(ts[1:]), "check": chk}
+    # the same with the points already in pinned memory (what bench.py's e2e measures)
+    from kadal_b200 import _capi
+    xp = _capi.pinned_empty(x.shape)
+    xp[:] = x
+    ts = []
+    for rep in range(4):
+        t0 = time.perf_counter()
+        r = m.predict(xp, want, normtype=1, norm_a=lb, norm_b=ub)
+        ts.append(time.perf_counter() - t0)
+        del r
+    out[name]["pinned_input_ms_best"] = min(ts[1:]) * 1e3
+    _capi.pinned_free(xp)
     m.close()
 print(json.dumps(out))
