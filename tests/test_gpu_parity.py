@@ -248,6 +248,37 @@ def test_predict_crosses_chunk_boundary(kb, golden_c3):
     assert relerr(s[sel], ra[1], 1e-3 * np.sqrt(s2)) < TOL_VAR
 
 
+def test_host_memory_paths_give_identical_predictions(kb, golden_c3, monkeypatch):
+    """Pageable input through the threaded pinned staging ring (h2d_bulk, several trips round the 3 x 32 MiB ring),
+    input already pinned, results in recycled pinned arrays or in pageable ones: the same bits every time."""
+    from kadal_b200 import _capi
+    from kadal_b200.model import model_for
+    g = golden_c3
+    info, _ = cases.c3_info(g)
+    kb.likelihood(g["fit_x"].copy(), info, "all", False)
+    m = model_for(info)
+    npred = 3_000_011                                       # 144 MB of points
+    rng = np.random.default_rng(4)
+    xp = rng.uniform(g["lb"], g["ub"], (npred, 6))
+    want = 1 | 4
+    kw = dict(normtype=1, norm_a=g["lb"], norm_b=g["ub"])
+    a = m.predict(xp, want, **kw)
+    assert a["pred"].base is not None                        # a view of a pinned buffer
+    xpin = _capi.pinned_empty(xp.shape)
+    xpin[:] = xp
+    b = m.predict(xpin, want, **kw)
+    monkeypatch.setattr(_capi, "_RES_LIMIT", 0)
+    c = m.predict(xp, want, **kw)
+    assert c["pred"].base is None
+    for nm in ("pred", "s"):
+        assert np.array_equal(a[nm], b[nm]) and np.array_equal(a[nm], c[nm])
+    sel = rng.integers(0, npred, 400)
+    ra = ko.prediction(xp[sel], info, ["pred", "s"])
+    assert relerr(a["pred"][sel], ra[0].ravel()) < TOL_MEAN
+    assert relerr(a["s"][sel], ra[1].ravel(), 1e-3 * np.sqrt(float(info["SigmaSqr"][0, 0]))) < TOL_VAR
+    _capi.pinned_free(xpin)
+
+
 def test_return_types_and_errors(kb, golden_c):
     info, x, tv = cases.appendix_c_info(golden_c, "gaussian")
     kb.likelihood(x.copy(), info, "all", tv)
