@@ -44,7 +44,8 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("KB200_NVCC_EXTRA", "").split()   # A/B builds (tools/ab_build.sh), e.g. -DKB200_CORR_FAST_BLOCKS=2
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

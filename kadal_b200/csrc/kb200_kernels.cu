@@ -33,6 +33,14 @@ constexpr int CORR_THREADS = 256;
 #ifndef KB200_CORR_FAST_BLOCKS
 #define KB200_CORR_FAST_BLOCKS 3
 #endif
+// 1: the Gaussian fast path computes both rows of a thread per column quad for 8 <= d < 16 (kb200_corr.cuh:corr_quad_gauss2;
+// C2 assembly 1.70 -> 1.52 ms per generation, mean prediction at d = 10 9.26 -> 8.26 ms per 2e6 points, same bits); 0: one row at a time
+#ifndef KB200_CORR_PAIR2
+#define KB200_CORR_PAIR2 1
+#endif
+#ifndef KB200_CORR_PAIR2_EDGE   // the same on diagonal tiles / the last tile row of the assembly: measured 1.52 -> 1.82 ms (ptxas spills
+#define KB200_CORR_PAIR2_EDGE 0 // 864 instead of 228 bytes at the 85-register cap), off
+#endif
 
 __device__ __forceinline__ double standardize1(double x, int normtype, double a, double b) {
   if (normtype == 1) {  // 'default': ((x-lb)/(ub-lb) - 0.5) * 2   samplingplan.py:77-83
@@ -53,6 +61,83 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
                                           int ti, int tj, double* tile, int warp, int g, int ch,
                                           double (&facc)[2], double (&uacc)[2]) {
   const int d = A.spec.d;
+#if KB200_CORR_PAIR2
+  if (FAST && INTERIOR) {
+    // both rows of the thread per column quad (corr_quad_gauss2); per entry and per row the same operations in the
+    // same order as the loop below
+    const int row0 = 8 * warp + g, row1 = row0 + 64;
+    const double2* thi = reinterpret_cast<const double2*>(th2 + 2 * d);
+#pragma unroll 1
+    for (int s = 0; s < NSLAB; ++s) {
+      const int c0 = s * KS + 4 * ch;
+      Quad q0, q1;
+      corr_quad_gauss2<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV>(d, th2, th2 + d, thi, w0, As + row0 * lda,
+                                                                         As + row1 * lda, Bt + c0, TB, q0, q1);
+      if (MODE == CORR_ASSEMBLE || tile) {
+        double2* dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row0 * KS + ((ch ^ (row0 & 3)) << 2));
+        dst[0] = make_double2(q0.v[0], q0.v[1]);
+        dst[1] = make_double2(q0.v[2], q0.v[3]);
+        dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row1 * KS + ((ch ^ (row1 & 3)) << 2));
+        dst[0] = make_double2(q1.v[0], q1.v[1]);
+        dst[1] = make_double2(q1.v[2], q1.v[3]);
+      }
+      if (MODE == CORR_PREDICT) {
+        const int gc0 = tj * TB + c0;
+        double fa0 = 0.0, fa1 = 0.0, ua0 = 0.0, ua1 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double al = A.alpha[gc0 + e];
+          fa0 = fma(q0.v[e], al, fa0);
+          fa1 = fma(q1.v[e], al, fa1);
+          if (A.wvec) {
+            const double wv = A.wvec[gc0 + e];
+            ua0 = fma(q0.v[e], wv, ua0);
+            ua1 = fma(q1.v[e], wv, ua1);
+          }
+        }
+        facc[0] += fa0; uacc[0] += ua0;
+        facc[1] += fa1; uacc[1] += ua1;
+      }
+    }
+    return;
+  }
+  if (KB200_CORR_PAIR2_EDGE && FAST && !INTERIOR && MODE == CORR_ASSEMBLE) {
+    // diagonal tiles and the last tile row: the same pairing where both rows of the thread need the quad, then the
+    // per-entry fix-ups of the loop below (identity padding, nugget, zeroed upper triangle)
+    const int row0 = 8 * warp + g, row1 = row0 + 64;
+    const long grow0 = (long)ti * TB + row0, grow1 = grow0 + 64;
+    const double2* thi = reinterpret_cast<const double2*>(th2 + 2 * d);
+#pragma unroll 1
+    for (int s = 0; s < NSLAB; ++s) {
+      const int c0 = s * KS + 4 * ch;
+      const int gc0 = tj * TB + c0;
+      const bool colok = gc0 < A.n;
+      const bool n0 = colok && grow0 < A.n && !(ti == tj && c0 > row0);
+      const bool n1 = colok && grow1 < A.n && !(ti == tj && c0 > row1);
+      Quad q0 = quad_set(0.0), q1 = quad_set(0.0);
+      if (n0 && n1) corr_quad_gauss2<true>(d, th2, th2 + d, thi, w0, As + row0 * lda, As + row1 * lda, Bt + c0, TB, q0, q1);
+      else if (n1) q1 = corr_quad_gauss<true>(d, th2, th2 + d, w0, As + row1 * lda, Bt + c0, TB);
+      else if (n0) q0 = corr_quad_gauss<true>(d, th2, th2 + d, w0, As + row0 * lda, Bt + c0, TB);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gc = gc0 + e;
+        if (grow0 >= A.n || gc >= A.n) q0.v[e] = (grow0 == gc) ? 1.0 : 0.0;
+        else if (grow0 == gc && A.add_eps) q0.v[e] = __dadd_rn(q0.v[e], eps);
+        else if (ti == tj && gc > grow0) q0.v[e] = 0.0;
+        if (grow1 >= A.n || gc >= A.n) q1.v[e] = (grow1 == gc) ? 1.0 : 0.0;
+        else if (grow1 == gc && A.add_eps) q1.v[e] = __dadd_rn(q1.v[e], eps);
+        else if (ti == tj && gc > grow1) q1.v[e] = 0.0;
+      }
+      double2* dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row0 * KS + ((ch ^ (row0 & 3)) << 2));
+      dst[0] = make_double2(q0.v[0], q0.v[1]);
+      dst[1] = make_double2(q0.v[2], q0.v[3]);
+      dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row1 * KS + ((ch ^ (row1 & 3)) << 2));
+      dst[0] = make_double2(q1.v[0], q1.v[1]);
+      dst[1] = make_double2(q1.v[2], q1.v[3]);
+    }
+    return;
+  }
+#endif
 #pragma unroll 1
   for (int rgi = 0; rgi < 2; ++rgi) {
     const int row = 8 * (warp + 8 * rgi) + g;
@@ -117,7 +202,7 @@ corr_tile_kernel(CorrArgs A) {
   const int lda = d | 1;
   double* As = reinterpret_cast<double*>(smem_raw);          // [128][lda]
   double* Bt = As + ((TB * lda + 1) & ~1);                   // [d][128]
-  double* th2 = Bt + d * TB;                                 // [d] theta^2, then [d] RN(1/theta^2)
+  double* th2 = Bt + d * TB;                                 // [d] theta^2, [d] RN(1/theta^2), [d] pairs of both
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, ch = lane & 3;
 
@@ -139,7 +224,11 @@ corr_tile_kernel(CorrArgs A) {
     m = 0;
   }
   const double* cand = A.cand + m * A.cand_stride;
-  if (FAST && tid < 2 * d) th2[tid] = cand[2 * A.spec.ntheta + tid];   // theta2 | rtheta2 are adjacent
+  if (FAST && tid < 2 * d) {   // theta2 | rtheta2 are adjacent; second copy interleaved {theta2_k, rtheta2_k} for one 16-byte load
+    const double v = cand[2 * A.spec.ntheta + tid];
+    th2[tid] = v;
+    th2[2 * d + 2 * (tid % d) + tid / d] = v;
+  }
   const double w0 = cand[4 * A.spec.ntheta];
 
   // ---- row coordinates -> As
@@ -1734,7 +1823,7 @@ static_assert(PS_SMEM <= 227 * 1024, "predict_small_kernel shared memory");
 // ====================================================================== launchers
 static inline size_t corr_smem_bytes(int d) {
   const int lda = d | 1;
-  return (size_t)(((TB * lda + 1) & ~1) + d * TB + 2 * d) * sizeof(double);
+  return (size_t)(((TB * lda + 1) & ~1) + d * TB + 4 * d) * sizeof(double);
 }
 
 #define KB_LAUNCH_CHECK()                          \
