@@ -43,3 +43,20 @@ def test_version_and_no_gpu_is_loud(lib):
         info = ko.make_kriginfo(np.random.default_rng(0).uniform(-1, 1, (8, 2)), np.ones((8, 1)))
         with pytest.raises(_capi.Kb200Error):   # no silent CPU fallback
             kadal_b200.likelihood(np.zeros(2), info, "default", False)
+
+
+def test_correlation_fast_path_does_not_spill(lib):
+    """The Gaussian fast path of corr_tile_kernel runs at an 85-register cap (three CTAs per SM); small source changes
+    have made ptxas spill 400-1200 bytes there, which costs 20 % of the assembly and 28 % of the C4 prediction
+    (DESIGN.md section 4, r1s).  Resource usage of the built object: stack frame of both instantiations <= 64 bytes."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    obj = os.path.join(os.path.dirname(_build.LIB), "kb200_kernels.o")
+    if not os.path.exists(cuobjdump) or not os.path.exists(obj):
+        pytest.skip("cuobjdump or the object file is not available")
+    txt = subprocess.run([cuobjdump, "-res-usage", obj], capture_output=True, text=True).stdout
+    found = re.findall(r"Function (\S*corr_tile_kernelILb1ELi[01]E\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", txt)
+    assert len(found) == 2, txt[:400]
+    for name, reg, stack in found:
+        assert int(reg) <= 85 and int(stack) <= 64, (name, reg, stack)
