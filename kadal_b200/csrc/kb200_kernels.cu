@@ -55,7 +55,7 @@ __device__ __forceinline__ double standardize1(double x, int normtype, double a,
 // INTERIOR: every row and column of the pair is a real sample / point and the pair is not on the
 // diagonal, so none of the per-entry fix-ups (identity padding, nugget, zeroed upper triangle, skipped
 // quads) can apply: 21 of the 36 tiles of C2, all but the last sample tile of a prediction.
-template <bool FAST, int MODE, bool INTERIOR>
+template <int FAST, int MODE, bool INTERIOR>   // FAST: 0 general path; Gaussian fast path: 1..3 = d class 1..3 only (kb200_corr.cuh), 4 = any d
 __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __restrict__ cand, const double* th2,
                                           double w0, double eps, const double* As, const double* Bt, int lda,
                                           int ti, int tj, double* tile, int warp, int g, int ch,
@@ -71,7 +71,7 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
     for (int s = 0; s < NSLAB; ++s) {
       const int c0 = s * KS + 4 * ch;
       Quad q0, q1;
-      corr_quad_gauss2<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV>(d, th2, th2 + d, thi, w0, As + row0 * lda,
+      corr_quad_gauss2<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV, FAST & 3>(d, th2, th2 + d, thi, w0, As + row0 * lda,
                                                                          As + row1 * lda, Bt + c0, TB, q0, q1);
       if (MODE == CORR_ASSEMBLE || tile) {
         double2* dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row0 * KS + ((ch ^ (row0 & 3)) << 2));
@@ -115,9 +115,9 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
       const bool n0 = colok && grow0 < A.n && !(ti == tj && c0 > row0);
       const bool n1 = colok && grow1 < A.n && !(ti == tj && c0 > row1);
       Quad q0 = quad_set(0.0), q1 = quad_set(0.0);
-      if (n0 && n1) corr_quad_gauss2<true>(d, th2, th2 + d, thi, w0, As + row0 * lda, As + row1 * lda, Bt + c0, TB, q0, q1);
-      else if (n1) q1 = corr_quad_gauss<true>(d, th2, th2 + d, w0, As + row1 * lda, Bt + c0, TB);
-      else if (n0) q0 = corr_quad_gauss<true>(d, th2, th2 + d, w0, As + row0 * lda, Bt + c0, TB);
+      if (n0 && n1) corr_quad_gauss2<true, FAST & 3>(d, th2, th2 + d, thi, w0, As + row0 * lda, As + row1 * lda, Bt + c0, TB, q0, q1);
+      else if (n1) q1 = corr_quad_gauss<true, FAST & 3>(d, th2, th2 + d, w0, As + row1 * lda, Bt + c0, TB);
+      else if (n0) q0 = corr_quad_gauss<true, FAST & 3>(d, th2, th2 + d, w0, As + row0 * lda, Bt + c0, TB);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int gc = gc0 + e;
@@ -157,7 +157,7 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
         }
       }
       if (need) {
-        if (FAST) q = corr_quad_gauss<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV>(d, th2, th2 + d, w0, As + row * lda, Bt + c0, TB);
+        if (FAST) q = corr_quad_gauss<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV, FAST & 3>(d, th2, th2 + d, w0, As + row * lda, Bt + c0, TB);
         else q = corr_quad<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV>(A.spec, cand, As + row * lda, Bt + c0, TB);
       } else {
         q = quad_set(0.0);
@@ -194,7 +194,7 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
   }
 }
 
-template <bool FAST, int MODE>
+template <int FAST, int MODE>
 __global__ void __launch_bounds__(CORR_THREADS, FAST ? KB200_CORR_FAST_BLOCKS : 2)
 corr_tile_kernel(CorrArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -2047,25 +2047,35 @@ cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t 
   const int dev = cur_dev();
   if (sm > g_corr_attr[dev]) {
     const int want = (int)(sm > 48 * 1024 ? sm : 48 * 1024);
-    cudaError_t e = cudaFuncSetAttribute(corr_tile_kernel<false, CORR_ASSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(corr_tile_kernel<true, CORR_ASSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(corr_tile_kernel<false, CORR_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(corr_tile_kernel<true, CORR_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e != cudaSuccess) return e;
+    const void* kernels[] = {(const void*)corr_tile_kernel<0, CORR_ASSEMBLE>, (const void*)corr_tile_kernel<1, CORR_ASSEMBLE>,
+                             (const void*)corr_tile_kernel<4, CORR_ASSEMBLE>, (const void*)corr_tile_kernel<0, CORR_PREDICT>,
+                             (const void*)corr_tile_kernel<1, CORR_PREDICT>,  (const void*)corr_tile_kernel<2, CORR_PREDICT>,
+                             (const void*)corr_tile_kernel<4, CORR_PREDICT>};
+    for (const void* k : kernels) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      if (e != cudaSuccess) return e;
+    }
     g_corr_attr[dev] = sm;
   }
   const bool fast = a.spec.nkernel == 1 && a.spec.kid[0] == K_GAUSS && !a.spec.kpls;
+  // One kernel per class of d where that measured faster (r1s A/B, profiles/r1s_ab_assembly_pairing.log): d < 8 both modes
+  // (prediction at d = 6 2.09 -> 1.91 ms per 2e6 points), 8 <= d < 16 prediction (8.11 -> 7.91 ms); the kernel holding all
+  // three summation schemes (4) elsewhere: specialised, ptxas spills in the assembly at 8 <= d < 16 (1.53 -> 1.65 ms) and
+  // for d >= 16 (C4 11.8 -> 14.2 ms).
+  const int d = a.spec.d;
   const dim3 grid(grid_x, grid_y);
+#define KB_CORR_LAUNCH(DC, MODE) corr_tile_kernel<DC, MODE><<<grid, CORR_THREADS, sm, st>>>(a)
   if (a.mode == CORR_ASSEMBLE) {
-    if (fast) corr_tile_kernel<true, CORR_ASSEMBLE><<<grid, CORR_THREADS, sm, st>>>(a);
-    else corr_tile_kernel<false, CORR_ASSEMBLE><<<grid, CORR_THREADS, sm, st>>>(a);
+    if (!fast) KB_CORR_LAUNCH(0, CORR_ASSEMBLE);
+    else if (d < 8) KB_CORR_LAUNCH(1, CORR_ASSEMBLE);
+    else KB_CORR_LAUNCH(4, CORR_ASSEMBLE);
   } else {
-    if (fast) corr_tile_kernel<true, CORR_PREDICT><<<grid, CORR_THREADS, sm, st>>>(a);
-    else corr_tile_kernel<false, CORR_PREDICT><<<grid, CORR_THREADS, sm, st>>>(a);
+    if (!fast) KB_CORR_LAUNCH(0, CORR_PREDICT);
+    else if (d < 8) KB_CORR_LAUNCH(1, CORR_PREDICT);
+    else if (d < 16) KB_CORR_LAUNCH(2, CORR_PREDICT);
+    else KB_CORR_LAUNCH(4, CORR_PREDICT);
   }
+#undef KB_CORR_LAUNCH
   KB_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -48,7 +48,7 @@ def test_version_and_no_gpu_is_loud(lib):
 def test_correlation_fast_path_does_not_spill(lib):
     """The Gaussian fast path of corr_tile_kernel runs at an 85-register cap (three CTAs per SM); small source changes
     have made ptxas spill 400-1200 bytes there, which costs 20 % of the assembly and 28 % of the C4 prediction
-    (DESIGN.md section 4, r1s).  Resource usage of the built object: stack frame of both instantiations <= 64 bytes."""
+    (DESIGN.md section 4, r1s).  Resource usage of the built object: stack frame of every fast instantiation <= 64 bytes."""
     import shutil
     import subprocess
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
@@ -56,7 +56,8 @@ def test_correlation_fast_path_does_not_spill(lib):
     if not os.path.exists(cuobjdump) or not os.path.exists(obj):
         pytest.skip("cuobjdump or the object file is not available")
     txt = subprocess.run([cuobjdump, "-res-usage", obj], capture_output=True, text=True).stdout
-    found = re.findall(r"Function (\S*corr_tile_kernelILb1ELi[01]E\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", txt)
-    assert len(found) == 2, txt[:400]
+    # fast instantiations: <1, *> d < 8, <2, predict> 8 <= d < 16, <4, *> all summation schemes in one kernel
+    found = re.findall(r"Function (\S*corr_tile_kernelILi[124]ELi[01]E\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", txt)
+    assert len(found) == 5, txt[:400]
     for name, reg, stack in found:
         assert int(reg) <= 85 and int(stack) <= 64, (name, reg, stack)
