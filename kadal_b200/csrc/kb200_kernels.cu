@@ -8,6 +8,7 @@
 //                            "extra rows" of the factorisation and reuse this kernel.
 //   lik_finalize_kernel  K4  GLS beta, sigma^2, concentrated / trainvar ln-likelihood
 //   trsv_diag / trsv_update  alpha = L^-T r, w = L^-T b (predictor state, once per fit), forward solves
+//   append_extract / append_row  one-sample append to a factor (believer / sequential refits, kb200_fit_append)
 //   predict_epilogue_kernel  mean / SSqr / s / EI / PoI / PoF / U-function
 //   import / export kernels  row-major U, Psi  <->  tile layout
 //
