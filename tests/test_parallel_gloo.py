@@ -82,3 +82,67 @@ def test_shard_bounds_cover_everything():
             assert all(b[r][1] == b[r + 1][0] for r in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ------------------------------------------------------------------ AK-MCS reductions across ranks
+class _FakeAkModel:
+    """Stands in for the device model: the per-shard reductions kb200_akmcs_reduce returns, in numpy."""
+
+    def akmcs_reduce(self, x, normtype, na, nb):
+        g, s = x[:, 0], np.abs(x[:, 1]) + 0.1
+        with np.errstate(invalid="ignore"):
+            u = np.abs(g) / s
+        arg = int(np.argmin(u)) if not np.isnan(u).any() else int(np.flatnonzero(np.isnan(u))[0])
+        return float(u[arg]), arg, [int((g <= 0).sum()), int((g - 1.96 * s <= 0).sum()), int((g + 1.96 * s <= 0).sum())]
+
+
+def _ak_population(with_nan):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((1001, 2))
+    x[700, 0] = 1e-9          # the global minimum of U lives in the second shard
+    if with_nan:
+        x[900, 0] = np.nan    # np.argmin puts NaN first
+    return x
+
+
+def _ak_worker(rank, world, port, with_nan, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from kadal_b200 import parallel, reliability
+    reliability.model_for = lambda K: _FakeAkModel()
+    reliability._ensure_predictor = lambda m, K: None
+    reliability._check_supported = lambda K, a, b: None
+    reliability._norm_args = lambda K: (0, None, None)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        x = _ak_population(with_nan)
+        lo, hi = parallel.shard_bounds(len(x), world, rank)
+        q.put((rank, reliability.akmcs_reductions(x[lo:hi], {})))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("with_nan", [False, True])
+def test_akmcs_reductions_combine_across_ranks(with_nan):
+    """reliability.akmcs_reductions under data parallelism: every rank reduces its shard on its GPU (stand-in here), the
+    scalars are combined -- global arg-min with the shard offset, NaN first as np.argmin, counts added -- and every rank
+    gets what one process computes on the whole population (akmcs.py:267-297)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ak_worker, args=(r, 2, port, with_nan, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x = _ak_population(with_nan)
+    mu, arg, cnt = _FakeAkModel().akmcs_reduce(x, 0, None, None)
+    assert arg == (900 if with_nan else 700)
+    pf = cnt[0] / len(x)
+    for rank, r in res:
+        assert r["minUloc"] == arg and (r["minU"] == mu or (np.isnan(mu) and np.isnan(r["minU"])))
+        assert [r["nGless"], r["n_minus"], r["n_plus"]] == cnt and r["nmc"] == len(x)
+        assert r["Pf"] == pf and r["stop_criteria"] == (cnt[1] / len(x) - cnt[2] / len(x)) / pf
