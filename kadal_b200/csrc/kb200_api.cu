@@ -1107,11 +1107,18 @@ static void parallel_memcpy(char* dst, const char* src, size_t bytes, int thread
   }
   const size_t per = ((bytes / threads) + 4095) & ~(size_t)4095;
   std::vector<std::thread> th;
+  size_t done_to = std::min(bytes, per);          // [0, per) is this thread's share
   for (int t = 1; t < threads; ++t) {
-    const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
-    if (hi > lo) th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+    const size_t lo = std::min(bytes, per * t), hi = (t == threads - 1) ? bytes : std::min(bytes, per * (t + 1));
+    if (hi <= lo) continue;
+    try {
+      th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+    } catch (...) {                               // no more threads to be had: the calling thread copies the rest
+      memcpy(dst + lo, src + lo, bytes - lo);
+      break;
+    }
   }
-  memcpy(dst, src, std::min(bytes, per));
+  memcpy(dst, src, done_to);
   for (auto& t : th) t.join();
 }
 
