@@ -55,6 +55,25 @@ def c3_data():
     return X, y, np.full(6, 0.2)
 
 
+def krig_info(X, y, kernel=("gaussian",), pls=None, n_princomp=False):
+    """Minimal KrigInfo dict of an ordinary-Kriging model on inputs already scaled to [-1, 1]^d (the keys
+    likelihood() / prediction() read) -- built here so that the GPU arm imports nothing of oracle/."""
+    n, d = X.shape
+    return dict(nvar=d, nsamp=n, X=X, X_norm=X, y=y, F=np.ones((n, 1)), kernel=list(kernel), nkernel=len(kernel),
+                standardization=True, normtype="default", norm_y=False, type="kriging" if pls is None else "kpls",
+                n_princomp=n_princomp, nugget=-6, idx=np.zeros((1, d)), TrendOrder=0, lb=-np.ones(d), ub=np.ones(d),
+                **({"plscoeff": pls} if pls is not None else {}))
+
+
+def headline_config(n_gpus):
+    """`config` of the JSON line -- the same dict for both arms (the driver compares them key by key)."""
+    return {"workload": "C2 batched likelihood sweep: n=1000, d=10, CMA-ES population 512 theta candidates per GPU",
+            "n": N_C2, "d": D_C2, "population_per_gpu": P_PER_GPU, "kernel": "gaussian", "nugget": -6,
+            "candidates": "popB: log10(theta) ~ U(-0.5, 1.5) (informative region, cond up to ~9e8)",
+            "l2": "working set %.1f GB of factor tiles per step >> 126 MB L2 (inputs larger than L2)" % (P_PER_GPU * 36 * 131072 / 1e9),
+            "parallelism": "dp%d (candidates sharded per GPU, NCCL all-gather of NLL)" % n_gpus}
+
+
 # ------------------------------------------------------------------ algorithmic work
 def chol_panel_flops(n, P):
     """Algorithmic flops of all chol_panel_kernel launches of one likelihood pass: for tile
@@ -199,8 +218,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "likelihood_evals_per_sec", "value": val, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 batched likelihood sweep: n=1000, d=10, population 512 (bounded sample)",
-                   "n": N_C2, "d": D_C2, "population_per_gpu": P_PER_GPU, "kernel": "gaussian", "nugget": -6},
+        "config": headline_config(args.gpus),
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -340,7 +358,11 @@ def run_ours(args, rank, local_rank, world):
     e2e_val = world * P * args.steps / e2e_s
     assert np.array_equal(nll_h, nll_host)
 
-    # ---- prediction throughput (configs[2]: n=200, d=6, pred + s), device resident + e2e
+    # ---- sustained: back-to-back generations for >= args.sustain_seconds (a CMA-ES training is hundreds of them)
+    sustained = sustained_record(args, rank, local_rank, world, torch, dist, barrier, step, P)
+    # ---- strong scaling through the product API (kadal_b200.parallel / reliability / sensitivity), checked in the run
+    strong = strong_scaling(args, rank, local_rank, world, torch, dist, barrier) if not args.no_strong else None
+    # ---- prediction throughput (configs[2]: n=200, d=6, pred + s over 10^7 points per GPU), device resident + e2e
     pred = predict_bench(args, rank, local_rank, world, torch, dist, barrier)
     extra = extra_configs(args, rank, local_rank, world, torch, dist, barrier) if not args.no_extra else None
 
@@ -391,11 +413,7 @@ def run_ours(args, rank, local_rank, world):
         "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 batched likelihood sweep: n=1000, d=10, CMA-ES population 512 theta candidates per GPU",
-                   "n": N_C2, "d": D_C2, "population_per_gpu": P, "kernel": "gaussian", "nugget": -6,
-                   "candidates": "popB: log10(theta) ~ U(-0.5, 1.5) (informative region, cond up to ~7e8)",
-                   "l2": "working set %.1f GB of factor tiles per step >> 126 MB L2 (inputs larger than L2)" % (P * 36 * 131072 / 1e9),
-                   "parallelism": "dp%d (candidates sharded per GPU, NCCL all-gather of NLL)" % world},
+        "config": headline_config(world),
         "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": world * P * nb * 8,
                 "d2h_bytes_per_step": world * P * 12},
         "gpu_launches": launches,
@@ -417,6 +435,8 @@ def run_ours(args, rank, local_rank, world):
                                   "note": "factor tiles written once by assembly, read+written once by the factorisation "
                                           "(compulsory traffic); not the binding roof (AI >> 6 flop/B)"}},
         "kernel_ms": kernel_ms,
+        "sustained": sustained,
+        "strong_scaling": strong,
         "predict": pred,
         "other_configs": extra,
     }
@@ -425,6 +445,149 @@ def run_ours(args, rank, local_rank, world):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sustained_record(args, rank, local_rank, world, torch, dist, barrier, step, P):
+    """The headline step repeated back to back for >= --sustain-seconds with the clock sampler running: the number a
+    training of hundreds of generations sees (this pool's B200s drop from 1965 MHz under seconds-long load,
+    MEASURED_PEAKS.json)."""
+    if args.sustain_seconds <= 0:
+        return None
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_done, block = 0, 50
+    t0 = time.perf_counter()
+    ev0.record()
+    while True:
+        for _ in range(block):
+            step()
+        n_done += block
+        torch.cuda.current_stream().synchronize()
+        go = torch.tensor([1.0 if time.perf_counter() - t0 < args.sustain_seconds else 0.0], device="cuda:%d" % local_rank)
+        if world > 1:
+            dist.all_reduce(go, op=dist.ReduceOp.MIN)      # every rank runs the same number of blocks
+        if go.item() == 0.0:
+            break
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": world * P * n_done / (ms * 1e-3), "unit": "evals/s", "steps": n_done, "seconds": ms * 1e-3,
+            "ms_per_step": ms / n_done, "clocks": clocks,
+            "note": "same step as the headline, %d generations back to back (includes one host sync per %d steps)" % (n_done, block)}
+
+
+def strong_scaling(args, rank, local_rank, world, torch, dist, barrier):
+    """Fixed total work split over the ranks THROUGH THE PRODUCT API, with the results checked inside the run:
+      * likelihood: ONE 512-candidate population (C2, popB) via kadal_b200.parallel.likelihood_batch_sharded
+        (host arrays in, full nll / info vectors out on every rank: device-side gather, H2D / D2H inside the timing);
+        asserted bit-equal to this rank evaluating the whole population alone, arg-min identical;
+      * prediction: ONE 10^7-point Monte-Carlo population (C3) resident in HBM as row shards, one AK-MCS iteration via
+        kadal_b200.reliability.akmcs_reductions(group=...) (scalars all-reduced); asserted equal to rank 0 reducing the
+        whole population alone;
+      * C4: the 2e7 Saltelli predictions of one Sobol analysis (N = 909 091, d = 20, A, B, 20 x C_i) via
+        kadal_b200.sensitivity.sobol_sums_generated(group=...): rows sharded, drawn on the device, sums all-reduced."""
+    import kadal_b200 as kb
+    from kadal_b200 import parallel, reliability, sensitivity
+    dev = torch.device("cuda", local_rank)
+    group = dist.group.WORLD if world > 1 else None
+    out = {"n_gpus": world, "scaling": "strong"}
+
+    def wall(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        barrier()
+        dt = (time.perf_counter() - t0) / reps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    # ---- likelihood
+    X, y, popB = c2_data()
+    info = krig_info(X, y)
+    res = {}
+    dt = wall(lambda: res.update(v=parallel.likelihood_batch_sharded(popB, info, False, group=group)), max(3, min(args.steps, 10)), warm=2)
+    nll, inf = res["v"]
+    ref_nll, ref_inf = kb.likelihood_batch(popB, info, False)           # this rank alone, whole population
+    assert np.array_equal(nll, ref_nll) and np.array_equal(inf, ref_inf), "sharded likelihood differs from the single-GPU result"
+    i, v = parallel.argmin_sharded(popB, info, False, group=group)
+    assert i == int(np.argmin(ref_nll)) and v == ref_nll[i]
+    out["likelihood"] = {"workload": "C2: ONE population of 512 candidates (popB) split over %d GPU(s), n=1000, d=10" % world,
+                         "api": "kadal_b200.parallel.likelihood_batch_sharded (host arrays in / out, device-side gather)",
+                         "value": len(popB) / dt, "unit": "evals/s", "ms_per_generation": dt * 1e3,
+                         "candidates_per_gpu": len(popB) // world, "argmin": i,
+                         "checked": "bit-equal to one GPU evaluating all 512 candidates; arg-min identical"}
+    # ---- prediction (AK-MCS iteration over a resident population)
+    X3, y3, th3 = c3_data()
+    info3 = krig_info(X3, y3 - 3.6)                                      # the limit state G = 0 cuts through the population
+    kb.likelihood(th3.copy(), info3, "all", False)
+    ntot = int(args.predict_points)
+    lo, hi = parallel.shard_bounds(ntot, world, rank)
+    # the whole population is a pure function of the row index, so every rank can make its shard (and rank 0 the rest)
+    def rows(a, b):
+        g = torch.Generator(device=dev)
+        blocks = []
+        B = 1 << 20
+        for b0 in range(a - a % B, b, B):
+            g.manual_seed(77 + b0 // B)
+            t = (torch.randn(B, 6, generator=g, device=dev, dtype=torch.float64) * 0.5).clamp_(-1, 1)
+            blocks.append(t[max(a - b0, 0):min(b - b0, B)])
+        return torch.cat(blocks).contiguous()
+    shard = rows(lo, hi)
+    torch.cuda.synchronize()
+    r = {}
+    dt = wall(lambda: r.update(v=reliability.akmcs_reductions(shard, info3, group=group)), 3, warm=1)
+    got = r["v"]
+    # single-rank reference of the same reduction: rank 0 alone over the whole population (no group)
+    if rank == 0:
+        full = rows(0, ntot) if world > 1 else shard
+        torch.cuda.synchronize()
+        from kadal_b200.model import model_for
+        from kadal_b200.prediction import _norm_args
+        m3 = model_for(info3)
+        nt_, na_, nb_ = _norm_args(info3)
+        mu, arg, cnt = m3.akmcs_reduce_dev(full.data_ptr(), ntot, nt_, na_, nb_)
+        assert got["minUloc"] == arg and got["minU"] == mu and [got["nGless"], got["n_minus"], got["n_plus"]] == cnt, \
+            "sharded AK-MCS reduction differs from the single-GPU result"
+        del full
+    out["akmcs_iteration"] = {"workload": "C3: ONE Monte-Carlo population of %d points (n=200, d=6) resident in HBM as row shards over %d GPU(s)" % (ntot, world),
+                              "api": "kadal_b200.reliability.akmcs_reductions(resident population, group): pred + s + U-function reductions, scalars all-reduced",
+                              "value": ntot / dt, "unit": "pts/s", "ms_per_iteration": dt * 1e3, "Pf": got["Pf"], "minUloc": got["minUloc"],
+                              "checked": "minU, arg-min index and the three counts equal to one GPU reducing the whole population"}
+    # ---- C4 Sobol analysis, rows drawn on the device
+    rng = np.random.default_rng(7)
+    X4 = rng.uniform(-1, 1, (800, 20))
+    y4 = (np.sin(X4[:, :3].sum(1)) + 0.05 * rng.standard_normal(800))[:, None] + 3.0
+    info4 = krig_info(X4, y4)
+    kb.likelihood(np.full(20, 0.4), info4, "all", False)
+    N4, sets = 909_091, [(i,) for i in range(20)]
+    lo2, hi2 = -np.ones(40), np.ones(40)
+    r4 = {}
+    dt = wall(lambda: r4.update(v=sensitivity.sobol_sums_generated(N4, info4, sets, lo2, hi2, group=group)), 2, warm=1)
+    if r4["v"] is not None:
+        base, yayc, ybyc = r4["v"]
+        fo2 = (base[0] / N4) ** 2
+        den = base[1] / N4 - fo2
+        s1 = (yayc / N4 - fo2) / den
+        out["sobol_analysis"] = {"workload": "C4: Sobol indices via Kriging surrogate, n=800, d=20, N=909091 base rows -> 22 x N = %.2e Saltelli predictions split over %d GPU(s)" % (22 * N4, world),
+                                 "api": "kadal_b200.sensitivity.sobol_sums_generated(group): A, B drawn on the device (bit-identical to the host Sobol plan), C_i composed on the device, sums all-reduced",
+                                 "value": 22 * N4 / dt, "unit": "pts/s", "ms_per_analysis": dt * 1e3,
+                                 "pcie_bytes_per_analysis": 40 * 30 * 8 + 80 * 8 + 20 * 20 + 44 * 8,
+                                 "first_order_indices_x1_x2_x3": [float(v) for v in s1[:3]], "max_abs_first_order_x4_x20": float(np.abs(s1[3:]).max())}
+    return out
 
 
 def predict_bench(args, rank, local_rank, world, torch, dist, barrier):
@@ -483,12 +646,75 @@ def predict_bench(args, rank, local_rank, world, torch, dist, barrier):
     assert np.allclose(out["pred"], o_pred.cpu().numpy(), rtol=0, atol=0)
     pts = world * npts * steps / (ms * 1e-3)
     fl = predict_flops_per_point(n, d, True)
-    return {"metric": "predicted_points_per_sec", "value": pts, "unit": "pts/s", "e2e_value": world * npts / e2e_s,
-            "config": {"workload": "C3 AK-MCS: n=200, d=6, pred + s over %d Monte-Carlo points per GPU" % npts},
-            "ms_per_step": ms / steps, "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
-            "fp64_tflops_algorithmic": pts * fl / 1e12,
-            "hbm_gbs_algorithmic": pts * (8 * d + 16) / 1e9,
-            "h2d_bytes_per_step": world * npts * d * 8, "d2h_bytes_per_step": world * npts * 16}
+    rec = {"metric": "predicted_points_per_sec", "value": pts, "unit": "pts/s", "n_gpus": world, "scaling": "weak",
+           "e2e": {"value": world * npts / e2e_s, "unit": "pts/s", "h2d_bytes_per_step": world * npts * d * 8,
+                   "d2h_bytes_per_step": world * npts * 16,
+                   "note": "kb200_predict with pinned host points in and pinned host results out, copies inside the timing"},
+           "e2e_value": world * npts / e2e_s,
+           "config": {"workload": "C3 AK-MCS: n=200, d=6, pred + s over %d Monte-Carlo points per GPU" % npts,
+                      "n": n, "d": d, "points_per_gpu": npts, "outputs": "pred + s",
+                      "l2": "%.0f MB of points + %.0f MB of results per step >> 126 MB L2" % (npts * d * 8 / 1e6, npts * 16 / 1e6)},
+           "steps": steps, "ms_per_step": ms / steps, "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+           "fp64_tflops_algorithmic": pts * fl / 1e12 / world,
+           "hbm_gbs_algorithmic": pts * (8 * d + 16) / 1e9 / world,
+           "h2d_bytes_per_step": world * npts * d * 8, "d2h_bytes_per_step": world * npts * 16}
+    if rank == 0:
+        from kadal_b200.model import fp64_probe
+        dmma_tf, _ = fp64_probe(local_rank)
+        peaks = measured_peaks()
+        k_ms, k_cnt = prof["pred_solve"]
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("predict_small")
+        except Exception:
+            pass
+        if k_cnt:
+            tf = fl * npts * steps / (k_ms * 1e-3) / 1e12
+            rec["roofline"] = {"bound": "tensor", "kernel": "predict_small_kernel (fused standardise + psi + mean + DMMA TRSM variance + epilogue, n <= 256)",
+                               "achieved": tf, "peak": dmma_tf, "unit": "TFLOP/s", "frac": tf / dmma_tf, "traffic": traffic,
+                               "launches": k_cnt, "avg_launch_ms": k_ms / k_cnt,
+                               "flops_per_point": fl, "points_per_launch": npts,
+                               "peak_source": "kb200_fp64_probe (DMMA, this run)",
+                               "hbm_view": {"achieved": npts * steps * (8 * d + 16) / (k_ms * 1e-3) / 1e9,
+                                            "peak": peaks["hbm_gbs"] if peaks else 6650.0, "unit": "GB/s",
+                                            "note": "algorithmic bytes 8 d + 16 per point; arithmetic intensity %.0f flop/B against a machine "
+                                                    "balance of ~5.7: the FP64 pipe binds, not HBM (SURVEY.md section 8d)" % (fl / (8 * d + 16))}}
+        if world == 1 and not args.no_cpu_baseline:
+            rec["cpu_baseline"] = cpu_baseline_predict()
+    return rec
+
+
+def cpu_baseline_predict(budget_s=8.0):
+    """The reference's prediction() (oracle port) on this box's host cores: C3 model, ['pred', 's'] on 10 000-point chunks
+    as AKMCS.run issues them (akmcs.py:95-106), and the C4 model, 'pred' on 10 000-point chunks (sobol_ind.py:48-58)."""
+    all_host_threads()
+    from oracle import kriging_oracle as ko
+    out = {"unit": "pts/s", "cores": os.cpu_count(), "kind": "port"}
+    X, y, th = c3_data()
+    info = ko.make_kriginfo(X, y)
+    ko.likelihood(th.copy(), info, "all", False, check_pd=False)
+    rng = np.random.default_rng(2)
+    chunk = np.clip(rng.standard_normal((10_000, 6)) * 0.5, -1, 1)
+    ko.prediction(chunk, info, ["pred", "s"])
+    t0, k = time.perf_counter(), 0
+    while k < 10 and time.perf_counter() - t0 < budget_s * 0.5:
+        ko.prediction(chunk, info, ["pred", "s"])
+        k += 1
+    out["value"] = k * 10_000 / (time.perf_counter() - t0)
+    out["sample"] = "%d chunks of 10 000 points, oracle.prediction(chunk, ['pred', 's']) on the C3 model (n=200, d=6)" % k
+    rng = np.random.default_rng(7)
+    X4 = rng.uniform(-1, 1, (800, 20))
+    y4 = (np.sin(X4[:, :3].sum(1)) + 0.05 * rng.standard_normal(800))[:, None] + 3.0
+    info4 = ko.make_kriginfo(X4, y4)
+    ko.likelihood(np.full(20, 0.4), info4, "all", False, check_pd=False)
+    chunk4 = rng.uniform(-1, 1, (10_000, 20))
+    t0, k = time.perf_counter(), 0
+    while k < 3 and time.perf_counter() - t0 < budget_s * 0.5:
+        ko.prediction(chunk4, info4, ["pred"])
+        k += 1
+    out["c4_value"] = k * 10_000 / (time.perf_counter() - t0)
+    out["c4_sample"] = "%d chunks of 10 000 points, oracle.prediction(chunk, ['pred']) on the C4 model (n=800, d=20)" % k
+    return out
 
 
 def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
@@ -635,7 +861,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--predict-points", type=float, default=4e6)
+    ap.add_argument("--predict-points", type=float, default=1e7, help="C3 Monte-Carlo points per GPU (BASELINE configs[2]: 10^7)")
+    ap.add_argument("--sustain-seconds", type=float, default=5.0, help="length of the sustained-throughput record (0: skip)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling records")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 sub-benchmarks")
     args = ap.parse_args()

@@ -12,7 +12,15 @@
  *   - numerical failure is reported per item in info[] (0 ok, k>0 = first non-positive
  *     pivot at row k-1), never as a crash;
  *   - `*_dev` variants take device pointers and a cudaStream_t (as void*) and do no
- *     host<->device copies; the plain variants take host pointers.
+ *     host<->device copies; the plain variants take host pointers and block.
+ *   - stream ordering of the `*_dev` variants: with a non-NULL stream the call is asynchronous and
+ *     ordered on that stream (inputs must be ready on it, outputs are ready on it).  With stream ==
+ *     NULL the work runs on the model's own stream and the call BLOCKS until the outputs are complete.
+ *   - a model supports ONE call in flight: its scratch buffers (decoded candidates, prediction slots,
+ *     workspaces) are shared by every entry point.  The library enforces this itself -- each call first
+ *     makes its stream wait for the last work of the previous call on the same model, whatever stream
+ *     that ran on -- so calls on different streams are serialised, never concurrent.  Use one model per
+ *     stream for concurrency.  A model must not be used from two host threads at once.
  *   - there is no CPU fallback: without a CUDA device every call fails.
  */
 #ifndef KB200_H
@@ -126,6 +134,14 @@ int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int nor
                        const double* norm_a, const double* norm_b, double* min_u,
                        long long* argmin_u, unsigned long long* counts);
 
+/* The same with the population already in HBM (d_x: [npred][d] device doubles): an AK-MCS run predicts the SAME
+ * Monte-Carlo population after every added sample (akmcs.py:95-106, 144-155), so the caller uploads it once and every
+ * iteration is this call -- no 8 d npred bytes over PCIe per iteration.  Runs on `stream` (NULL: the model's own),
+ * returns the scalars on the host (blocking). */
+int kb200_akmcs_reduce_dev(kb200_model* m, const double* d_x, long long npred, int normtype,
+                           const double* norm_a, const double* norm_b, double* min_u,
+                           long long* argmin_u, unsigned long long* counts, void* stream);
+
 /* Saltelli sums for Sobol indices without shipping predictions back
  * (sensitivity_analysis/sobol_ind.py:45-141): A, B are the two [N][d] sample matrices (host), set q
  * builds C_q = B with the columns k where from_a[q*d + k] != 0 taken from A (one column: first /
@@ -136,6 +152,25 @@ int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int nor
 int kb200_sobol_sums(kb200_model* m, const double* A, const double* B, long long N, int normtype,
                      const double* norm_a, const double* norm_b, const unsigned char* from_a, int nsets,
                      double* base, double* ya_yc, double* yb_yc);
+
+/* The same with A, B already in HBM ([N][d] device doubles each); runs on `stream` (NULL: the model's own), the sums
+ * come back to the host (blocking). */
+int kb200_sobol_sums_dev(kb200_model* m, const double* d_A, const double* d_B, long long N, int normtype,
+                         const double* norm_a, const double* norm_b, const unsigned char* from_a, int nsets,
+                         double* base, double* ya_yc, double* yb_yc, void* stream);
+/* The same with A, B GENERATED on the device as the reference draws them (sensitivity_analysis/sobol_ind.py:24-29 via
+ * misc/sampling/samplingplan.py:13-35): one unscrambled Sobol plan of 2 d columns, A = columns 0..d-1, B = columns
+ * d..2d-1, rows i0 .. i0+N-1 of the sequence (the reference drops the all-zero row 0: i0 = 1; a rank that owns rows
+ * [r0, r1) of the plan passes i0 = 1 + r0), scaled to [lo, hi] (2 d doubles each, realval :37-51; NULL: unit cube).
+ * dirnum: [2 d][bits] direction numbers v_k,b of the host generator the caller would otherwise use (e.g. scipy's
+ * qmc.Sobol(2 d, scramble=False)._sv), point i = xor of v_k,b over the set bits b of i ^ (i >> 1), times 2^-bits:
+ * bit-identical to that generator, order-free.  Nothing but the sums crosses PCIe. */
+int kb200_sobol_sums_gen(kb200_model* m, const unsigned long long* dirnum, int bits, long long i0, long long N,
+                         const double* lo, const double* hi, int normtype, const double* norm_a, const double* norm_b,
+                         const unsigned char* from_a, int nsets, double* base, double* ya_yc, double* yb_yc);
+/* The generator alone: d_out [N][dims] device doubles = rows i0 .. i0+N-1 of the same sequence.  No model handle. */
+int kb200_sobol_points_dev(int device, const unsigned long long* dirnum, int bits, int dims, long long i0, long long N,
+                           const double* lo, const double* hi, double* d_out, void* stream);
 
 /* 2-objective expected hyper-volume improvement of npop candidates over a Pareto front
  * (optim_tools/ehvi/exi2d.py:7-84 as called by EHVIcomputation.py:57 and :169-175): pareto is
@@ -212,6 +247,13 @@ int kb200_profile_get(kb200_model* m, double* ms, unsigned long long* counts, in
  * every group runs its launch sequence on its own stream so that launch tails overlap.  With 1
  * all kernels are serialised on the caller's stream (what the per-kernel profile wants). */
 int kb200_set_groups(kb200_model* m, int ngroups);
+
+/* The factorisation has two schedules (left-looking for populations that fill the machine, right-looking for a few
+ * matrices) that round differently (~1e-10 relative); which one runs is decided by the number of candidates of the
+ * call.  A rank that evaluates a SHARD of a population passes the size of the whole population here, so that every
+ * candidate gets the same bits -- and the population the same arg-min -- as in a single-GPU call on all of it.
+ * 0 (default): decide from the call's own P. */
+int kb200_set_schedule_population(kb200_model* m, long long population);
 
 /* Empirical FP64 roof of the device: register-resident DMMA (mode 0) or DFMA (mode 1)
  * loops, best of 5, in TFLOP/s. */

@@ -57,9 +57,19 @@ SIGNATURES = {
     "kb200_profile_get": (ctypes.c_int, [c_void_p, c_double_p, c_u64_p, ctypes.c_int]),
     "kb200_fp64_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_double_p]),
     "kb200_set_groups": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "kb200_set_schedule_population": (ctypes.c_int, [c_void_p, ctypes.c_longlong]),
     "kb200_loocv": (ctypes.c_int, [c_void_p, c_void_p]),
     "kb200_akmcs_reduce": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
                                           c_double_p, ctypes.POINTER(ctypes.c_longlong), c_u64_p]),
+    "kb200_akmcs_reduce_dev": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
+                                              c_double_p, ctypes.POINTER(ctypes.c_longlong), c_u64_p, c_void_p]),
+    "kb200_sobol_sums_dev": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
+                                            c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kb200_sobol_sums_gen": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong,
+                                            c_void_p, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p, ctypes.c_int,
+                                            c_void_p, c_void_p, c_void_p]),
+    "kb200_sobol_points_dev": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_longlong,
+                                              ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kb200_sobol_sums": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
                                         c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p]),
     "kb200_ehvi2d": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p,

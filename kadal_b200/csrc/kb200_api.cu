@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <mutex>
 #include <thread>
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges show up in nsys / ncu --nvtx, no library to link
 #include "../../include/kb200.h"
 #include "kb200_kernels.h"
 
@@ -30,6 +31,12 @@ static int fail_arg(const std::string& msg) {
     cudaError_t e__ = (call);                      \
     if (e__ != cudaSuccess) return fail(#call, e__); \
   } while (0)
+
+// NVTX range around a host-side phase (assemble / factorise / predict ...): `ncu --nvtx --nvtx-include "kb200_factorize/"`
+struct Nvtx {
+  explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+  ~Nvtx() { nvtxRangePop(); }
+};
 
 // Device allocations are recycled through a small process-wide pool: the sequential flows of KADAL (Kriging believer,
 // AK-MCS, SOBO) build a new model of n + 1 samples for every update, and ~25 cudaMalloc / cudaFree pairs per model cost
@@ -149,6 +156,7 @@ struct kb200_model {
   DevBuf Rw;
   bool rl_lookahead = true;
   int rl_mode = -1;          // right-looking factorisation for large matrices: -1 auto (nt > 16), 0 off, 1 on
+  long sched_pop = 0;        // > 0: choose the schedule as for a population of this size (kb200_set_schedule_population)
   DevBuf tiles, W, Z, cand, xdev, nll, info, logdet, sigma2, beta, btb, resid, rhs2, sol2;
   // predictor state
   bool has_pred = false;
@@ -180,9 +188,15 @@ struct kb200_model {
   cudaEvent_t ev_fork = nullptr, ev_join[MAXG] = {nullptr};
   int group_min = 32;   // fewest candidates per group
   DevBuf norm_a, norm_b, stats, akpart;
-  DevBuf sobB, sobC, sobY, sobAcc, sobPart, sobMask;
+  DevBuf sobB, sobC, sobY, sobAcc, sobPart, sobMask, sobDir;
   unsigned long long launches = 0;
   size_t ws_cap_bytes = 0;
+  // One call in flight per model: every entry point that touches the shared scratch (cand, stats, norm vectors,
+  // prediction slots, workspaces) first makes its stream wait for the previous call's last work (ev_last, recorded
+  // on last_stream) -- calls issued on different streams are serialised by the library, never concurrent.
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_pending = false;
   // optional per-kernel-class event timing (kb200_profile_*)
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int cls; };
@@ -208,6 +222,19 @@ struct Timed {
     if (b) cudaEventRecord(b, st);
   }
 };
+
+// stream ordering between successive calls on one model (see kb200_model::ev_last)
+static cudaError_t call_enter(kb200_model* m, cudaStream_t st) {
+  if (m->last_pending && m->last_stream != st) return cudaStreamWaitEvent(st, m->ev_last, 0);
+  return cudaSuccess;
+}
+static cudaError_t call_leave(kb200_model* m, cudaStream_t st) {   // asynchronous return: work may still be running on st
+  cudaError_t e = cudaEventRecord(m->ev_last, st);
+  m->last_stream = st;
+  m->last_pending = true;
+  return e;
+}
+static void call_idle(kb200_model* m) { m->last_pending = false; }  // the call synchronised everything it launched
 
 static CorrSpec make_spec(const kb200_model* m) {
   CorrSpec sp;
@@ -289,6 +316,7 @@ int kb200_model_create(kb200_model** out, int device, int n, int d, int p, int h
   } while (0)
   MCK(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
   MCK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  MCK(cudaEventCreateWithFlags(&m->ev_last, cudaEventDisableTiming));
   for (int s = 0; s < 2; ++s) MCK(cudaStreamCreateWithFlags(&m->slot[s].stream, cudaStreamNonBlocking));
   {
     const char* eg = getenv("KB200_GROUPS");
@@ -370,7 +398,7 @@ void kb200_model_destroy(kb200_model* m) {
                     &m->nll, &m->info, &m->logdet, &m->sigma2, &m->beta, &m->btb, &m->resid,
                     &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand, &m->pZ, &m->plogdet, &m->appdiag, &m->appvec, &m->trwork,
                     &m->norm_a, &m->norm_b, &m->stats, &m->akpart,
-                    &m->Rw, &m->sobB, &m->sobC, &m->sobY, &m->sobAcc, &m->sobPart, &m->sobMask};
+                    &m->Rw, &m->sobB, &m->sobC, &m->sobY, &m->sobAcc, &m->sobPart, &m->sobMask, &m->sobDir};
   cudaDeviceSynchronize();   // nothing of this model is in flight when its buffers go back to the pool
   for (DevBuf* b : bufs) b->release(true);
   for (int s = 0; s < 2; ++s) {
@@ -391,6 +419,7 @@ void kb200_model_destroy(kb200_model* m) {
     if (m->ev_join[g]) cudaEventDestroy(m->ev_join[g]);
   }
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_last) cudaEventDestroy(m->ev_last);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -491,6 +520,7 @@ static int kpls_planes_build(kb200_model* m, cudaStream_t st) {
 
 // assemble + factorise Pb candidates whose parameter rows start at d_cand
 static int assemble(kb200_model* m, const double* d_cand, int Pb, double* tiles, int add_eps, cudaStream_t st) {
+  Nvtx range("kb200_assemble");
   if (kpls_planes_usable(m)) {
     int rc = kpls_planes_build(m, st);
     if (rc) return rc;
@@ -521,6 +551,7 @@ static int assemble(kb200_model* m, const double* d_cand, int Pb, double* tiles,
 
 static int factorize(kb200_model* m, int Pb, double* tiles, double* W, double* Z, double* logdet,
                      int* info, cudaStream_t st, int g = 0, long Ptotal = 1) {
+  Nvtx range("kb200_factorize");
   CholArgs a = chol_args(m, tiles, W, Z, logdet, info);
   a.fuse_diag = a.naive ? 0 : 1;
   // Two schedules on the half-SM kernels (kb200_half.cu, two CTAs per SM), chosen by the amount of parallel
@@ -714,8 +745,12 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
                         double nugget_log10, double* d_nll, int* d_info, void* stream) {
   if (!m || !d_x || !d_nll || !d_info) return fail_arg("kb200_lik_batch_dev: null argument");
   if (P < 1) return 0;
+  Nvtx range("kb200_lik_batch");
   CK(cudaSetDevice(m->device));
+  // stream == NULL: the model's own stream, and the call blocks until the results are complete (a caller that passes
+  // no stream has nothing to order later work against); otherwise asynchronous on the caller's stream.
   cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  CK(call_enter(m, st));
   int Pb = (int)std::min<size_t>((size_t)P, std::max<size_t>(1, m->ws_cap_bytes / per_matrix_bytes(m)));
   Pb = std::min(Pb, 32768);
   int rc = reserve_lik(m, P, Pb);
@@ -742,7 +777,7 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
       rc = assemble(m, cand, pg, tiles, 1, sg);
       if (rc) return rc;
       if (G > 1 && m->stagger) CK(cudaEventRecord(m->ev_asm[g], sg));
-      rc = factorize(m, pg, tiles, W8, Z, logdet, d_info + p0 + o0, sg, g, P);
+      rc = factorize(m, pg, tiles, W8, Z, logdet, d_info + p0 + o0, sg, g, m->sched_pop > 0 ? m->sched_pop : (long)P);
       if (rc) return rc;
       FinArgs f;
       memset(&f, 0, sizeof(f));
@@ -761,6 +796,12 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
       }
     }
   }
+  if (!stream) {
+    CK(cudaStreamSynchronize(st));
+    call_idle(m);
+  } else {
+    CK(call_leave(m, st));
+  }
   return 0;
 }
 
@@ -769,6 +810,7 @@ int kb200_lik_batch(kb200_model* m, const double* x, int P, int nbhyp, int train
   if (!m || !x || !nll || !info) return fail_arg("kb200_lik_batch: null argument");
   if (P < 1) return 0;
   CK(cudaSetDevice(m->device));
+  CK(call_enter(m, m->stream));
   CK(m->xdev.reserve((size_t)P * nbhyp * 8));
   CK(m->nll.reserve((size_t)P * 8));
   CK(m->info.reserve((size_t)P * 4));
@@ -779,6 +821,7 @@ int kb200_lik_batch(kb200_model* m, const double* x, int P, int nbhyp, int train
   CK(cudaMemcpyAsync(nll, m->nll.p, (size_t)P * 8, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaMemcpyAsync(info, m->info.p, (size_t)P * 4, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
+  call_idle(m);
   return 0;
 }
 
@@ -787,6 +830,7 @@ int kb200_debug_psi(kb200_model* m, const double* x, int nbhyp, int trainvar,
   if (!m || !x || !Psi) return fail_arg("kb200_debug_psi: null argument");
   CK(cudaSetDevice(m->device));
   cudaStream_t st = m->stream;
+  CK(call_enter(m, st));
   int rc = reserve_lik(m, 1, 1);
   if (rc) return rc;
   CK(m->xdev.reserve((size_t)nbhyp * 8));
@@ -817,7 +861,8 @@ static int install_predictor(kb200_model* m, const double* tiles, const double* 
   CK(m->pw.reserve((size_t)m->npad * 8));
   if (tiles != m->pL.d()) CK(cudaMemcpyAsync(m->pL.p, tiles, tb, cudaMemcpyDeviceToDevice, st));
   if (W != m->pW.d()) CK(cudaMemcpyAsync(m->pW.p, W, wb, cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpyAsync(m->pcand.p, d_cand_row, (size_t)m->cstride * 8, cudaMemcpyDeviceToDevice, st));
+  if (d_cand_row != m->pcand.d())
+    CK(cudaMemcpyAsync(m->pcand.p, d_cand_row, (size_t)m->cstride * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(m->rhs2.d(), d_resid, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(m->rhs2.d() + m->npad, d_b, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   BackArgs b;
@@ -868,8 +913,11 @@ static int fit_state_impl(kb200_model* m, kb200_model* prev, const double* x, in
                           double* nll, int* info, double* theta_log10, double* nugget_out,
                           double* wgkf) {
   if (!m || !x) return fail_arg("kb200_fit_state: null argument");
+  Nvtx range(prev ? "kb200_fit_append" : "kb200_fit_state");
   CK(cudaSetDevice(m->device));
   cudaStream_t st = m->stream;
+  CK(call_enter(m, st));
+  if (prev && prev != m) CK(call_enter(prev, st));   // the append reads prev's factor
   int rc = reserve_lik(m, 1, 1);
   if (rc) return rc;
   CK(m->xdev.reserve((size_t)nbhyp * 8));
@@ -993,6 +1041,7 @@ int kb200_predictor_load(kb200_model* m, const double* theta_log10, const double
     return fail_arg("prediction with TrendOrder >= 1 is broken in the reference (prediction.py:250) and not supported");
   CK(cudaSetDevice(m->device));
   cudaStream_t st = m->stream;
+  CK(call_enter(m, st));
   const size_t nn = (size_t)m->n * m->n * 8;
   CK(m->sol2.reserve(std::max(nn, (size_t)2 * m->npad * 8)));
   CK(m->pL.reserve((size_t)m->tiles_per_mat * TILE_ELEMS * 8));
@@ -1075,7 +1124,7 @@ struct HostStager {
   std::mutex mu;
   bool init(int device) {
     if (failed) return false;
-    if (buf[0]) return dev == device;        // one ring per process (events belong to its device)
+    if (buf[0]) return true;
     const char* e = getenv("KB200_STAGE_THREADS");
     if (e) threads = atoi(e);
     if (threads <= 0) { failed = true; return false; }
@@ -1097,7 +1146,8 @@ struct HostStager {
     return true;
   }
 };
-static HostStager g_stager;
+// one ring per device, created on first use (the events and the pinned slots belong to that device's context)
+static HostStager g_stagers[16];
 
 static void parallel_memcpy(char* dst, const char* src, size_t bytes, int threads) {
   threads = (int)std::min<size_t>((size_t)threads, bytes >> 21);   // at least 2 MiB per thread
@@ -1133,7 +1183,8 @@ static cudaError_t h2d_bulk(void* dst, const void* src, size_t bytes, int device
       staged = false;                         // already pinned (or managed): the DMA engine reads it directly
     }
   }
-  if (!staged) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  if (!staged || device < 0 || device >= 16) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  HostStager& g_stager = g_stagers[device];
   std::lock_guard<std::mutex> g(g_stager.mu);
   if (!g_stager.init(device)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
   for (size_t off = 0; off < bytes; off += HostStager::SLOT) {
@@ -1169,6 +1220,7 @@ static long chunk_tiles_for(const kb200_model* m) {
 static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long npts, int normtype,
                         unsigned want, double ymin, double limit, int limit_ge, double* outs[7],
                         cudaStream_t st) {
+  Nvtx range("kb200_predict_core");
   const bool need_var = (want & ~KB200_OUT_PRED) != 0;
   CK(sl.fdot.reserve((size_t)npts * 8));
   CorrArgs c;
@@ -1273,6 +1325,7 @@ extern "C" int kb200_loocv(kb200_model* m, double* loo) {
   if (!m->has_pred) return fail_arg("kb200_loocv: no fit installed (call kb200_fit_state or kb200_predictor_load)");
   CK(cudaSetDevice(m->device));
   cudaStream_t st = m->stream;
+  CK(call_enter(m, st));
   PredSlot& sl = m->slot[0];
   const long ct = std::min<long>(chunk_tiles_for(m), m->nt);
   const long cpts = ct * TB;
@@ -1330,7 +1383,9 @@ int kb200_predict_dev(kb200_model* m, const double* d_x, long long npred, int no
   if (!m || !d_x) return fail_arg("kb200_predict_dev: null argument");
   if (npred < 1) return 0;
   CK(cudaSetDevice(m->device));
+  // stream == NULL: the model's own stream and a blocking call (see kb200_lik_batch_dev)
   cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+  CK(call_enter(m, st));
   double* outs[7] = {d_pred, d_ssqr, d_s, d_ei, d_poi, d_pof, d_ufun};
   int rc = predict_prepare(m, normtype, norm_a, norm_b, want, outs, st);
   if (rc) return rc;
@@ -1338,51 +1393,70 @@ int kb200_predict_dev(kb200_model* m, const double* d_x, long long npred, int no
     if (!((want >> i) & 1u)) outs[i] = nullptr;
   rc = predict_core(m, m->slot[0], d_x, (long)npred, normtype, want, ymin, limit, limit_ge, outs, st);
   if (rc) return rc;
-  if (stats) {
-    CK(cudaMemcpyAsync(stats, m->stats.p, 16, cudaMemcpyDeviceToHost, st));
+  if (stats) CK(cudaMemcpyAsync(stats, m->stats.p, 16, cudaMemcpyDeviceToHost, st));
+  if (stats || !stream) {
     CK(cudaStreamSynchronize(st));
+    call_idle(m);
+  } else {
+    CK(call_leave(m, st));
   }
   return 0;
 }
 
-int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int normtype,
-                       const double* norm_a, const double* norm_b, double* min_u,
-                       long long* argmin_u, unsigned long long* counts) {
+// x_is_device: the population is already resident in HBM (no copies, chunks run back to back on `user`, or on the
+// model's stream when user is NULL); otherwise host memory, staged chunk by chunk on the two slot streams.
+static int akmcs_core(kb200_model* m, const double* x, bool x_is_device, long long npred, int normtype,
+                      const double* norm_a, const double* norm_b, double* min_u, long long* argmin_u,
+                      unsigned long long* counts, cudaStream_t user) {
   if (!m || !x || !min_u || !argmin_u || !counts) return fail_arg("kb200_akmcs_reduce: null argument");
   if (npred < 1) return fail_arg("kb200_akmcs_reduce: empty population");
+  Nvtx range("kb200_akmcs_reduce");
   CK(cudaSetDevice(m->device));
   const unsigned want = KB200_OUT_PRED | KB200_OUT_S;
   double* dummy[7] = {(double*)1, nullptr, (double*)1, nullptr, nullptr, nullptr, nullptr};
-  int rc = predict_prepare(m, normtype, norm_a, norm_b, want, dummy, m->stream);
+  cudaStream_t base = x_is_device && user ? user : m->stream;
+  CK(call_enter(m, base));       // predict_prepare synchronises `base`: the previous call is complete after it
+  int rc = predict_prepare(m, normtype, norm_a, norm_b, want, dummy, base);
   if (rc) return rc;
   struct Part { double min_u; long long arg; unsigned long long c0, cm, cp; };
   static_assert(sizeof(Part) == AK_PARTIAL_BYTES, "AkPartial layout");
   const long ct = chunk_tiles_for(m) * TB;
-  const long sc = std::max<long>(ct, (1L << 19) / ct * ct);
+  long sc = std::max<long>(ct, (1L << 19) / ct * ct);
+  if (x_is_device) sc = std::max<long>(sc, (1L << 22) / ct * ct);   // nothing to overlap: fewer, larger launches
   const long nchunks = (npred + sc - 1) / sc;
   std::vector<Part> host((size_t)nchunks * AK_BLOCKS);
   CK(m->akpart.reserve((size_t)nchunks * AK_BLOCKS * sizeof(Part)));
   long it = 0;
   for (long p0 = 0; p0 < npred; p0 += sc, ++it) {
-    PredSlot& sl = m->slot[it & 1];
-    cudaStream_t st = sl.stream;
+    PredSlot& sl = m->slot[x_is_device ? 0 : (it & 1)];
+    cudaStream_t st = x_is_device ? base : sl.stream;
     const long np = std::min<long>(sc, npred - p0);
-    CK(sl.x.reserve((size_t)std::min<long>(sc, npred) * m->d * 8));
-    CK(h2d_bulk(sl.x.p, x + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
+    const double* xs = x + (size_t)p0 * m->d;
+    if (!x_is_device) {
+      CK(sl.x.reserve((size_t)std::min<long>(sc, npred) * m->d * 8));
+      CK(h2d_bulk(sl.x.p, xs, (size_t)np * m->d * 8, m->device, st));
+      xs = sl.x.d();
+    }
     double* outs[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     CK(sl.out[0].reserve((size_t)std::min<long>(sc, npred) * 8));
     CK(sl.out[2].reserve((size_t)std::min<long>(sc, npred) * 8));
     outs[0] = sl.out[0].d();
     outs[2] = sl.out[2].d();
-    rc = predict_core(m, sl, sl.x.d(), np, normtype, want, 0.0, 0.0, 1, outs, st);
+    rc = predict_core(m, sl, xs, np, normtype, want, 0.0, 0.0, 1, outs, st);
     if (rc) return rc;
     CK(launch_akmcs_reduce(outs[0], outs[2], np, p0, static_cast<char*>(m->akpart.p) + (size_t)it * AK_BLOCKS * sizeof(Part),
                            AK_BLOCKS, st));
     m->launches++;
   }
-  CK(cudaStreamSynchronize(m->slot[0].stream));
-  CK(cudaStreamSynchronize(m->slot[1].stream));
-  CK(cudaMemcpy(host.data(), m->akpart.p, host.size() * sizeof(Part), cudaMemcpyDeviceToHost));
+  if (x_is_device) {
+    CK(cudaMemcpyAsync(host.data(), m->akpart.p, host.size() * sizeof(Part), cudaMemcpyDeviceToHost, base));
+    CK(cudaStreamSynchronize(base));
+  } else {
+    CK(cudaStreamSynchronize(m->slot[0].stream));
+    CK(cudaStreamSynchronize(m->slot[1].stream));
+    CK(cudaMemcpy(host.data(), m->akpart.p, host.size() * sizeof(Part), cudaMemcpyDeviceToHost));
+  }
+  call_idle(m);
   double bu = INFINITY;
   long long bi = 0x7fffffffffffffffLL;
   unsigned long long c[3] = {0, 0, 0};
@@ -1401,6 +1475,18 @@ int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int nor
   return 0;
 }
 
+int kb200_akmcs_reduce(kb200_model* m, const double* x, long long npred, int normtype,
+                       const double* norm_a, const double* norm_b, double* min_u,
+                       long long* argmin_u, unsigned long long* counts) {
+  return akmcs_core(m, x, false, npred, normtype, norm_a, norm_b, min_u, argmin_u, counts, nullptr);
+}
+
+int kb200_akmcs_reduce_dev(kb200_model* m, const double* d_x, long long npred, int normtype,
+                           const double* norm_a, const double* norm_b, double* min_u,
+                           long long* argmin_u, unsigned long long* counts, void* stream) {
+  return akmcs_core(m, d_x, true, npred, normtype, norm_a, norm_b, min_u, argmin_u, counts, (cudaStream_t)stream);
+}
+
 int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype,
                   const double* norm_a, const double* norm_b, unsigned want, double ymin,
                   double limit, int limit_ge, double* pred, double* ssqr, double* s, double* ei,
@@ -1409,6 +1495,7 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
   if (npred < 1) return 0;
   CK(cudaSetDevice(m->device));
   double* houts[7] = {pred, ssqr, s, ei, poi, pof, ufun};
+  CK(call_enter(m, m->stream));       // predict_prepare synchronises m->stream: the previous call is complete after it
   int rc = predict_prepare(m, normtype, norm_a, norm_b, want, houts, m->stream);
   if (rc) return rc;
   // super-chunks alternate between two streams so that the H2D copy of chunk i+1 and the
@@ -1439,6 +1526,7 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
   CK(cudaStreamSynchronize(m->slot[0].stream));
   CK(cudaStreamSynchronize(m->slot[1].stream));
   if (stats) CK(cudaMemcpy(stats, m->stats.p, 16, cudaMemcpyDeviceToHost));
+  call_idle(m);
   return 0;
 }
 
@@ -1447,46 +1535,86 @@ int kb200_predict(kb200_model* m, const double* x, long long npred, int normtype
 extern "C" {
 
 // ------------------------------------------------- Saltelli sums
-int kb200_sobol_sums(kb200_model* m, const double* A, const double* B, long long N, int normtype,
-                     const double* norm_a, const double* norm_b, const unsigned char* from_a, int nsets,
-                     double* base, double* ya_yc, double* yb_yc) {
-  if (!m || !A || !B || !base || (nsets > 0 && (!from_a || !ya_yc || !yb_yc)))
-    return fail_arg("kb200_sobol_sums: null argument");
+// Where the two Saltelli sample matrices come from: host arrays (staged), device arrays (used in place), or the first
+// 2 d columns of the unscrambled Sobol sequence generated on the device (sobol_ind.py:24-29: A = columns 0..d-1,
+// B = columns d..2d-1 of one 2d-dimensional plan; samplingplan.py:18-19, 37-51: row 0 dropped, realval scaling).
+struct SobolSource {
+  int kind = 0;                 // 0 host, 1 device, 2 generated
+  const double *A = nullptr, *B = nullptr;
+  const unsigned long long* dirnum = nullptr;   // host [2 d][bits]
+  int bits = 0;
+  long long i0 = 0;             // sequence index of row 0 of this call
+  const double *lo = nullptr, *hi = nullptr;    // host [2 d] or null (unit cube)
+};
+
+static int sobol_core(kb200_model* m, const SobolSource& src, long long N, int normtype,
+                      const double* norm_a, const double* norm_b, const unsigned char* from_a, int nsets,
+                      double* base, double* ya_yc, double* yb_yc, cudaStream_t user) {
+  if (!m || !base || (nsets > 0 && (!from_a || !ya_yc || !yb_yc))) return fail_arg("kb200_sobol_sums: null argument");
   if (N < 1 || nsets < 0) return fail_arg("kb200_sobol_sums: empty sample");
+  Nvtx range("kb200_sobol_sums");
   CK(cudaSetDevice(m->device));
-  cudaStream_t st = m->stream;
+  cudaStream_t st = user ? user : m->stream;
   double* dummy[7] = {(double*)1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  CK(call_enter(m, st));
   int rc = predict_prepare(m, normtype, norm_a, norm_b, KB200_OUT_PRED, dummy, st);
   if (rc) return rc;
   const long sc = std::min<long>((long)N, 1L << 18);
   const size_t cb = (size_t)sc * m->d * 8;
   PredSlot& sl = m->slot[0];
-  CK(sl.x.reserve(cb));
-  CK(m->sobB.reserve(cb));
+  if (src.kind != 1) {
+    CK(sl.x.reserve(cb));
+    CK(m->sobB.reserve(cb));
+  }
   CK(m->sobC.reserve(cb));
   CK(m->sobY.reserve((size_t)3 * sc * 8));
   CK(m->sobAcc.reserve((size_t)(4 + 2 * nsets) * 8));
   CK(m->sobPart.reserve((size_t)2 * SOBOL_BLOCKS * 8));
   CK(m->sobMask.reserve((size_t)std::max(1, nsets) * m->d));
   if (nsets) CK(cudaMemcpyAsync(m->sobMask.p, from_a, (size_t)nsets * m->d, cudaMemcpyHostToDevice, st));
+  if (src.kind == 2) {
+    const int dims = 2 * m->d;
+    CK(m->sobDir.reserve((size_t)dims * src.bits * 8 + (size_t)2 * dims * 8));
+    CK(cudaMemcpyAsync(m->sobDir.p, src.dirnum, (size_t)dims * src.bits * 8, cudaMemcpyHostToDevice, st));
+    std::vector<double> lohi((size_t)2 * dims);
+    for (int k = 0; k < dims; ++k) { lohi[k] = src.lo ? src.lo[k] : 0.0; lohi[dims + k] = src.hi ? src.hi[k] : 1.0; }
+    CK(cudaMemcpyAsync(static_cast<char*>(m->sobDir.p) + (size_t)dims * src.bits * 8, lohi.data(), lohi.size() * 8,
+                       cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // lohi is a local
+  }
   CK(cudaMemsetAsync(m->sobAcc.p, 0, (size_t)(4 + 2 * nsets) * 8, st));
   double *ya = m->sobY.d(), *yb = ya + sc, *yc = yb + sc, *acc = m->sobAcc.d(), *part = m->sobPart.d();
   const unsigned char* masks = static_cast<const unsigned char*>(m->sobMask.p);
   for (long p0 = 0; p0 < N; p0 += sc) {
     const long np = std::min<long>(sc, (long)N - p0);
-    CK(h2d_bulk(sl.x.p, A + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
-    CK(h2d_bulk(m->sobB.p, B + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
+    const double *dA, *dB;
+    if (src.kind == 0) {
+      CK(h2d_bulk(sl.x.p, src.A + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
+      CK(h2d_bulk(m->sobB.p, src.B + (size_t)p0 * m->d, (size_t)np * m->d * 8, m->device, st));
+      dA = sl.x.d(); dB = m->sobB.d();
+    } else if (src.kind == 1) {
+      dA = src.A + (size_t)p0 * m->d; dB = src.B + (size_t)p0 * m->d;
+    } else {
+      const int dims = 2 * m->d;
+      const unsigned long long* dv = static_cast<const unsigned long long*>(m->sobDir.p);
+      const double* lohi = reinterpret_cast<const double*>(dv + (size_t)dims * src.bits);
+      const bool scaled = src.lo && src.hi;
+      CK(launch_sobol_points(dv, src.bits, dims, src.i0 + p0, np, scaled ? lohi : nullptr, scaled ? lohi + dims : nullptr,
+                             sl.x.d(), m->sobB.d(), m->d, st));
+      m->launches++;
+      dA = sl.x.d(); dB = m->sobB.d();
+    }
     double* outs[7] = {ya, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    rc = predict_core(m, sl, sl.x.d(), np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
+    rc = predict_core(m, sl, dA, np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
     if (rc) return rc;
     outs[0] = yb;
-    rc = predict_core(m, sl, m->sobB.d(), np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
+    rc = predict_core(m, sl, dB, np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
     if (rc) return rc;
     CK(launch_sobol_dot(ya, nullptr, nullptr, np, 1, part, acc + 0, acc + 1, st));
     CK(launch_sobol_dot(yb, nullptr, nullptr, np, 1, part, acc + 2, acc + 3, st));
     m->launches += 4;
     for (int q = 0; q < nsets; ++q) {
-      CK(launch_sobol_compose(sl.x.d(), m->sobB.d(), masks + (size_t)q * m->d, np, m->d, m->sobC.d(), st));
+      CK(launch_sobol_compose(dA, dB, masks + (size_t)q * m->d, np, m->d, m->sobC.d(), st));
       outs[0] = yc;
       rc = predict_core(m, sl, m->sobC.d(), np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
       if (rc) return rc;
@@ -1497,8 +1625,62 @@ int kb200_sobol_sums(kb200_model* m, const double* A, const double* B, long long
   std::vector<double> h((size_t)4 + 2 * nsets);
   CK(cudaMemcpyAsync(h.data(), acc, h.size() * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  call_idle(m);
   for (int i = 0; i < 4; ++i) base[i] = h[i];
   for (int q = 0; q < nsets; ++q) { ya_yc[q] = h[4 + 2 * q]; yb_yc[q] = h[5 + 2 * q]; }
+  return 0;
+}
+
+int kb200_sobol_sums(kb200_model* m, const double* A, const double* B, long long N, int normtype,
+                     const double* norm_a, const double* norm_b, const unsigned char* from_a, int nsets,
+                     double* base, double* ya_yc, double* yb_yc) {
+  if (!A || !B) return fail_arg("kb200_sobol_sums: null argument");
+  SobolSource src;
+  src.kind = 0; src.A = A; src.B = B;
+  return sobol_core(m, src, N, normtype, norm_a, norm_b, from_a, nsets, base, ya_yc, yb_yc, nullptr);
+}
+
+int kb200_sobol_sums_dev(kb200_model* m, const double* d_A, const double* d_B, long long N, int normtype,
+                         const double* norm_a, const double* norm_b, const unsigned char* from_a, int nsets,
+                         double* base, double* ya_yc, double* yb_yc, void* stream) {
+  if (!d_A || !d_B) return fail_arg("kb200_sobol_sums_dev: null argument");
+  SobolSource src;
+  src.kind = 1; src.A = d_A; src.B = d_B;
+  return sobol_core(m, src, N, normtype, norm_a, norm_b, from_a, nsets, base, ya_yc, yb_yc, (cudaStream_t)stream);
+}
+
+int kb200_sobol_sums_gen(kb200_model* m, const unsigned long long* dirnum, int bits, long long i0, long long N,
+                         const double* lo, const double* hi, int normtype, const double* norm_a, const double* norm_b,
+                         const unsigned char* from_a, int nsets, double* base, double* ya_yc, double* yb_yc) {
+  if (!dirnum) return fail_arg("kb200_sobol_sums_gen: null argument");
+  if (bits < 1 || bits > 64 || i0 < 0) return fail_arg("kb200_sobol_sums_gen: 1 <= bits <= 64, i0 >= 0");
+  if (bits < 64 && (unsigned long long)(i0 + N) > (1ull << bits))
+    return fail_arg("kb200_sobol_sums_gen: the sequence has only 2^bits points");
+  SobolSource src;
+  src.kind = 2; src.dirnum = dirnum; src.bits = bits; src.i0 = i0; src.lo = lo; src.hi = hi;
+  return sobol_core(m, src, N, normtype, norm_a, norm_b, from_a, nsets, base, ya_yc, yb_yc, nullptr);
+}
+
+int kb200_sobol_points_dev(int device, const unsigned long long* dirnum, int bits, int dims, long long i0, long long N,
+                           const double* lo, const double* hi, double* d_out, void* stream) {
+  if (!dirnum || !d_out) return fail_arg("kb200_sobol_points_dev: null argument");
+  if (bits < 1 || bits > 64 || dims < 1 || i0 < 0) return fail_arg("kb200_sobol_points_dev: bad bits / dims / i0");
+  if (N < 1) return 0;
+  CK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* dv = nullptr;
+  CK(cudaMallocAsync((void**)&dv, (size_t)dims * bits * 8 + (size_t)2 * dims * 8, st));
+  std::vector<double> lohi((size_t)2 * dims);
+  for (int k = 0; k < dims; ++k) { lohi[k] = lo ? lo[k] : 0.0; lohi[dims + k] = hi ? hi[k] : 1.0; }
+  double* dl = reinterpret_cast<double*>(dv + (size_t)dims * bits);
+  cudaError_t e = cudaMemcpyAsync(dv, dirnum, (size_t)dims * bits * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dl, lohi.data(), lohi.size() * 8, cudaMemcpyHostToDevice, st);
+  const bool scaled = lo && hi;
+  if (e == cudaSuccess)
+    e = launch_sobol_points(dv, bits, dims, i0, N, scaled ? dl : nullptr, scaled ? dl + dims : nullptr, d_out, nullptr, dims, st);
+  cudaFreeAsync(dv, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // lohi / dirnum are the caller's and a local
+  if (e != cudaSuccess) return fail("kb200_sobol_points_dev", e);
   return 0;
 }
 
@@ -1532,6 +1714,7 @@ int kb200_ehvi2d_dev(int device, const double* d_pareto, int k, const double* re
                      long long inc, long long npop, double sign, double* d_out, void* stream) {
   if (!ref || !d_mu0 || !d_mu1 || !d_s0 || !d_s1 || !d_out || (k > 0 && !d_pareto))
     return fail_arg("kb200_ehvi2d_dev: null argument");
+  if (npop < 1) return 0;
   CK(cudaSetDevice(device));
   return ehvi_core(device, d_pareto, k, ref, d_mu0, d_mu1, d_s0, d_s1, (long)inc, (long)npop, sign, d_out,
                    (cudaStream_t)stream);
@@ -1573,17 +1756,30 @@ static int ehvi3_core(const double* d_front, int n, const double* ref, const dou
                       long inc, long cinc, long npop, int mode, double sign, double* d_out, cudaStream_t st) {
   if (n < 0 || n > 1000) return fail_arg("kb200_ehvi3d: 0 <= k <= 1000 front points supported (the reference's static tables)");
   if (mode != 0 && mode != 1) return fail_arg("kb200_ehvi3d: mode must be 0 (reference) or 1 (independent)");
-  const size_t nn = (size_t)n * n, n1 = (size_t)n + 1, np = (size_t)npop;
+  const size_t nn = (size_t)n * n, n1 = (size_t)n + 1;
+  // Workspace: the front geometry (2 (n+1) n^2 doubles: 16 GB at the k = 1000 limit, 17 MB at k = 100) is built once;
+  // the per-candidate terms ((9 + ysplit) (n+1) doubles per candidate) are bounded by a byte budget ($KB200_EHVI3_WS_MB,
+  // default 4096) by scoring the candidates in chunks against the same tables -- in the independent mode, where
+  // candidates do not interact.  The reference mode's early exit couples every candidate to the ones before it in the
+  // batch (ehvi_multi.cc:296-308), so there the whole batch is one chunk, as in the reference.
+  static const size_t budget = (size_t)(getenv("KB200_EHVI3_WS_MB") ? atof(getenv("KB200_EHVI3_WS_MB")) : 4096.0) << 20;
+  long chunk = npop;
+  if (mode == 1) {
+    const size_t per_cand = (size_t)(9 + 16) * n1 * 8;
+    chunk = (long)std::max<size_t>(1024, budget / per_cand);
+    chunk = std::min(chunk, npop);
+  }
+  const size_t np = (size_t)chunk;
   // doubles: coord 3n | xlim nn | ylim nn | slice n1 nn | chunk n1 nn | E, G, EX 3 n1 np each | partial ysplit n1 np
   // then longs first 3 n1, ints rank 3n | hd nn
-  const int ysplit = ehvi3_ysplit(n, npop);
+  const int ysplit = ehvi3_ysplit(n, chunk);
   const size_t nd = 3 * (size_t)n + 2 * nn + 2 * n1 * nn + (9 + (size_t)ysplit) * n1 * np;
   const size_t bytes = nd * 8 + 3 * n1 * 8 + (3 * (size_t)n + nn) * 4 + 64;
   unsigned char* ws = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&ws, bytes, st);
   if (e != cudaSuccess) return fail("kb200_ehvi3d workspace", e);
   Ehvi3Args a;
-  a.n = n; a.npop = npop; a.mode = mode; a.r0 = ref[0]; a.r1 = ref[1]; a.r2 = ref[2];
+  a.n = n; a.npop = chunk; a.mode = mode; a.r0 = ref[0]; a.r1 = ref[1]; a.r2 = ref[2];
   a.front = d_front;
   double* p = reinterpret_cast<double*>(ws);
   a.coord = p; p += 3 * (size_t)n;
@@ -1599,10 +1795,14 @@ static int ehvi3_core(const double* d_front, int n, const double* ref, const dou
   a.first = reinterpret_cast<long*>(p);
   a.rank = reinterpret_cast<int*>(a.first + 3 * n1);
   a.hd = a.rank + 3 * (size_t)n;
-  a.mean = d_mean; a.sdev = d_sdev; a.inc = inc; a.cinc = cinc; a.sign = sign; a.out = d_out;
+  a.inc = inc; a.cinc = cinc; a.sign = sign;
   int rc = 0;
-  e = launch_ehvi3(a, st);
-  if (e != cudaSuccess) rc = fail("ehvi3d", e);
+  for (long c0 = 0; c0 < npop && !rc; c0 += chunk) {
+    a.npop = std::min(chunk, npop - c0);
+    a.mean = d_mean + c0 * inc; a.sdev = d_sdev + c0 * inc; a.out = d_out + c0;
+    e = launch_ehvi3(a, st, c0 == 0 ? 3 : 2);
+    if (e != cudaSuccess) rc = fail("ehvi3d", e);
+  }
   cudaFreeAsync(ws, st);
   return rc;
 }
@@ -1684,6 +1884,13 @@ int kb200_set_groups(kb200_model* m, int ngroups) {
   }
   m->ngroups = ngroups;
   m->dual = m->dual_env == 1 && ngroups > 1;   // 1 group = everything serialised on one stream
+  return 0;
+}
+
+int kb200_set_schedule_population(kb200_model* m, long long population) {
+  if (!m) return fail_arg("null model");
+  if (population < 0) return fail_arg("kb200_set_schedule_population: population >= 0 (0 = decide per call)");
+  m->sched_pop = (long)population;
   return 0;
 }
 

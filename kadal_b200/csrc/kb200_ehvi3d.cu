@@ -299,11 +299,12 @@ int ehvi3_ysplit(int n, long npop) {
   return (int)max(1L, min(want, min((long)(n + 1), 16L)));
 }
 
-cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st) {
+// phase bit 0: front geometry (ranks, nodes, slices, chunks -- independent of the candidates); bit 1: score a.npop candidates
+cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st, int phase) {
   const int n = a.n, n1 = n + 1;
   auto blocks = [](long work, int per) { return (unsigned)max(1L, min((work + per - 1) / per, 148L * 16)); };
 #define E3_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return e__; } while (0)
-  if (n > 0) {
+  if (n > 0 && (phase & 1)) {
     ehvi3_rank_kernel<<<blocks(n, 128), 128, 0, st>>>(a);
     E3_CHECK();
     ehvi3_node_kernel<<<blocks((long)n * n, 128), 128, 0, st>>>(a);
@@ -313,7 +314,7 @@ cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st) {
     ehvi3_chunk_kernel<<<blocks((long)n * n, 128), 128, 0, st>>>(a);
     E3_CHECK();
   }
-  if (a.npop <= 0) return cudaSuccess;
+  if (a.npop <= 0 || !(phase & 2)) return cudaSuccess;
   ehvi3_axis_kernel<<<blocks(3L * n1 * a.npop, 256), 256, 0, st>>>(a);
   E3_CHECK();
   ehvi3_first_kernel<<<3 * n1, E3_THREADS, 0, st>>>(a);

@@ -172,13 +172,15 @@ struct Ehvi3Args {
   double sign;
   double* out;                 // [npop]
 };
-cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st);
+cudaError_t launch_ehvi3(const Ehvi3Args& a, cudaStream_t st, int phase = 3);
 int ehvi3_ysplit(int n, long npop);
 
 // Saltelli sums (kb200_sobol.cu)
 constexpr int SOBOL_BLOCKS = 296;       // 2 x 148
 cudaError_t launch_sobol_compose(const double* A, const double* B, const unsigned char* from_a, long n, int d, double* C,
                                  cudaStream_t st);
+cudaError_t launch_sobol_points(const unsigned long long* dirnum, int bits, int dims, long long i0, long long n,
+                                const double* lo, const double* hi, double* outA, double* outB, int split, cudaStream_t st);
 cudaError_t launch_sobol_dot(const double* u, const double* v, const double* w, long n, int mode, double* partial,
                              double* acc0, double* acc1, cudaStream_t st);
 

@@ -55,6 +55,46 @@ __global__ void sobol_accum_kernel(const double* __restrict__ partial, int nbloc
   *acc1 += s1;
 }
 
+// Unscrambled Sobol points in Gray-code order, as scipy.stats.qmc.Sobol(scramble=False) and the reference's
+// sobolsampling package generate them one after the other (x_i = x_{i-1} xor v[lowest zero bit of i-1]): in closed form
+// x_i = xor of the direction numbers v[b] over the set bits b of gray(i) = i ^ (i >> 1), which needs no sequential state,
+// so every thread makes its own point.  value = x * 2^-bits (exact), then optionally realval's samp * (ub - lb) + lb
+// (samplingplan.py:37-51) without FMA contraction.  Row r of the call is sequence index i0 + r.  Column k < split goes to
+// outA[r][k], column k >= split to outB[r][k - split] (the Saltelli A | B halves, sobol_ind.py:28-29); outB null: all
+// `dims` columns into outA.
+__global__ void __launch_bounds__(256)
+sobol_points_kernel(const unsigned long long* __restrict__ dirnum, int bits, int dims, long long i0, long long n,
+                    const double* __restrict__ lo, const double* __restrict__ hi, double* __restrict__ outA,
+                    double* __restrict__ outB, int split) {
+  const double scale = ldexp(1.0, -bits);
+  const long long total = n * dims;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / dims;
+    const int k = (int)(idx - r * dims);
+    const unsigned long long i = (unsigned long long)(i0 + r);
+    unsigned long long gray = i ^ (i >> 1), x = 0;
+    const unsigned long long* v = dirnum + (size_t)k * bits;
+    while (gray) {
+      const int b = __ffsll((long long)gray) - 1;
+      x ^= v[b];
+      gray &= gray - 1;
+    }
+    double u = __dmul_rn((double)x, scale);
+    if (lo) u = __dadd_rn(__dmul_rn(u, __dsub_rn(hi[k], lo[k])), lo[k]);
+    if (outB == nullptr) outA[idx] = u;
+    else if (k < split) outA[r * split + k] = u;
+    else outB[r * (dims - split) + (k - split)] = u;
+  }
+}
+
+cudaError_t launch_sobol_points(const unsigned long long* dirnum, int bits, int dims, long long i0, long long n,
+                                const double* lo, const double* hi, double* outA, double* outB, int split, cudaStream_t st) {
+  long long blocks = (n * dims + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sobol_points_kernel<<<(int)blocks, 256, 0, st>>>(dirnum, bits, dims, i0, n, lo, hi, outA, outB, split);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sobol_compose(const double* A, const double* B, const unsigned char* from_a, long n, int d, double* C,
                                  cudaStream_t st) {
   long blocks = (n * d + 255) / 256;

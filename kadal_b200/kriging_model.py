@@ -179,6 +179,8 @@ def _tune_many(KrigInfo, xhyp, trainvar, ubhyp, lbhyp, sigmacmaes, scaling, opti
                                         scaling=scaling, seed=seed)
         return bx, bf, obj
     if opt not in ("lbfgsb", "slsqp", "cobyla"):
+        # 'ga' passes kriginfocheck in the reference as well (kriging_model.py:490) but is only wired up for
+        # nbhyp == 1 (:219-221); with more hyper-parameters its tune_hyperparameters ends in this same KeyError (:455-458)
         raise KeyError("%s in KrigInfo['Optimizer'] is not recognised." % opt)
     if optimbound is None:
         raise ValueError("optimbound must be set if optimizer is %s." % opt)

@@ -6,6 +6,7 @@ in a side cache keyed by the identity (+ cheap checksum) of the arrays the refer
 """
 import ctypes
 import os
+import zlib
 from collections import OrderedDict
 
 import numpy as np
@@ -71,7 +72,7 @@ class GpuModel:
         check(lib.kb200_model_create(ctypes.byref(h), device, self.n, self.d, self.p, self.h, ptr(X), ptr(y),
                                      ptr(F), ptr(pls), kid, self.nkernel,
                                      float(self.n if nsamp is None else nsamp), flags))
-        self.handle = h
+        self._h = h
         self.device = device
         self.ymin = float(np.min(y))
         self.pred_token = None
@@ -79,9 +80,23 @@ class GpuModel:
         self.fit_key = None       # (x bytes, trainvar, nugget) of the fit an append may continue from
 
     def close(self):
-        if getattr(self, "handle", None):
-            self.lib.kb200_model_destroy(self.handle)
-            self.handle = None
+        if getattr(self, "_h", None):
+            self.lib.kb200_model_destroy(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        """The live ``kb200_model*``; a model evicted from the cache (or closed by hand) raises instead of handing
+        a dangling pointer to the C library."""
+        h = getattr(self, "_h", None)
+        if not h:
+            raise _capi.Kb200Error("GpuModel is closed (evicted from the model cache: raise $KADAL_B200_CACHE, or "
+                                   "obtain the model again with model_for(KrigInfo))")
+        return h
+
+    @property
+    def closed(self):
+        return not getattr(self, "_h", None)
 
     def __del__(self):
         try:
@@ -100,6 +115,10 @@ class GpuModel:
         return nll, info
 
     def lik_batch_dev(self, x_ptr, P, nbhyp, trainvar, nugget_log10, nll_ptr, info_ptr, stream=0):
+        """Device-pointer batch.  ``stream`` is a raw ``cudaStream_t`` (e.g. ``torch.cuda.current_stream().cuda_stream``):
+        the call is asynchronous and ordered on that stream.  ``stream=0`` runs on the model's own stream and BLOCKS
+        until the results are complete.  One call in flight per model: successive calls on different streams are
+        serialised by the library (include/kb200.h)."""
         check(self.lib.kb200_lik_batch_dev(self.handle, c_void_p(x_ptr), P, nbhyp, int(bool(trainvar)),
                                            float(nugget_log10), c_void_p(nll_ptr), c_void_p(info_ptr),
                                            c_void_p(stream)))
@@ -197,6 +216,16 @@ class GpuModel:
                                           ctypes.byref(mu), ctypes.byref(arg), cnt))
         return float(mu.value), int(arg.value), [int(c) for c in cnt]
 
+    def akmcs_reduce_dev(self, x_ptr, npred, normtype=0, norm_a=None, norm_b=None, stream=0):
+        """The same over a population that is already resident in HBM (``x_ptr``: raw device address of
+        [npred][d] doubles, e.g. ``tensor.data_ptr()``): nothing but the scalars crosses PCIe."""
+        na = as_f64(norm_a) if norm_a is not None else None
+        nb = as_f64(norm_b) if norm_b is not None else None
+        mu, arg, cnt = ctypes.c_double(), ctypes.c_longlong(), (ctypes.c_ulonglong * 3)()
+        check(self.lib.kb200_akmcs_reduce_dev(self.handle, c_void_p(x_ptr), int(npred), int(normtype), ptr(na), ptr(nb),
+                                              ctypes.byref(mu), ctypes.byref(arg), cnt, c_void_p(stream)))
+        return float(mu.value), int(arg.value), [int(c) for c in cnt]
+
     def loocv(self):
         """Leave-one-out predictions (n,) of the installed fit (krigloocv2.py semantics)."""
         out = np.empty(self.n, dtype=np.float64)
@@ -206,6 +235,11 @@ class GpuModel:
     def set_groups(self, ngroups):
         """Number of candidate groups (streams) of a likelihood batch; 1 serialises the kernels."""
         check(self.lib.kb200_set_groups(self.handle, int(ngroups)))
+
+    def set_schedule_population(self, population):
+        """Choose the factorisation schedule as for a population of this size (0: from each call's own P); what a
+        rank evaluating a shard passes so that its bits equal the single-GPU result (kb200.h)."""
+        check(self.lib.kb200_set_schedule_population(self.handle, int(population)))
 
     def profile(self, on):
         check(self.lib.kb200_profile_enable(self.handle, int(bool(on))))
@@ -226,8 +260,15 @@ _CACHE_MAX = int(os.environ.get("KADAL_B200_CACHE", "8"))
 
 
 def _fingerprint(a):
+    """Identity + content of an array the device copy was made from: an in-place edit of any kind (a swapped pair of
+    rows keeps the sum) must give a new key.  CRC-32 of the bytes, O(size) like the sum it replaces (~1 ms per MB)."""
     a = np.asarray(a)
-    return (id(a), a.shape, float(a.sum()) if a.size else 0.0)
+    c = a if a.flags.c_contiguous else np.ascontiguousarray(a)
+    return (id(a), a.shape, str(a.dtype), zlib.crc32(memoryview(c).cast("B")) if a.size else 0)
+
+
+def _content(a):
+    return _fingerprint(a)[1:]
 
 
 def model_for(KrigInfo):
@@ -250,6 +291,7 @@ def model_for(KrigInfo):
         raise ValueError("plscoeff has %d components, n_princomp=%s" % (np.shape(pls)[1], KrigInfo["n_princomp"]))
     m = GpuModel(X, y, F, kids, pls=pls, nsamp=KrigInfo["nsamp"], iso=iso)
     m._keep = (X, y, F, pls)   # keep the arrays alive so ids stay unique
+    m._uploaded = tuple(_content(a) if a is not None else None for a in m._keep)   # what the device copy holds
     _CACHE[key] = m
     while len(_CACHE) > _CACHE_MAX:
         _, old = _CACHE.popitem(last=False)
@@ -267,7 +309,11 @@ def append_source(m, x, trainvar, nugget_log10):
     want = (x.tobytes(), bool(trainvar), float(nugget_log10))
     X, y, F, pls = m._keep
     for prev in reversed(list(_CACHE.values())):
-        if prev is m or prev.handle is None or prev.fit_key != want or prev._keep is None:
+        if prev is m or prev.closed or prev.fit_key != want or prev._keep is None:
+            continue
+        # prev's host arrays must still be what was uploaded (an in-place edit after the upload would let the
+        # append extend a factor of other data: the C side leaves the prefix check to the caller)
+        if getattr(prev, "_uploaded", None) != tuple(_content(a) if a is not None else None for a in prev._keep):
             continue
         if (prev.n != m.n - 1 or prev.d != m.d or prev.p != m.p or prev.h != m.h or prev.iso != m.iso
                 or prev.device != m.device or prev.kernels != m.kernels):

@@ -64,16 +64,68 @@ def all_gather_rows(local, n_total, group=None, device=None):
     return np.concatenate([out[r, :hi - lo] for r, (lo, hi) in enumerate(counts)], axis=0)
 
 
+def _nccl(group):
+    d = _dist()
+    return d.is_available() and d.is_initialized() and d.get_backend(group) == "nccl"
+
+
+def _gather_device(local_t, n_total, group):
+    """all_gather of per-rank 1-D device tensors of unequal length (``shard_bounds`` order) ON THE DEVICE: padded to
+    the longest shard, one ``all_gather_into_tensor`` over NVLink, trimmed with device slicing.  Returns the full
+    device tensor; nothing touches host memory."""
+    import torch
+    dist = _dist()
+    world, rank = _world(group)
+    counts = [shard_bounds(n_total, world, r) for r in range(world)]
+    maxc = max(hi - lo for lo, hi in counts)
+    pad = local_t
+    if local_t.shape[0] != maxc:
+        pad = torch.zeros(maxc, dtype=local_t.dtype, device=local_t.device)
+        pad[:local_t.shape[0]] = local_t
+    out = torch.empty(world * maxc, dtype=local_t.dtype, device=local_t.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    if all(hi - lo == maxc for lo, hi in counts):
+        return out
+    return torch.cat([out[r * maxc:r * maxc + (hi - lo)] for r, (lo, hi) in enumerate(counts)])
+
+
 def likelihood_batch_sharded(Xpop, KrigInfo, trainvar=False, group=None, eval_fn=None):
     """``likelihood_batch`` with the candidates split over the ranks of ``group``: every rank
     evaluates its contiguous slice on its own GPU and all ranks return the full
     ``(nll[P], info[P])``.  ``eval_fn`` (default: the CUDA ``likelihood_batch``) is injectable
-    for the CPU (gloo) tests of the sharding logic."""
-    if eval_fn is None:
-        from .likelihood_func import likelihood_batch as eval_fn
+    for the CPU (gloo) tests of the sharding logic.
+
+    Over NCCL the shard is evaluated with device pointers (``kb200_lik_batch_dev`` on the rank's torch stream), the
+    P / world doubles are gathered on the device and the full vector comes to the host once.  The factorisation
+    schedule is chosen from the GLOBAL population size, so that every candidate gets the same bits as in a
+    single-GPU call on the whole population (the two schedules round differently) and the
+    arg-min is the same for every world size."""
     Xpop = np.atleast_2d(np.asarray(Xpop, dtype=float))
     world, rank = _world(group)
     lo, hi = shard_bounds(len(Xpop), world, rank)
+    if eval_fn is None and world > 1 and _nccl(group):
+        import torch
+        from .likelihood_func import _fixed_nugget
+        from .model import model_for
+        m = model_for(KrigInfo)
+        dev = torch.device(comm_device(group))
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev)
+            x_t = torch.from_numpy(np.ascontiguousarray(Xpop[lo:hi])).to(dev, non_blocking=False)
+            nll_t = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+            inf_t = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+            if hi > lo:
+                m.set_schedule_population(len(Xpop))
+                try:
+                    m.lik_batch_dev(x_t.data_ptr(), hi - lo, Xpop.shape[1], trainvar is True, _fixed_nugget(KrigInfo),
+                                    nll_t.data_ptr(), inf_t.data_ptr(), st.cuda_stream)
+                finally:
+                    m.set_schedule_population(0)
+            nll = _gather_device(nll_t, len(Xpop), group)
+            info = _gather_device(inf_t, len(Xpop), group)
+            return nll.cpu().numpy(), info.cpu().numpy()
+    if eval_fn is None:
+        from .likelihood_func import likelihood_batch as eval_fn
     if hi > lo:
         nll, info = eval_fn(Xpop[lo:hi], KrigInfo, trainvar)
     else:
@@ -86,15 +138,28 @@ def likelihood_batch_sharded(Xpop, KrigInfo, trainvar=False, group=None, eval_fn
 def predict_sharded(x, KrigInfo, outputs=("pred",), group=None, gather=True, eval_fn=None):
     """``predict_arrays`` with the points split over the ranks.  With ``gather=False`` every
     rank keeps only its slice (what AK-MCS / Sobol reductions want); otherwise all ranks
-    return the full arrays."""
+    return the full arrays.  Over NCCL the gather runs on the device (the shard's results are copied up once,
+    ``all_gather_into_tensor`` over NVLink, one device->host copy of the full array)."""
     if eval_fn is None:
         from .prediction import predict_arrays as eval_fn
+        default_fn = True
+    else:
+        default_fn = False
     x = np.atleast_2d(np.asarray(x, dtype=float))
     world, rank = _world(group)
     lo, hi = shard_bounds(len(x), world, rank)
     res = eval_fn(x[lo:hi], KrigInfo, outputs) if hi > lo else {k: np.zeros(0) for k in outputs}
     if not gather or world == 1:
         return res
+    if default_fn and _nccl(group):
+        import torch
+        dev = torch.device(comm_device(group))
+        out = {}
+        with torch.cuda.device(dev):
+            for k in outputs:
+                t = torch.from_numpy(np.ascontiguousarray(np.asarray(res[k], dtype=np.float64).ravel())).to(dev)
+                out[k] = _gather_device(t, len(x), group).cpu().numpy()
+        return out
     return {k: all_gather_rows(np.asarray(res[k], dtype=np.float64).ravel(), len(x), group) for k in outputs}
 
 

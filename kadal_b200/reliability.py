@@ -9,6 +9,49 @@ from .model import model_for
 from .prediction import _check_supported, _ensure_predictor, _norm_args
 
 
+class DevicePopulation:
+    """A Monte-Carlo population kept in HBM across AK-MCS iterations.
+
+    ``AKMCS.run`` predicts the SAME population ``init_samp`` after every added sample (akmcs.py:95-106 before the
+    loop, :144-155 inside it): uploading its 8 d N bytes once instead of once per iteration removes the PCIe traffic
+    the host-pointer path pays every time (480 MB per iteration at BASELINE config 3).  Device memory comes from
+    PyTorch (plumbing only); the upload goes through a pinned staging copy.  Pass the object to
+    :func:`akmcs_reductions` in place of the numpy array; ``rows(i)`` fetches single rows (``xnew = init_samp[minUloc]``)."""
+
+    def __init__(self, init_samp, device=None):
+        import os
+        import torch
+        x = np.ascontiguousarray(np.atleast_2d(np.asarray(init_samp, dtype=np.float64)))
+        if device is None:
+            k = int(os.environ.get("KADAL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            device = "cuda:%d" % (k % max(1, torch.cuda.device_count()))
+        self.shape = x.shape
+        self.device = torch.device(device)
+        self.tensor = torch.empty(x.shape, dtype=torch.float64, device=self.device)
+        step = max(1, (64 << 20) // (8 * x.shape[1]))            # 64 MiB pinned staging slices, copy and DMA overlap
+        stage = [torch.empty((min(step, len(x)), x.shape[1]), dtype=torch.float64).pin_memory() for _ in range(2)]
+        evs = [None, None]
+        for k, lo in enumerate(range(0, len(x), step)):
+            hi = min(len(x), lo + step)
+            b = k & 1
+            if evs[b] is not None:
+                evs[b].synchronize()
+            stage[b][:hi - lo].numpy()[:] = x[lo:hi]
+            self.tensor[lo:hi].copy_(stage[b][:hi - lo], non_blocking=True)
+            evs[b] = torch.cuda.Event()
+            evs[b].record(torch.cuda.current_stream(self.device))
+        torch.cuda.synchronize(self.device)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def data_ptr(self):
+        return self.tensor.data_ptr()
+
+    def rows(self, idx):
+        return self.tensor[idx].cpu().numpy()
+
+
 def akmcs_reductions(init_samp, KrigInfo, group=None):
     """Learning-function and stopping quantities of one AK-MCS iteration.
 
@@ -18,12 +61,25 @@ def akmcs_reductions(init_samp, KrigInfo, group=None):
     shard of the population (``parallel.shard_bounds`` order) and all ranks get the global result.
     """
     _check_supported(KrigInfo, None, None)
-    x = np.atleast_2d(np.asarray(init_samp, dtype=float))
     m = model_for(KrigInfo)
     _ensure_predictor(m, KrigInfo)
     normtype, na, nb = _norm_args(KrigInfo)
-    min_u, arg, cnt = m.akmcs_reduce(x, normtype, na, nb)
-    nmc = x.shape[0]
+    if isinstance(init_samp, DevicePopulation) or (hasattr(init_samp, "data_ptr") and getattr(init_samp, "is_cuda", False)):
+        # resident population (DevicePopulation or a float64 CUDA tensor of shape [N, d]): kb200_akmcs_reduce_dev
+        shape = tuple(init_samp.shape)
+        if len(shape) != 2 or shape[1] != m.d:
+            raise ValueError("population has shape %r, model has %d columns" % (shape, m.d))
+        if not isinstance(init_samp, DevicePopulation):
+            import torch
+            if init_samp.dtype != torch.float64 or not init_samp.is_contiguous():
+                raise ValueError("a device-resident population must be a contiguous float64 tensor")
+            torch.cuda.current_stream(init_samp.device).synchronize()     # the library runs on its own stream
+        min_u, arg, cnt = m.akmcs_reduce_dev(init_samp.data_ptr(), shape[0], normtype, na, nb)
+        nmc = shape[0]
+    else:
+        x = np.atleast_2d(np.asarray(init_samp, dtype=float))
+        min_u, arg, cnt = m.akmcs_reduce(x, normtype, na, nb)
+        nmc = x.shape[0]
     from . import parallel
     world, rank = parallel._world(group)
     if world > 1:

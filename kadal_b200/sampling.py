@@ -75,6 +75,50 @@ def sobol_unit(nsamp, nvar):
             return qmc.Sobol(nvar, scramble=False).random(nsamp + 1)[1:, :]
 
 
+def sobol_direction_numbers(nvar, nsamp):
+    """(v, bits): the direction numbers ``v[nvar][bits]`` (uint64) of the generator :func:`sobol_unit` uses, for the
+    device-side generator (``kb200_sobol_sums_gen`` / ``kb200_sobol_points_dev``), which reproduces
+    ``sobol_unit(nsamp, nvar)`` bit for bit without any host array: point ``i`` is the xor of ``v[:, b]`` over the set
+    bits ``b`` of ``i ^ (i >> 1)``, times ``2**-bits``.  ``None`` when the host generator is the ``sobolsampling``
+    package (its tables are not exposed; callers then generate on the host and upload)."""
+    try:
+        import sobolsampling.sobol_new  # noqa: F401
+        return None
+    except Exception:
+        pass
+    from scipy.stats import qmc
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        eng = qmc.Sobol(nvar, scramble=False)
+    bits = int(eng.bits)
+    if nsamp + 1 > (1 << bits):
+        return None
+    return np.ascontiguousarray(eng._sv, dtype=np.uint64), bits
+
+
+def sobol_points_device(nsamp, nvar, lobound=None, upbound=None, first_row=1, device=None, out_ptr=None, stream=0):
+    """Rows ``first_row .. first_row + nsamp - 1`` of the plan ``sampling('sobol', nvar, ...)`` draws (``first_row=1``:
+    the reference drops row 0), written to device memory at ``out_ptr`` ([nsamp][nvar] doubles), scaled like
+    ``realval`` when bounds are given.  Returns False when the host generator cannot be reproduced on the device."""
+    import ctypes
+    import os
+    from . import _capi
+    dn = sobol_direction_numbers(nvar, first_row + nsamp)
+    if dn is None:
+        return False
+    v, bits = dn
+    lib = _capi.require_gpu()
+    if device is None:
+        device = int(os.environ.get("KADAL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0"))) % max(1, lib.kb200_device_count())
+    lo = _capi.as_f64(lobound) if lobound is not None else None
+    hi = _capi.as_f64(upbound) if upbound is not None else None
+    _capi.check(lib.kb200_sobol_points_dev(int(device), v.ctypes.data_as(ctypes.c_void_p), bits, int(nvar), int(first_row),
+                                           int(nsamp), _capi.ptr(lo), _capi.ptr(hi), ctypes.c_void_p(out_ptr),
+                                           ctypes.c_void_p(stream)))
+    return True
+
+
 def sampling(option, nvar, nsamp, result="normalized", upbound=None, lobound=None):
     """samplingplan.sampling (:13-35) for the options the hyper-parameter search uses."""
     opt = option.lower()

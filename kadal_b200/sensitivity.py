@@ -17,29 +17,15 @@ from .model import model_for
 from .prediction import _check_supported, _ensure_predictor, _norm_args
 
 
-def sobol_sums(A, B, KrigInfo, column_sets, group=None):
-    """(base[4], ya_yc[nsets], yb_yc[nsets]) — see include/kb200.h:kb200_sobol_sums.  ``column_sets`` is
-    a list of column-index tuples taken from A."""
-    _check_supported(KrigInfo, None, None)
-    A = as_f64(np.atleast_2d(A))
-    B = as_f64(np.atleast_2d(B))
-    if A.shape != B.shape:
-        raise ValueError("A and B must have the same shape")
-    m = model_for(KrigInfo)
-    if A.shape[1] != m.d:
-        raise ValueError("sample has %d columns, model has %d" % (A.shape[1], m.d))
-    _ensure_predictor(m, KrigInfo)
-    normtype, na, nb = _norm_args(KrigInfo)
+def _masks(column_sets, d):
     nsets = len(column_sets)
-    masks = np.zeros((max(nsets, 1), m.d), dtype=np.uint8)
+    masks = np.zeros((max(nsets, 1), d), dtype=np.uint8)
     for q, cols in enumerate(column_sets):
         masks[q, list(cols)] = 1
-    base, yayc, ybyc = np.zeros(4), np.zeros(max(nsets, 1)), np.zeros(max(nsets, 1))
-    na = as_f64(na) if na is not None else None
-    nb = as_f64(nb) if nb is not None else None
-    if A.shape[0] > 0:
-        check(m.lib.kb200_sobol_sums(m.handle, ptr(A), ptr(B), A.shape[0], int(normtype), ptr(na), ptr(nb),
-                                     masks.ctypes.data_as(ctypes.c_void_p), nsets, ptr(base), ptr(yayc), ptr(ybyc)))
+    return masks
+
+
+def _all_reduce_sums(base, yayc, ybyc, group):
     from . import parallel
     world, _ = parallel._world(group)
     if world > 1:
@@ -50,6 +36,78 @@ def sobol_sums(A, B, KrigInfo, column_sets, group=None):
         dist.all_reduce(t, group=group)
         v = t.cpu().numpy()
         base, yayc, ybyc = v[:4], v[4:4 + len(yayc)], v[4 + len(yayc):]
+    return base, yayc, ybyc
+
+
+def sobol_sums(A, B, KrigInfo, column_sets, group=None, stream=0):
+    """(base[4], ya_yc[nsets], yb_yc[nsets]) — see include/kb200.h:kb200_sobol_sums.  ``column_sets`` is
+    a list of column-index tuples taken from A.  ``A`` / ``B`` are host arrays, or raw device addresses (ints) with
+    ``A = (ptr, N)``-style tuples ``(data_ptr, nrows)`` for samples that are already resident in HBM
+    (``kb200_sobol_sums_dev``)."""
+    _check_supported(KrigInfo, None, None)
+    m = model_for(KrigInfo)
+    _ensure_predictor(m, KrigInfo)
+    normtype, na, nb = _norm_args(KrigInfo)
+    nsets = len(column_sets)
+    masks = _masks(column_sets, m.d)
+    base, yayc, ybyc = np.zeros(4), np.zeros(max(nsets, 1)), np.zeros(max(nsets, 1))
+    na = as_f64(na) if na is not None else None
+    nb = as_f64(nb) if nb is not None else None
+    if isinstance(A, tuple):
+        (pa, N), (pb, Nb) = A, B
+        if N != Nb:
+            raise ValueError("A and B must have the same number of rows")
+        if N > 0:
+            check(m.lib.kb200_sobol_sums_dev(m.handle, ctypes.c_void_p(pa), ctypes.c_void_p(pb), int(N), int(normtype), ptr(na),
+                                             ptr(nb), masks.ctypes.data_as(ctypes.c_void_p), nsets, ptr(base), ptr(yayc),
+                                             ptr(ybyc), ctypes.c_void_p(stream)))
+    else:
+        A = as_f64(np.atleast_2d(A))
+        B = as_f64(np.atleast_2d(B))
+        if A.shape != B.shape:
+            raise ValueError("A and B must have the same shape")
+        if A.shape[1] != m.d:
+            raise ValueError("sample has %d columns, model has %d" % (A.shape[1], m.d))
+        if A.shape[0] > 0:
+            check(m.lib.kb200_sobol_sums(m.handle, ptr(A), ptr(B), A.shape[0], int(normtype), ptr(na), ptr(nb),
+                                         masks.ctypes.data_as(ctypes.c_void_p), nsets, ptr(base), ptr(yayc), ptr(ybyc)))
+    base, yayc, ybyc = _all_reduce_sums(base, yayc, ybyc, group)
+    return base, yayc[:nsets], ybyc[:nsets]
+
+
+def sobol_sums_generated(nMC, KrigInfo, column_sets, lb=None, ub=None, group=None):
+    """The same sums with A and B drawn ON THE DEVICE exactly as the reference draws them (sobol_ind.py:24-29: one Sobol
+    plan of 2*nvar columns, row 0 dropped, A | B its halves, realval-scaled to [lb, ub] of length 2*nvar): bit-identical to
+    ``sampling('sobolnew', 2*nvar, nMC, ...)`` on the host, nothing but the sums crosses PCIe
+    (``kb200_sobol_sums_gen``).  Under ``torch.distributed`` every rank generates its own contiguous row shard
+    (``parallel.shard_bounds``) and the sums are all-reduced.  Returns None when the host generator in use cannot be
+    reproduced on the device (the ``sobolsampling`` package is installed): generate on the host then."""
+    from . import parallel
+    from .sampling import sobol_direction_numbers
+    _check_supported(KrigInfo, None, None)
+    m = model_for(KrigInfo)
+    dn = sobol_direction_numbers(2 * m.d, int(nMC) + 1)
+    if dn is None:
+        return None
+    v, bits = dn
+    _ensure_predictor(m, KrigInfo)
+    normtype, na, nb = _norm_args(KrigInfo)
+    nsets = len(column_sets)
+    masks = _masks(column_sets, m.d)
+    base, yayc, ybyc = np.zeros(4), np.zeros(max(nsets, 1)), np.zeros(max(nsets, 1))
+    na = as_f64(na) if na is not None else None
+    nb = as_f64(nb) if nb is not None else None
+    lo = as_f64(lb) if lb is not None else None
+    hi = as_f64(ub) if ub is not None else None
+    if (lo is None) != (hi is None) or (lo is not None and (lo.shape != (2 * m.d,) or hi.shape != (2 * m.d,))):
+        raise ValueError("lb and ub must both have 2*nvar entries (the A | B halves of one plan, as in the reference)")
+    world, rank = parallel._world(group)
+    r0, r1 = parallel.shard_bounds(int(nMC), world, rank)
+    if r1 > r0:
+        check(m.lib.kb200_sobol_sums_gen(m.handle, v.ctypes.data_as(ctypes.c_void_p), bits, 1 + r0, r1 - r0, ptr(lo), ptr(hi),
+                                         int(normtype), ptr(na), ptr(nb), masks.ctypes.data_as(ctypes.c_void_p), nsets,
+                                         ptr(base), ptr(yayc), ptr(ybyc)))
+    base, yayc, ybyc = _all_reduce_sums(base, yayc, ybyc, group)
     return base, yayc[:nsets], ybyc[:nsets]
 
 
@@ -67,18 +125,35 @@ class SobolIndices:
         self.problem = problem
         self.n = int(nMC)
         self.group = group
-        if A is None or B is None:
-            from .sampling import sampling
-            if ub is not None and lb is not None:
-                _, init_mat = sampling("sobolnew", self.nvar * 2, self.n, result="real",
-                                       upbound=ub, lobound=lb)      # 2*nvar-long bounds, as in the reference
-            else:
-                init_mat, _ = sampling("sobolnew", self.nvar * 2, self.n)
-            A, B = init_mat[:, :self.nvar], init_mat[:, self.nvar:]
-        self.A = np.ascontiguousarray(A, dtype=float)
-        self.B = np.ascontiguousarray(B, dtype=float)
+        self.ub, self.lb = ub, lb
+        self._A = None if A is None else np.ascontiguousarray(A, dtype=float)
+        self._B = None if B is None else np.ascontiguousarray(B, dtype=float)
         self.fo_2 = None
         self.denom = None
+
+    def _draw(self):
+        """The reference's sample matrices on the host (sobol_ind.py:24-29); only materialised when somebody asks for
+        ``.A`` / ``.B`` or the device generator cannot reproduce the host one."""
+        from .sampling import sampling
+        if self.ub is not None and self.lb is not None:
+            _, init_mat = sampling("sobolnew", self.nvar * 2, self.n, result="real",
+                                   upbound=self.ub, lobound=self.lb)      # 2*nvar-long bounds, as in the reference
+        else:
+            init_mat, _ = sampling("sobolnew", self.nvar * 2, self.n)
+        self._A = np.ascontiguousarray(init_mat[:, :self.nvar], dtype=float)
+        self._B = np.ascontiguousarray(init_mat[:, self.nvar:], dtype=float)
+
+    @property
+    def A(self):
+        if self._A is None:
+            self._draw()
+        return self._A
+
+    @property
+    def B(self):
+        if self._B is None:
+            self._draw()
+        return self._B
 
     def _info(self):
         return self.krigobj.KrigInfo if hasattr(self.krigobj, "KrigInfo") else self.krigobj
@@ -88,7 +163,12 @@ class SobolIndices:
         if first or total or second:
             sets += [(i,) for i in range(self.nvar)]
         pairs = [(i, j) for i in range(self.nvar - 1) for j in range(i + 1, self.nvar)] if second else []
-        base, yayc, ybyc = sobol_sums(self.A, self.B, self._info(), sets + pairs, self.group)
+        res = None
+        if self._A is None and self._B is None:      # no sample given: draw it on the device, as the reference would on the host
+            res = sobol_sums_generated(self.n, self._info(), sets + pairs, self.lb, self.ub, self.group)
+        if res is None:
+            res = sobol_sums(self.A, self.B, self._info(), sets + pairs, self.group)
+        base, yayc, ybyc = res
         n = self.n
         self.fo_2 = (base[0] / n) ** 2                       # sobol_ind.py:84
         self.denom = (base[1] / n) - self.fo_2               # :85

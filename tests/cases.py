@@ -31,5 +31,23 @@ def std_info(g):
                 X_mean=g["X_mean"], X_std=g["X_std"])
 
 
+def trend_info(g, order):
+    """KrigInfo of the TrendOrder 1 / 2 goldens (r2_options.npz): X_norm, idx and F exactly as the reference's
+    Kriging.standardize wrote them (kriging_model.py:99-164)."""
+    t = "trend%d_" % order
+    n, d = g[t + "Xraw"].shape
+    return dict(nvar=d, nsamp=n, X=g[t + "Xraw"], X_norm=g[t + "X_norm"], y=g[t + "y"], F=g[t + "F"], idx=g[t + "idx"],
+                kernel=["gaussian"], nkernel=1, standardization=True, normtype="default", norm_y=False, type="kriging",
+                n_princomp=False, nugget=-6, TrendOrder=order, lb=g[t + "lb"], ub=g[t + "ub"])
+
+
+def iso_info(g):
+    return ko.make_kriginfo(g["iso_X"], g["iso_y"], kernel=("iso_gaussian",))
+
+
+def pof_lcb_info(g):
+    return ko.make_kriginfo(g["pl_X"], g["pl_y"], kernel=("matern52",))
+
+
 APPENDIX_C_CASES = ["gaussian", "exponential", "matern32", "matern52", "trainvar", "tuned", "composite", "kpls"]
 PT = ["pred", "SSqr", "s", "EI", "PoI"]

@@ -48,6 +48,16 @@ def golden_c2_truth():
     return load_golden("c2_truth.npz")
 
 
+@pytest.fixture(scope="session")
+def golden_c2_truth_full():
+    return load_golden("c2_truth_full.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_r2():
+    return load_golden("r2_options.npz")
+
+
 def relerr(a, b, floor=1.0):
     a = np.asarray(a, dtype=float)
     b = np.asarray(b, dtype=float)

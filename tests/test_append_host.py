@@ -10,12 +10,13 @@ class _Fake:
     def __init__(self, X, y, x, d=None, kernels=(0,), p=1, h=0, iso=False, device=0, pls=None):
         self.n, self.d = X.shape
         self.p, self.h, self.iso, self.device, self.kernels = p, h, iso, device, tuple(kernels)
-        self.handle = object()
+        self.closed = False
         self._keep = (X, y, np.ones((self.n, 1)), pls)
+        self._uploaded = tuple(M._content(a) if a is not None else None for a in self._keep)
         self.fit_key = None if x is None else (np.asarray(x, dtype=np.float64).tobytes(), False, -6.0)
 
     def close(self):
-        self.handle = None
+        self.closed = True
 
 
 @pytest.fixture
@@ -62,6 +63,21 @@ def test_append_source_rules(cache, monkeypatch):
     prev.fit_key = (x.tobytes(), False, -6.0)
     prev.close()
     assert M.append_source(nxt, x, False, -6.0) is None
+    # prev's host arrays edited in place after the upload (sum-preserving row swap): the device copy no longer is
+    # what the host arrays say, no append from it
+    prev2 = _Fake(X[:10].copy(), y[:10].copy(), x)
+    cache["prev2"] = prev2
+    assert M.append_source(nxt, x, False, -6.0) is prev2
+    prev2._keep[0][[0, 1]] = prev2._keep[0][[1, 0]]
+    assert M.append_source(nxt, x, False, -6.0) is None
+
+
+def test_model_cache_key_sees_in_place_edits_that_keep_the_sum():
+    a = np.arange(12.0).reshape(4, 3)
+    k0 = M._fingerprint(a)
+    a[[0, 1]] = a[[1, 0]]
+    assert M._fingerprint(a) != k0 and M._fingerprint(a)[0] == k0[0]
+    assert M._fingerprint(a[:, ::2])[1] == (4, 2)          # non-contiguous views are hashed by value
 
 
 def test_pinned_result_arrays_are_recycled(monkeypatch):

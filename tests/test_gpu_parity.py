@@ -114,6 +114,120 @@ def test_std_normalisation_against_golden(kb, golden_std):
     assert relerr(p[1].ravel(), g["SSqr"], 1e-6 * s2) < TOL_VAR
 
 
+# ------------------------------------------------------------------ round-2 option goldens (r2_options.npz)
+@pytest.mark.parametrize("order", [1, 2])
+def test_trend_order_likelihood_against_reference_golden(kb, golden_r2, order):
+    """TrendOrder 1 (p = 4 trend columns) and 2 (p = 6): F from the reference's compute_regression_mat
+    (trendfunction.py:72-111) through the fused forward substitution of [y F] and the p x p generalised least squares
+    of likelihood_func.py:183-193; concentrated and trainvar likelihood, population + 'all' call.  Prediction with
+    p > 1 raises in the reference (prediction.py:250) and here."""
+    g, t = golden_r2, "trend%d_" % order
+    info = cases.trend_info(g, order)
+    p = g[t + "F"].shape[1]
+    nll, inf = kb.likelihood_batch(g[t + "pop"], info, False)
+    assert np.all(inf == 0)
+    conds = conds_of(info, g[t + "pop"])
+    rel = np.abs(nll - g[t + "pop_nll"]) / np.maximum(np.abs(g[t + "pop_nll"]), 1.0)
+    assert np.all(rel < np.array([nll_tol(c) for c in conds])), rel.max()
+    assert np.all(rel[conds < 1e7] < TOL_NLL)
+    assert int(np.argmin(nll)) == int(np.argmin(g[t + "pop_nll"]))
+    A = copy.deepcopy(info)
+    kb.likelihood(g[t + "x"].copy(), A, "all", False)
+    assert relerr(A["NegLnLike"], g[t + "nll"]) < TOL_NLL
+    assert A["BE"].shape == (p, 1) and relerr(A["BE"], g[t + "BE"], 1e-6 * np.abs(g[t + "BE"]).max()) < 1e-7
+    assert relerr(np.asarray(A["SigmaSqr"]).ravel(), g[t + "s2"], 1e-300) < TOL_MEAN
+    assert relerr(A["U"], g[t + "U"]) < TOL_MEAN
+    B = copy.deepcopy(info)
+    kb.likelihood(g[t + "tv_x"].copy(), B, "all", True)
+    assert relerr(B["NegLnLike"], g[t + "tv_nll"]) < TOL_NLL
+    assert relerr(B["BE"], g[t + "tv_BE"], 1e-6 * np.abs(g[t + "tv_BE"]).max()) < 1e-7
+    assert np.shape(B["SigmaSqr"]) == () and relerr(B["SigmaSqr"], g[t + "tv_s2"][0]) < 1e-15
+    with pytest.raises(NotImplementedError):
+        kb.prediction(g[t + "Xraw"][:3], A, "pred")
+
+
+def test_more_than_seven_trend_columns_fail_loudly(kb, golden_r2):
+    """The fused forward substitution carries [y F] as one 8-row DMMA strip: p <= 7 (TrendOrder 2 at d = 3 is p = 10).
+    No silent CPU diversion: the model constructor refuses."""
+    from kadal_b200 import _capi
+    g = golden_r2
+    info = cases.trend_info(g, 1)
+    info["F"] = np.hstack([info["F"], info["F"], info["F"][:, :2]])     # p = 10
+    with pytest.raises(_capi.Kb200Error, match="trend columns"):
+        kb.likelihood_batch(g["trend1_pop"][:2], info, False)
+
+
+def test_iso_gaussian_against_reference_golden(kb, golden_r2):
+    """kernel ['iso_gaussian'] (likelihood_func.py:60-61, KB200_FLAG_ISO): one length scale for every dimension,
+    scalar x as minimize_scalar passes it; Theta written back as nvar copies; prediction from that state."""
+    g = golden_r2
+    info = cases.iso_info(g)
+    out = kb.likelihood(float(g["iso_x"]), info, "all", False)
+    assert out is info and relerr(info["NegLnLike"], g["iso_nll"]) < TOL_NLL
+    assert np.array_equal(np.asarray(info["Theta"], dtype=float), g["iso_Theta"])
+    s2 = float(g["iso_s2"][0])
+    assert relerr(info["BE"], g["iso_BE"]) < TOL_MEAN and relerr(np.asarray(info["SigmaSqr"]).ravel(), g["iso_s2"]) < TOL_MEAN
+    pr = kb.prediction(g["iso_xp"], info, ["pred", "SSqr", "s"])
+    assert relerr(pr[0].ravel(), g["iso_pred"]) < TOL_MEAN
+    assert relerr(pr[1].ravel(), g["iso_SSqr"], 1e-6 * s2) < TOL_VAR
+    assert relerr(pr[2].ravel(), g["iso_s"], 1e-3 * np.sqrt(s2)) < TOL_VAR
+    nll, inf = kb.likelihood_batch(g["iso_grid"][:, None], cases.iso_info(g), False)      # P x 1 population
+    assert np.all(inf == 0) and relerr(nll, g["iso_grid_nll"]) < TOL_NLL
+    assert relerr(kb.likelihood(float(g["iso_grid"][3]), cases.iso_info(g), "default", False), g["iso_grid_nll"][3]) < TOL_NLL
+
+
+def test_pof_less_than_lcb_and_ebe_against_reference_golden(kb, golden_r2):
+    """PoF with limittype '<' / '<=' (prediction.py:303-306), 'lcb' with its (npred, 1) - (1, npred) broadcast
+    (prediction.py:268: an (npred, npred) array, variance not s) and the untransposed 'ebe' (:270)."""
+    g = golden_r2
+    info = cases.pof_lcb_info(g)
+    kb.likelihood(g["pl_x"].copy(), info, "all", False)
+    for lt, tag in (("<", "lt"), ("<=", "le"), (">", "gt")):
+        info["limit"], info["limittype"] = float(g["pl_limit"]), lt
+        pof = kb.prediction(g["pl_xp"], info, "PoF")
+        assert pof.shape == (25, 1) and relerr(pof.ravel(), g["pl_pof_" + tag], 1e-9) < 1e-6
+    info["limittype"] = "=="
+    with pytest.raises(ValueError):
+        kb.prediction(g["pl_xp"], info, "PoF")
+    info["sigmalcb"] = float(g["pl_sigmalcb"])
+    lcb = kb.prediction(g["pl_xp"], info, "LCB")
+    assert lcb.shape == (25, 25) and relerr(lcb, g["pl_lcb"]) < TOL_VAR
+    ebe = kb.prediction(g["pl_xp"], info, "ebe")
+    assert ebe.shape == (1, 25) and relerr(ebe, g["pl_ebe"], 1e-6 * float(np.asarray(info["SigmaSqr"]).ravel()[0])) < TOL_VAR
+    del info["sigmalcb"]
+    with pytest.raises(KeyError):           # nothing sets KrigInfo['sigmalcb'] in the reference either (SURVEY App. B)
+        kb.prediction(g["pl_xp"], info, "LCB")
+
+
+@pytest.mark.parametrize("kernel", [["gaussian"], ["iso_gaussian"]])
+def test_single_hyperparameter_training_path(kb, kernel):
+    """nbhyp == 1 (1-D input, or iso_gaussian at any d): the reference calls minimize_scalar(method='golden',
+    bounds=...) (kriging_model.py:210-213), which scipy >= 1.5 rejects -- here five batched grids.
+    The optimum must be at least as good as a dense oracle grid allows, and the fitted model must predict."""
+    rng = np.random.default_rng(8)
+    d = 1 if kernel == ["gaussian"] else 3
+    n = 40
+    X = rng.uniform(-3, 3, (n, d))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.1 * X[:, :1] ** 2
+    K = dict(X=X, y=y, nvar=d, nsamp=n, nrestart=3, ub=np.full(d, 3.0), lb=np.full(d, -3.0), kernel=list(kernel),
+             nugget=-6, optimizer="lbfgsb")
+    k = kb.Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+    k.train(disp=False)
+    assert k.nbhyp == 1 and k.train_stats["batches"] == 5
+    best = float(np.asarray(k.KrigInfo["Theta"]).ravel()[0])
+    assert np.asarray(k.KrigInfo["Theta"]).shape == (d,)
+    grid = np.linspace(-5, 5, 65)            # the first of the five batched grids: the result can only be better
+    probe = copy.deepcopy(k.KrigInfo)
+    ref = np.array([ko.likelihood(float(t) if kernel == ["iso_gaussian"] else np.array([t]), probe, "default", False,
+                                  check_pd=False) for t in grid])
+    assert k.KrigInfo["NegLnLike"] <= ref.min() + 1e-9 * max(1.0, abs(ref.min()))
+    assert abs(best - grid[int(np.argmin(ref))]) <= 10.0 / 64 + 1e-12
+    R = copy.deepcopy(k.KrigInfo)
+    ko.likelihood(float(best) if kernel == ["iso_gaussian"] else np.array([best]), R, "all", False, check_pd=False)
+    xp = rng.uniform(-3, 3, (50, d))
+    assert relerr(k.predict(xp, ["pred"]), ko.prediction(xp, R, ["pred"])) < TOL_MEAN
+
+
 # ------------------------------------------------------------------ BASELINE config 2
 @pytest.fixture(scope="module")
 def c2():
@@ -156,36 +270,61 @@ def test_c2_full_population_properties(kb, c2):
     assert np.array_equal(order_ref[:6], order_gpu[:6])
 
 
-def test_c2_every_candidate_against_live_reference(kb, c2, golden_c2_full, golden_c2_truth):
-    """All 2 x 512 candidates of BASELINE config 2 against the live reference (tests/golden/c2_full.npz,
-    make_golden.py c2full), through both factorisation schedules, and the worst-conditioned ones against the
-    extended-precision value of the same formula (c2_truth.npz, make_truth.py).
-
-    Bound: 1e-9, or 2 cond ulp where that is larger, and 99 % of the population inside 0.5 cond ulp.  The
-    reference's own float64 result is up to 1.4 cond ulp away from the exact value (candidate 114: reference
-    1.05e-7 off, |NLL| = 0.07), so nothing tighter can be asked of an agreement *with the reference*; against
-    the exact value the CUDA path has to be at least as close as the reference is."""
+def test_c2_every_candidate_against_live_reference(kb, c2, golden_c2_full, golden_c2_truth_full):
+    """All 2 x 512 candidates of BASELINE config 2, through both factorisation schedules, against
+      (a) the live reference's float64 result (tests/golden/c2_full.npz, make_golden.py c2full) and
+      (b) the binary128 value of the reference's own formula on the same float64 Psi
+          (tests/golden/c2_truth_full.npz, make_truth_full.py + oracle/truth/nll_quad.c).
+    Per candidate:  rel(gpu, ref) <= 1e-9   OR   |gpu - truth| <= |ref - truth|,
+    i.e. wherever the north star's 1e-9 is missed it is the *reference* that is further from the exact value of the
+    formula (its float64 LAPACK path is 0.02 .. 1.4 cond ulp away at cond ~ 1e9).  Arg-min and the order of the best
+    8 are exact.  The number of candidates in each branch goes to gpurun_out/parity_c2_counts.json (copied to
+    profiles/ by tools/gpu_round2.sh)."""
+    import json
+    import os
     w, info = c2
-    g, t = golden_c2_full, golden_c2_truth
+    g, t = golden_c2_full, golden_c2_truth_full
     ulp = 2.0 ** -53
+    counts = {}
     for pop in ("popA", "popB"):
-        ref, cond = g["nll_" + pop], g["cond_" + pop]
+        ref, cond, truth = g["nll_" + pop], g["cond_" + pop], t["truth_" + pop]
+        assert np.all(np.isfinite(truth))
+        den = np.maximum(1.0, np.abs(truth))
+        err_ref = np.abs(ref - truth) / den
         nll, inf = kb.likelihood_batch(w[pop], info, False)                  # population: left-looking schedule
         assert np.all(inf == 0)
-        rel = np.abs(nll - ref) / np.maximum(1.0, np.abs(ref))
-        assert np.all(rel <= np.maximum(TOL_NLL, 2.0 * cond * ulp))
-        assert np.mean(rel <= np.maximum(TOL_NLL, 0.5 * cond * ulp)) >= 0.99
         assert int(np.argmin(nll)) == int(np.argmin(ref))
         assert np.array_equal(np.argsort(nll)[:8], np.argsort(ref)[:8])
-    sel = t["idx"]
-    nll_b, _ = kb.likelihood_batch(w["popB"], info, False)
-    small, _ = kb.likelihood_batch(w["popB"][sel], info, False)             # 13 candidates: right-looking schedule
-    den = np.maximum(1.0, np.abs(t["truth"]))
-    err_ref = np.abs(t["ref"] - t["truth"]) / den
-    for got in (nll_b[sel], small):
-        err = np.abs(got - t["truth"]) / den
-        assert np.all(err <= np.maximum(err_ref, 0.1 * t["cond"] * ulp))
-        assert np.median(err) <= np.median(err_ref)
+        runs = {"left_looking_population": nll}
+        if pop == "popB":
+            # the 32 worst-conditioned candidates once more as a small batch: right-looking schedule
+            sel = np.argsort(cond)[-32:]
+            small, _ = kb.likelihood_batch(w[pop][sel], info, False)
+            full = nll.copy()
+            full[sel] = small
+            runs["right_looking_worst32"] = full
+        for name, got in runs.items():
+            rel = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+            err = np.abs(got - truth) / den
+            within = rel <= TOL_NLL
+            closer = err <= err_ref
+            bad = ~(within | closer)
+            counts[pop + "/" + name] = {
+                "candidates": int(len(ref)), "within_1e-9_of_reference": int(within.sum()),
+                "beyond_1e-9_but_closer_to_binary128_truth_than_reference": int((~within & closer).sum()),
+                "neither": int(bad.sum()), "max_rel_vs_reference": float(rel.max()),
+                "max_err_vs_truth_gpu": float(err.max()), "max_err_vs_truth_reference": float(err_ref.max()),
+                "max_err_vs_truth_gpu_in_cond_ulp": float((err / (cond * ulp)).max()),
+                "max_err_vs_truth_reference_in_cond_ulp": float((err_ref / (cond * ulp)).max()),
+                "median_err_vs_truth_gpu_in_cond_ulp": float(np.median(err / (cond * ulp))),
+                "median_err_vs_truth_reference_in_cond_ulp": float(np.median(err_ref / (cond * ulp)))}
+            assert not bad.any(), (pop, name, np.flatnonzero(bad)[:8], rel[bad][:8], err[bad][:8], err_ref[bad][:8])
+            # and as a population the CUDA path is the more accurate of the two
+            assert np.median(err) <= np.median(err_ref) and err.max() <= max(err_ref.max(), TOL_NLL)
+    print("C2 parity counts:", json.dumps(counts))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        json.dump(counts, open(os.path.join(out, "parity_c2_counts.json"), "w"), indent=1)
 
 
 def test_c2_factor_round_trip(kb, c2):
@@ -793,6 +932,22 @@ def test_c5_kpls_n4000_factor_and_candidate_scoring(kb):
     assert np.max(np.abs(np.exp(-0.5 * S) - Psi[:300, :300])) < 1e-14
     nll_b, inf = kb.likelihood_batch(np.vstack([x, x + 0.05]), info, False)
     assert inf[0] == 0 and relerr(nll_b[0], info["NegLnLike"]) < 1e-13
+    # NLL / BE / sigma^2 at full size against a lean float64 Cholesky (LAPACK dpotrf + two triangular solves) of the
+    # exported Psi -- SURVEY.md Appendix A steps 3-5, which the survey measured equal to the reference's six general
+    # solves to <= 1.1e-13 -- with the bound scaled by cond(Psi + eps I) as everywhere else
+    from scipy.linalg import solve_triangular
+    Lc = np.linalg.cholesky(A)
+    a = solve_triangular(Lc, info["y"], lower=True)
+    b = solve_triangular(Lc, np.ones((n, 1)), lower=True)
+    beta = float((b.T @ a) / (b.T @ b))
+    r = a - b * beta
+    s2_ref = float(r.T @ r) / n
+    nll_ref = 0.5 * n * np.log(s2_ref) + np.sum(np.log(np.diag(Lc)))
+    ev = np.linalg.eigvalsh(A)
+    cond = ev[-1] / ev[0]
+    assert relerr(info["NegLnLike"], nll_ref) < nll_tol(cond), (info["NegLnLike"], nll_ref, cond)
+    assert relerr(info["BE"][0, 0], beta) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+    assert relerr(float(info["SigmaSqr"][0, 0]), s2_ref, 1e-300) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
     # EHVI-style candidate scoring: pred + SSqr for a [n_pop, d] population (EHVIcomputation.py:169-172)
     cand = np.random.default_rng(21).uniform(-1, 1, (1500, 100))
     p = kb.predict_arrays(np.vstack([info["X"][:200], cand]), info, ("pred", "ssqr"))
@@ -877,6 +1032,16 @@ def test_akmcs_reductions_match_the_reference_formulas(kb):
     # a population that never fails: the reference's sentinel values
     safe = akmcs_reductions(pop[:1000] * 0.0, ko_shift(info, +50.0, kb), )
     assert safe["Pf"] == 0 and safe["cov"] == 1000 and safe["stop_criteria"] == 100
+    # the population resident in HBM across iterations (kb200_akmcs_reduce_dev): identical scalars, no upload per call
+    from kadal_b200.reliability import DevicePopulation
+    dp = DevicePopulation(pop)
+    for _ in range(2):
+        rd = akmcs_reductions(dp, info)
+        assert rd == r
+    assert np.array_equal(dp.rows(r["minUloc"]), pop[r["minUloc"]])
+    import torch
+    rt = akmcs_reductions(torch.from_numpy(pop[:200_001]).cuda(), info)
+    assert rt == akmcs_reductions(pop[:200_001], info)
 
 
 def ko_shift(info, dy, kb):

@@ -2,6 +2,7 @@
 SURVEY.md Appendix C's 17-digit values, and (when /root/reference is present) against the
 reference itself, bit for bit."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -87,6 +88,51 @@ def test_c2_truth_fixture(golden_c2_truth, golden_c2_full):
     assert 114 in t["idx"] and e.max() < 2.0 and e.max() > 0.05
 
 
+def test_c2_truth_full_fixture(golden_c2_truth_full, golden_c2_full, golden_c2_truth):
+    """Binary128 truth for all 2 x 512 candidates: consistent with the reference goldens and with the older
+    13-candidate long-double table (whose own error is ~2^-11 of the reference's).  What it shows about the reference:
+    its float64 result is up to 1.05e-7 (1.35 cond ulp) from the exact value of its own formula, 21 of the 512
+    popB candidates are more than 1e-9 away from it, and merely running its BLAS with one thread instead of two moves the result
+    by up to 2.1e-8 -- the scale any 1e-9 agreement *with the reference* has to be read against."""
+    t, g, old = golden_c2_truth_full, golden_c2_full, golden_c2_truth
+    ulp = 2.0 ** -53
+    for pop in ("popA", "popB"):
+        assert np.all(np.isfinite(t["truth_" + pop]))
+        e = np.abs(g["nll_" + pop] - t["truth_" + pop]) / np.maximum(1, np.abs(t["truth_" + pop]))
+        assert e.max() < 2.0 * g["cond_" + pop].max() * ulp
+    eB = np.abs(g["nll_popB"] - t["truth_popB"]) / np.maximum(1, np.abs(t["truth_popB"]))
+    assert int(np.argmax(eB)) == 114 and 1.0e-7 < eB.max() < 1.1e-7 and int((eB > 1e-9).sum()) == 21
+    d1 = np.abs(t["ref1t_popB"] - g["nll_popB"]) / np.maximum(1, np.abs(g["nll_popB"]))
+    assert 1e-9 < d1.max() < 5e-8
+    d = np.abs(t["truth_popB"][old["idx"]] - old["truth"]) / np.maximum(1, np.abs(old["truth"]))
+    assert d.max() < 1e-4 * old["cond"].max() * ulp
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libtruth_quad.so")),
+                    reason="oracle/_ref/libtruth_quad.so not built (make -C oracle/truth)")
+def test_binary128_truth_checker_on_a_small_known_case():
+    """oracle/truth/nll_quad.c against the float64 oracle on a well-conditioned matrix (they must agree to ~1e-13)
+    and against a hand-computable 2 x 2 case."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libtruth_quad.so"))
+    lib.kb_truth_nll_quad.restype = ctypes.c_double
+    lib.kb_truth_nll_quad.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-1, 1, (60, 3))
+    y = np.sin(X.sum(1, keepdims=True))
+    info = ko.make_kriginfo(X, y)
+    ko.likelihood(np.array([-0.5, -0.4, -0.6]), info, "all", False, check_pd=False)
+    A = np.ascontiguousarray(info["Psi"] + np.eye(60) * 1e-6)
+    yy = np.ascontiguousarray(y.ravel())
+    assert abs(lib.kb_truth_nll_quad(A.ctypes.data, yy.ctypes.data, 60) - info["NegLnLike"]) < 1e-11 * abs(info["NegLnLike"])
+    A2 = np.array([[1.0, 0.5], [0.5, 1.0]])
+    y2 = np.array([1.0, 3.0])
+    # mu = 2, r = (-1, 1), r' A^-1 r = 2 / (1 - 0.5) = 4, s2 = 2, ln det = ln 0.75
+    want = np.log(2.0) + 0.5 * np.log(0.75)
+    assert abs(lib.kb_truth_nll_quad(A2.ctypes.data, y2.ctypes.data, 2) - want) < 1e-15
+    assert np.isnan(lib.kb_truth_nll_quad(np.array([[1.0, 2.0], [2.0, 1.0]]).ctypes.data, y2.ctypes.data, 2))
+
+
 def test_oracle_errors():
     info = ko.make_kriginfo(np.zeros((4, 2)), np.zeros((4, 1)))
     with pytest.raises(np.linalg.LinAlgError):  # duplicate rows + 0 nugget-free? keep nugget tiny
@@ -112,3 +158,62 @@ def test_oracle_bit_identical_to_live_reference(golden_c, name):
     pb = ko.prediction(golden_c["xp"], B, cases.PT)
     for a, b in zip(pa, pb):
         assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+# ------------------------------------------------------------------ round-2 option goldens (r2_options.npz)
+@pytest.mark.parametrize("order", [1, 2])
+def test_oracle_trend_order_likelihood_golden(golden_r2, order):
+    """TrendOrder 1 (p = 4) and 2 (p = 6): likelihood_func.py:183-193 with F of p columns."""
+    g, t = golden_r2, "trend%d_" % order
+    info = cases.trend_info(g, order)
+    A = copy.deepcopy(info)
+    ko.likelihood(g[t + "x"].copy(), A, "all", False, check_pd=False)
+    assert relerr(A["NegLnLike"], g[t + "nll"]) < 1e-12
+    assert relerr(A["BE"], g[t + "BE"], 1e-300) < 1e-9 and A["BE"].shape == g[t + "BE"].shape
+    assert relerr(np.asarray(A["SigmaSqr"]).ravel(), g[t + "s2"], 1e-300) < 1e-10
+    nll = ko.likelihood_population(g[t + "pop"], copy.deepcopy(info), False, check_pd=False)
+    assert relerr(nll, g[t + "pop_nll"]) < 1e-12
+    B = copy.deepcopy(info)
+    ko.likelihood(g[t + "tv_x"].copy(), B, "all", True, check_pd=False)
+    assert relerr(B["NegLnLike"], g[t + "tv_nll"]) < 1e-12
+    assert relerr(B["BE"], g[t + "tv_BE"], 1e-300) < 1e-9
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_host_trend_mirror_reproduces_reference_regression_matrix(golden_r2, order):
+    """kadal_b200.trendfunction (independent implementation: direct enumeration + three-term recurrences) against
+    idx and F of the reference's polytruncation / compute_regression_mat (trendfunction.py:7-41, 72-111)."""
+    from kadal_b200.trendfunction import compute_regression_mat, polytruncation
+    g, t = golden_r2, "trend%d_" % order
+    d = g[t + "Xraw"].shape[1]
+    idx = polytruncation(order, d, 1)
+    assert np.array_equal(idx, g[t + "idx"])
+    F = compute_regression_mat(idx, g[t + "X_norm"], np.vstack((-np.ones(d), np.ones(d))), np.ones(d))
+    assert F.shape == g[t + "F"].shape and relerr(F, g[t + "F"], 1e-300) < 1e-12
+
+
+def test_oracle_iso_gaussian_golden(golden_r2):
+    g = golden_r2
+    info = cases.iso_info(g)
+    ko.likelihood(float(g["iso_x"]), info, "all", False, check_pd=False)
+    assert relerr(info["NegLnLike"], g["iso_nll"]) < 1e-12
+    assert np.array_equal(np.asarray(info["Theta"], dtype=float), g["iso_Theta"])
+    out = ko.prediction(g["iso_xp"], info, ["pred", "SSqr", "s"])
+    for k, v in zip(["pred", "SSqr", "s"], out):
+        assert relerr(np.asarray(v).ravel(), g["iso_" + k], 1e-300) < 1e-9, k
+    grid = np.array([ko.likelihood(float(x), cases.iso_info(g), "default", False, check_pd=False) for x in g["iso_grid"]])
+    assert relerr(grid, g["iso_grid_nll"]) < 1e-12
+
+
+def test_oracle_pof_less_than_and_lcb_golden(golden_r2):
+    g = golden_r2
+    info = cases.pof_lcb_info(g)
+    ko.likelihood(g["pl_x"].copy(), info, "all", False, check_pd=False)
+    for lt, tag in (("<", "lt"), ("<=", "le"), (">", "gt")):
+        info["limit"], info["limittype"] = float(g["pl_limit"]), lt
+        assert relerr(np.asarray(ko.prediction(g["pl_xp"], info, "PoF")).ravel(), g["pl_pof_" + tag], 1e-300) < 1e-9
+    assert np.array_equal(g["pl_pof_lt"], g["pl_pof_le"])
+    info["sigmalcb"] = float(g["pl_sigmalcb"])
+    lcb = ko.prediction(g["pl_xp"], info, "LCB")
+    assert lcb.shape == g["pl_lcb"].shape == (25, 25) and relerr(lcb, g["pl_lcb"]) < 1e-9
+    assert ko.prediction(g["pl_xp"], info, "ebe").shape == g["pl_ebe"].shape == (1, 25)
