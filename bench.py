@@ -739,6 +739,35 @@ def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
         barrier()
         return e0.elapsed_time(e1) / reps
 
+    # ---- small-n likelihood batches (north star (2): one CTA per matrix held in shared memory): C1 training
+    # (n=50, d=2: 7 restarts x 3-point L-BFGS-B stencils = 21 candidates per batch) and C3 training (n=200, d=6, a CMA-ES
+    # population of 512), each also through the tile path the same sizes took in round 1 ($KB200_NO_SMALL_LIK=1)
+    small = {}
+    for tag, n_s, d_s, P_s, seed in (("c1_train_lik", 50, 2, 21, 21), ("c3_train_lik", 200, 6, 512, 22)):
+        rng = np.random.default_rng(seed)
+        Xs = rng.uniform(-1, 1, (n_s, d_s))
+        ys = (np.sin(Xs.sum(1)) + 0.3 * Xs[:, 0] ** 2)[:, None] + 3.0
+        ms_ = GpuModel(Xs, ys, np.ones((n_s, 1)), [0], device=local_rank)
+        pops = rng.uniform(-0.5, 1.0, (P_s, d_s))
+        xd = torch.from_numpy(pops).to(dev)
+        nll = torch.empty(P_s, dtype=torch.float64, device=dev)
+        info = torch.empty(P_s, dtype=torch.int32, device=dev)
+        fn = lambda: ms_.lik_batch_dev(xd.data_ptr(), P_s, d_s, False, -6.0, nll.data_ptr(), info.data_ptr(), stream)
+        t_small = timed(fn, 20)
+        v_small = nll.cpu().numpy().copy()
+        os.environ["KB200_NO_SMALL_LIK"] = "1"
+        t_tile = timed(fn, 20)
+        del os.environ["KB200_NO_SMALL_LIK"]
+        v_tile = nll.cpu().numpy()
+        assert int((info != 0).sum().item()) == 0 and np.allclose(v_small, v_tile, rtol=1e-7, atol=1e-7)
+        fl = lik_flops_per_eval(n_s, d_s) * P_s
+        small[tag] = {"workload": "n=%d, d=%d, %d candidates per batch and GPU" % (n_s, d_s, P_s),
+                      "kernel": "lik_small_kernel (assembly + blocked POTF2 + forward substitution of one candidate per CTA in shared memory)",
+                      "evals_per_s_per_gpu": P_s / (t_small * 1e-3), "ms_per_batch": t_small,
+                      "fp64_tflops_algorithmic": fl / (t_small * 1e-3) / 1e12,
+                      "tile_path": {"evals_per_s_per_gpu": P_s / (t_tile * 1e-3), "ms_per_batch": t_tile}}
+        ms_.close()
+    out["small_n_likelihood"] = small
     # ---- C4
     rng = np.random.default_rng(7)
     X = rng.uniform(-1, 1, (800, 20))

@@ -751,6 +751,52 @@ int kb200_lik_batch_dev(kb200_model* m, const double* d_x, int P, int nbhyp, int
   // no stream has nothing to order later work against); otherwise asynchronous on the caller's stream.
   cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
   CK(call_enter(m, st));
+  // Small models (the whole matrix fits in shared memory): one CTA per candidate assembles, factorises and solves in
+  // shared memory -- nothing of Psi ever reaches HBM (lik_small_kernel; $KB200_NO_SMALL_LIK=1 forces the tile path).
+  const bool no_small = getenv("KB200_NO_SMALL_LIK") && atoi(getenv("KB200_NO_SMALL_LIK")) != 0;   // (read per call: A/B tests)
+  const int Nsmall = (no_small || (m->flags & KB200_FLAG_NAIVE)) ? 0 : lik_small_pad(m->n, m->d);
+  if (Nsmall > 0) {
+    const int Pb = std::min(P, 1 << 16);
+    CK(m->Z.reserve((size_t)Pb * m->nq * m->npad * 8));
+    CK(m->cand.reserve((size_t)P * m->cstride * 8));
+    CK(m->logdet.reserve((size_t)Pb * 8));
+    int rc = decode(m, d_x, P, nbhyp, trainvar, nugget_log10, m->cand.d(), st);
+    if (rc) return rc;
+    for (int p0 = 0; p0 < P; p0 += Pb) {
+      const int pb = std::min(Pb, P - p0);
+      CorrArgs c;
+      memset(&c, 0, sizeof(c));
+      c.spec = make_spec(m);
+      c.mode = CORR_ASSEMBLE;
+      c.n = m->n; c.nt = m->nt; c.X = m->X.d();
+      c.cand = m->cand.d() + (size_t)p0 * m->cstride; c.cand_stride = m->cstride;
+      c.add_eps = 1;
+      CholArgs a = chol_args(m, nullptr, nullptr, m->Z.d(), m->logdet.d(), d_info + p0);
+      {
+        Nvtx r2("kb200_lik_small");
+        Timed t(m, KB200_PROF_DIAG, st);
+        CK(launch_lik_small(c, a, pb, st));
+      }
+      FinArgs f;
+      memset(&f, 0, sizeof(f));
+      f.Z = m->Z.d(); f.logdet = m->logdet.d(); f.info = d_info + p0;
+      f.cand = c.cand; f.cand_stride = m->cstride;
+      f.nq = m->nq; f.npad = m->npad; f.n = m->n;
+      f.trainvar = trainvar; f.nsamp = m->nsamp;
+      f.nll = d_nll + p0;
+      {
+        Timed t(m, KB200_PROF_FINALIZE, st);
+        CK(launch_finalize(f, pb, st));
+      }
+    }
+    if (!stream) {
+      CK(cudaStreamSynchronize(st));
+      call_idle(m);
+    } else {
+      CK(call_leave(m, st));
+    }
+    return 0;
+  }
   int Pb = (int)std::min<size_t>((size_t)P, std::max<size_t>(1, m->ws_cap_bytes / per_matrix_bytes(m)));
   Pb = std::min(Pb, 32768);
   int rc = reserve_lik(m, P, Pb);

@@ -181,10 +181,10 @@ __device__ __forceinline__ void strip_trsm32_t(double* xrow, const double* S, in
 // trailing update after the 32-wide panel at column o: items it0 <= it < it1 of "lower 16x16 blocks in
 // row-major triangular order, then the RHS 8x16 blocks", warp `widx` of `nw`.
 __device__ __forceinline__ void trailing_update32_t(double* S, double* trow, int o, int it0, int it1, int widx, int nw,
-                                                    int lane) {
+                                                    int lane, const int N = TB, const int tld = TLD) {
   const int g = lane >> 2, tq = lane & 3;
   const int base = o + 32;
-  const int nb = (TB - base) >> 4;
+  const int nb = (N - base) >> 4;
   const int ntri = nb * (nb + 1) / 2;
   const int nitems = ntri + nb;
   if (it1 > nitems) it1 = nitems;
@@ -231,7 +231,7 @@ __device__ __forceinline__ void trailing_update32_t(double* S, double* trow, int
       }
     } else {
       const int bj = it - ntri;
-      double* ar0 = trow + g * TLD;
+      double* ar0 = trow + g * tld;
       const double* br0 = S + tri(base + 16 * bj + g);
       const double* br1 = S + tri(base + 16 * bj + g + 8);
       const int cc = base + 16 * bj + 2 * tq;
@@ -295,6 +295,136 @@ __device__ __forceinline__ void syrk_acc_init(double (&acc)[17][2], const double
 }
 
 }  // namespace
+
+
+// ============================================================================ small n: one CTA per matrix
+// likelihood_func.py:93-102 + 168-213 for ONE candidate per CTA when the whole correlation matrix fits in shared
+// memory (north star (2)): Psi + eps I is assembled straight into a PACKED lower
+// triangle in shared memory (never touches HBM), factorised there by the same blocked POTF2 as a diagonal tile
+// (32-wide panels: warp 0 factors the 32 x 32 block in registers with shuffles while warps 1..7 finish the previous
+// trailing update; 8-row strips and the 16 x 16 trailing blocks on DMMA), with [y F] riding along as the right-hand-side
+// strip (fused forward substitution); only Z = L^-1 [y F] (nq x n doubles), sum ln L_ii and info go back.
+// N = n rounded up to 32 (identity padding, as the tile path pads to 128: n = 50 costs 64^3/3 flops instead of 128^3/3).
+// Shared memory (doubles): S tri(N) | scratch max(8 (N + 4), d N + 32 lda + 2 d) (X staging during the assembly, then the
+// RHS strip) | dinv N | W8 2 x 256 | lbuf 64 | red 16 | s_bad.
+__host__ __device__ inline size_t lik_small_smem(int N, int d) {
+  const size_t lda = (size_t)(d | 1);
+  const size_t stage = (size_t)d * N + 32 * lda + 2 * (size_t)d + 8;
+  const size_t strip = (size_t)8 * (N + 4);
+  return ((size_t)N * (N + 1) / 2 + (stage > strip ? stage : strip) + N + 512 + 64 + 16 + 2) * 8;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(HT)
+lik_small_kernel(CorrArgs C, CholArgs A, int N) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* S = reinterpret_cast<double*>(smem_raw);
+  const int d = C.spec.d, lda = d | 1, n = C.n, tld = N + 4;
+  double* scratch = S + (size_t)N * (N + 1) / 2;
+  const size_t stage = (size_t)d * N + 32 * (size_t)lda + 2 * (size_t)d + 8, strip = (size_t)8 * tld;
+  double* dinv = scratch + (stage > strip ? stage : strip);
+  double* W8s = dinv + N;
+  double* lbuf = W8s + 512;
+  double* s_red = lbuf + 64;
+  int* s_bad = reinterpret_cast<int*>(s_red + 16);
+  // assembly staging inside `scratch`
+  double* Bt = scratch;                         // [d][N] samples, transposed, zero padded
+  double* As = Bt + (size_t)d * N;              // [32][lda] the rows of the current strip
+  double* th2 = As + 32 * lda + ((32 * lda) & 1);   // [d] theta^2 | [d] RN(1/theta^2)   (16-byte aligned for double2 loads)
+  double* trow = scratch;                       // afterwards: the RHS strip [8][tld]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long m = blockIdx.x;
+  const double* cand = C.cand + m * C.cand_stride;
+  const double w0 = cand[4 * C.spec.ntheta];
+  const double eps = cand[4 * C.spec.ntheta + C.spec.nkernel];
+  for (int idx = tid; idx < d * N; idx += HT) {
+    const int k = idx / N, c = idx - k * N;
+    Bt[idx] = c < n ? C.X[(size_t)c * d + k] : 0.0;
+  }
+  if (FAST && tid < 2 * d) th2[tid] = cand[2 * C.spec.ntheta + tid];
+  // ---- assembly: 32-row strips, lane = row of the strip, warps walk the column quads 4 q <= row
+  for (int r0 = 0; r0 < N; r0 += 32) {
+    __syncthreads();                            // Bt / th2 ready; previous strip's As consumed
+    for (int idx = tid; idx < 32 * d; idx += HT) {
+      const int r = idx / d, k = idx - r * d;
+      As[r * lda + k] = Bt[(size_t)k * N + r0 + r];
+    }
+    __syncthreads();
+    const int row = r0 + lane;
+    const int nq4 = (r0 + 32) >> 2;             // quads up to the end of the strip's diagonal block
+    for (int q = warp; q < nq4; q += HWARPS) {
+      const int c0 = 4 * q;
+      if (c0 > row) continue;                   // strictly above the diagonal: not stored
+      Quad v;
+      if (row >= n || c0 >= n) v = quad_set(0.0);
+      else if (FAST) v = corr_quad_gauss<true, 0>(d, th2, th2 + d, w0, As + lane * lda, Bt + c0, N);
+      else v = corr_quad<true>(C.spec, cand, As + lane * lda, Bt + c0, N);
+      double* dst = S + tri(row) + c0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + e;
+        if (c > row) break;
+        double x = v.v[e];
+        if (row >= n || c >= n) x = (row == c) ? 1.0 : 0.0;          // identity padding
+        else if (row == c && C.add_eps) x = __dadd_rn(x, eps);       // Psi + eye * eps  (likelihood_func.py:171)
+        dst[e] = x;
+      }
+    }
+  }
+  __syncthreads();                              // the staging area is dead: it becomes the RHS strip
+  for (int idx = tid; idx < 8 * tld; idx += HT) {
+    const int q = idx / tld, r = idx - q * tld;
+    trow[idx] = (q < A.nq && r < n) ? A.R[(size_t)q * A.npad + r] : 0.0;
+  }
+  if (tid == 0) *s_bad = 0;
+  __syncthreads();
+  // ---- blocked factorisation with the RHS strip riding along (potf2_blocked_t for N / 32 panels)
+  const int nblk = N >> 5;
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int o = 32 * kb;
+    double* W8k = W8s + (kb & 1) * 256;
+    if (warp == 0) {
+      const int b = potf2_32_warp_t(S, o, dinv, lbuf, lane);
+      __syncwarp();
+      inv8_warp_t(S, o, dinv, W8k, lane);
+      if (lane == 0 && b && *s_bad == 0) *s_bad = b;
+    } else if (kb > 0) {
+      trailing_update32_t(S, trow, o - 32, 3, 1 << 20, warp - 1, HWARPS - 1, lane, N, tld);
+    }
+    __syncthreads();
+    const int nrow_strips = (N - o - 32) >> 3;
+    for (int st = warp; st <= nrow_strips; st += HWARPS) {
+      const int g = lane >> 2;
+      if (st < nrow_strips) strip_trsm32_t(S + tri(o + 32 + 8 * st + g) + o, S, o, W8k, lane);
+      else strip_trsm32_t(trow + g * tld + o, S, o, W8k, lane);
+    }
+    __syncthreads();
+    if (kb + 1 < nblk) {
+      trailing_update32_t(S, trow, o, 0, 3, warp, HWARPS, lane, N, tld);
+      __syncthreads();
+    }
+  }
+  // ---- outputs
+  const int bad = *s_bad;
+  if (tid == 0) A.info[m] = bad;
+  double* z = A.Z + (size_t)m * A.nq * A.npad;
+  for (int idx = tid; idx < A.nq * A.npad; idx += HT) {
+    const int q = idx / A.npad, r = idx - q * A.npad;
+    z[idx] = r < N ? trow[q * tld + r] : 0.0;
+  }
+  double v = 0.0;
+  for (int i = tid; i < N; i += HT) v += log(fabs(S[tri(i) + i]));   // padded rows are exactly 1
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < HWARPS; ++i) s += s_red[i];
+    A.logdet[m] = s;
+  }
+}
 
 // ============================================================================ diagonal tile
 // smem (doubles): [0, DNST*2048) SYRK ring, aliased by the packed S (8256) | trow 8*TLD | dinv 128 |
@@ -803,6 +933,36 @@ static cudaError_t half_attrs() {
   cudaFuncSetAttribute(chol_panel_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   done[dev] = true;
   return cudaSuccess;
+}
+
+// largest n the in-shared-memory likelihood kernel takes for this input dimension (0: none)
+int lik_small_pad(int n, int d) {
+  const int N = (n + 31) & ~31;
+  if (N > 256 || lik_small_smem(N, d) > (size_t)227 * 1024) return 0;
+  return N;
+}
+
+cudaError_t launch_lik_small(const CorrArgs& c, const CholArgs& a, int nmat, cudaStream_t st) {
+  const int N = lik_small_pad(c.n, c.spec.d);
+  if (N == 0) return cudaErrorInvalidValue;
+  const size_t sm = lik_small_smem(N, c.spec.d);
+  static size_t attr[64][2] = {{0}};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  const bool fast = c.spec.nkernel == 1 && c.spec.kid[0] == K_GAUSS && !c.spec.kpls;
+  if (sm > attr[dev][fast]) {
+    const int want = (int)(sm > 48 * 1024 ? sm : 48 * 1024);
+    cudaError_t e = fast ? cudaFuncSetAttribute(lik_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)
+                         : cudaFuncSetAttribute(lik_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e != cudaSuccess) return e;
+    if (fast) cudaFuncSetAttribute(lik_small_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    else cudaFuncSetAttribute(lik_small_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr[dev][fast] = sm;
+  }
+  if (fast) lik_small_kernel<true><<<nmat, HT, sm, st>>>(c, a, N);
+  else lik_small_kernel<false><<<nmat, HT, sm, st>>>(c, a, N);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_chol_diag_half(const CholArgs& a, int j, int nmat, cudaStream_t st) {

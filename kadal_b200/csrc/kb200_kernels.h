@@ -204,6 +204,9 @@ cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, 
 // half-SM variants (kb200_half.cu): two CTAs per SM
 cudaError_t launch_chol_diag_half(const CholArgs& a, int j, int nmat, cudaStream_t st);
 cudaError_t launch_chol_panel_half(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);
+// small n: assembly + factorisation + forward substitution of one candidate per CTA in shared memory (kb200_half.cu)
+int lik_small_pad(int n, int d);
+cudaError_t launch_lik_small(const CorrArgs& c, const CholArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_rl_rhs_update(const CholArgs& a, int k, int nmat, cudaStream_t st, int ntiles = -1);
 cudaError_t launch_w8_from_tiles(const CholArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_finalize(const FinArgs& a, int nmat, cudaStream_t st);

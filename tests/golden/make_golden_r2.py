@@ -22,6 +22,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import ref_loader, kriging_oracle as ko  # noqa: E402
 
 
+def truth_F(ref, x, KI):
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "libtruth_quad.so"))
+    lib.kb_truth_nll_quad_F.restype = ctypes.c_double
+    lib.kb_truth_nll_quad_F.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p]
+    A = copy.deepcopy(KI)
+    ref.likelihood(x.copy(), A, "all", False)
+    n = A["Psi"].shape[0]
+    M = np.ascontiguousarray(A["Psi"] + np.eye(n) * 10.0 ** A["nugget"])
+    F = np.ascontiguousarray(A["F"], dtype=float)
+    y = np.ascontiguousarray(np.asarray(A["y"], dtype=float).ravel())
+    return lib.kb_truth_nll_quad_F(M.ctypes.data, y.ctypes.data, F.ctypes.data, n, F.shape[1], None)
+
+
 def trend_cases(ref, out):
     """TrendOrder 1 at d = 3 (p = 4 trend columns) and TrendOrder 2 at d = 2 (p = 6): the C ABI carries up to 7 trend
     columns next to y through the fused forward substitution (kb200_model_create)."""
@@ -47,11 +61,15 @@ def trend_cases(ref, out):
         ref.likelihood(x.copy(), A, "all", False)
         out[tag + "x"] = x
         out[tag + "nll"] = A["NegLnLike"]
+        out[tag + "nll_truth"] = truth_F(ref, x, KI)
         out[tag + "BE"] = np.asarray(A["BE"], dtype=float)
         out[tag + "s2"] = np.asarray(A["SigmaSqr"], dtype=float).reshape(-1)
         out[tag + "U"] = np.ascontiguousarray(A["U"])
         out[tag + "pop"] = pop
         out[tag + "pop_nll"] = np.array([ref.likelihood(p.copy(), copy.deepcopy(KI), "default", False) for p in pop])
+        # binary128 value of the same formula on the same float64 Psi and F (oracle/truth/nll_quad.c): with p > 1 the
+        # reference's own float64 result is up to 7e-9 away from it (TrendOrder 2, candidate 7)
+        out[tag + "pop_truth"] = np.array([truth_F(ref, p, KI) for p in pop])
         # trainvar: x carries log10 sigma^2 behind theta (likelihood_func.py:74-79, 197-199)
         B = copy.deepcopy(KI)
         xt = np.r_[x, 0.4]

@@ -128,12 +128,20 @@ def test_trend_order_likelihood_against_reference_golden(kb, golden_r2, order):
     assert np.all(inf == 0)
     conds = conds_of(info, g[t + "pop"])
     rel = np.abs(nll - g[t + "pop_nll"]) / np.maximum(np.abs(g[t + "pop_nll"]), 1.0)
-    assert np.all(rel < np.array([nll_tol(c) for c in conds])), rel.max()
-    assert np.all(rel[conds < 1e7] < TOL_NLL)
+    # per candidate: inside the bound, or closer to the binary128 value of the formula than the reference itself is
+    # (with p trend columns the p x p normal equations add their own conditioning: the reference is up to 7e-9 off)
+    den = np.maximum(np.abs(g[t + "pop_truth"]), 1.0)
+    err, err_ref = np.abs(nll - g[t + "pop_truth"]) / den, np.abs(g[t + "pop_nll"] - g[t + "pop_truth"]) / den
+    ok = (rel < np.array([nll_tol(c) for c in conds])) | (err <= err_ref)
+    assert np.all(ok), (rel[~ok], err[~ok], err_ref[~ok])
+    assert err.max() <= max(err_ref.max(), TOL_NLL)
+    assert np.all((rel[conds < 1e7] < TOL_NLL) | (err <= err_ref)[conds < 1e7])
     assert int(np.argmin(nll)) == int(np.argmin(g[t + "pop_nll"]))
     A = copy.deepcopy(info)
     kb.likelihood(g[t + "x"].copy(), A, "all", False)
-    assert relerr(A["NegLnLike"], g[t + "nll"]) < TOL_NLL
+    tr = float(g[t + "nll_truth"])
+    assert (relerr(A["NegLnLike"], g[t + "nll"]) < TOL_NLL
+            or abs(A["NegLnLike"] - tr) <= abs(float(g[t + "nll"]) - tr)), (A["NegLnLike"], float(g[t + "nll"]), tr)
     assert A["BE"].shape == (p, 1) and relerr(A["BE"], g[t + "BE"], 1e-6 * np.abs(g[t + "BE"]).max()) < 1e-7
     assert relerr(np.asarray(A["SigmaSqr"]).ravel(), g[t + "s2"], 1e-300) < TOL_MEAN
     assert relerr(A["U"], g[t + "U"]) < TOL_MEAN
@@ -967,6 +975,59 @@ def test_c5_kpls_n4000_factor_and_candidate_scoring(kb):
     s2s = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
     assert relerr(q[0], qr[0]) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
     assert relerr(q[1], qr[1], 1e-6 * s2s) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
+
+
+# ------------------------------------------------------------------ small n: one CTA per matrix in shared memory
+@pytest.mark.parametrize("n,d,kernel,tv", [(50, 2, ("gaussian",), False), (64, 4, ("matern52",), False),
+                                           (200, 6, ("gaussian",), False), (200, 6, ("gaussian",), True),
+                                           (97, 10, ("gaussian", "exponential"), False), (224, 3, ("exponential",), False),
+                                           (33, 1, ("gaussian",), False)])
+def test_small_n_in_shared_memory_likelihood_against_oracle_and_tile_path(kb, monkeypatch, n, d, kernel, tv):
+    """lik_small_kernel (north star (2): one CTA per matrix held in shared memory -- assembly, blocked POTF2 with warp
+    shuffles, fused forward substitution; n <= 224..256 depending on d) against the oracle at the north-star tolerance
+    and against the tile path ($KB200_NO_SMALL_LIK=1) it replaces for these sizes: same Psi bits, another order of the
+    factorisation's roundings."""
+    rng = np.random.default_rng(1000 * n + d)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.2 * X[:, :1] ** 2 + 3.0
+    info = ko.make_kriginfo(X, y, kernel=kernel)
+    nk = len(kernel)
+    P = 40
+    pop = rng.uniform(-1.0, 1.0, (P, d))
+    if tv:
+        pop = np.hstack([pop, rng.uniform(-1, 1, (P, 1))])
+    if nk > 1:
+        pop = np.hstack([pop, rng.uniform(0.1, 1.0, (P, nk))])
+    nll, inf = kb.likelihood_batch(pop, info, tv)
+    assert np.all(inf == 0)
+    ref = ko.likelihood_population(pop, copy.deepcopy(info), tv, check_pd=False)
+    conds = conds_of(info, pop) if not tv else conds_of(info, np.delete(pop, d, 1))
+    rel = np.abs(nll - ref) / np.maximum(np.abs(ref), 1.0)
+    assert np.all(rel < np.array([nll_tol(c) for c in conds])), (rel / np.array([nll_tol(c) for c in conds])).max()
+    assert int(np.argmin(nll)) == int(np.argmin(ref))
+    # batch composition does not matter: one CTA per candidate, no cross-talk
+    perm = rng.permutation(P)
+    assert np.array_equal(kb.likelihood_batch(pop[perm], info, tv)[0], nll[perm])
+    assert kb.likelihood_batch(pop[7:8], info, tv)[0][0] == nll[7]
+    monkeypatch.setenv("KB200_NO_SMALL_LIK", "1")
+    tile, inf2 = kb.likelihood_batch(pop, info, tv)
+    monkeypatch.delenv("KB200_NO_SMALL_LIK")
+    assert np.all(inf2 == 0)
+    relt = np.abs(nll - tile) / np.maximum(np.abs(tile), 1.0)
+    assert np.all(relt < np.array([nll_tol(c) for c in conds]))
+    assert not np.array_equal(nll, tile) or n <= 32          # (two different kernels really ran)
+
+
+def test_small_n_path_reports_non_positive_definite_candidates(kb):
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (40, 4))
+    info = ko.make_kriginfo(X, np.ones((40, 1)) + X[:, :1], pls=rng.standard_normal((4, 2)), n_princomp=2,
+                            kernel=("exponential",))
+    good = ko.make_kriginfo(X, np.ones((40, 1)) + X[:, :1])
+    nll, inf = kb.likelihood_batch(np.array([[0.0, 0.0], [-0.5, 0.3]]), info, False)
+    assert np.all(inf > 0) and np.all(inf <= 40) and np.all(np.isinf(nll))
+    nll, inf = kb.likelihood_batch(np.zeros((3, 4)), good, False)
+    assert np.all(inf == 0) and np.all(np.isfinite(nll))
 
 
 # ------------------------------------------------------------------ LOOCV (SURVEY §8 row f2)
