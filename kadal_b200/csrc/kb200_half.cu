@@ -97,10 +97,16 @@ __device__ __noinline__ int potf2_32_warp_t(double* S, int o, double* dinv, doub
   double* row = S + tri(o + lane) + o;
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? row[c] : 0.0;
+  // The lane's own diagonal entry is tracked in a register of its own: its update by column k is -l * l with the
+  // lane's OWN l (the same fma, the same bits as a[lane] -= l * lb[lane]), so the chain from one pivot to the next
+  // is shuffle -> rsqrt + Newton -> l -> one fma, without the shared-memory round trip of the column broadcast
+  // (which only feeds the off-diagonal entries and runs beside the next pivot's square root): ~350 -> ~200 cycles
+  // per pivot, 128 strictly sequential pivots per diagonal tile.
+  double dg = row[lane];
   int bad = 0;
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    double piv = __shfl_sync(FULLMASK, a[k], k);
+    double piv = __shfl_sync(FULLMASK, dg, k);
     const bool ok = piv > 0.0;
     bad = (!ok && bad == 0) ? o + k + 1 : bad;
     piv = ok ? piv : 1.0;
@@ -108,6 +114,7 @@ __device__ __noinline__ int potf2_32_warp_t(double* S, int o, double* dinv, doub
     double dk, h;
     sqrt_rsqrt(piv, dk, h);
     const double l = a2 * h;
+    dg = fma(-l, l, dg);
     double* lb = lbuf + (k & 1) * 32;
     lb[lane] = l;
     __syncwarp();

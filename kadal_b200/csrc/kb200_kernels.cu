@@ -247,6 +247,7 @@ corr_tile_kernel(CorrArgs A) {
       if (gp < A.npts) {
         v = A.xpts[(size_t)gp * d + k];
         v = standardize1(v, A.normtype, A.norm_a ? A.norm_a[k] : 0.0, A.norm_b ? A.norm_b[k] : 1.0);
+        if (FAST && !KB200_PREDICT_EXACT_DIV) v *= cand[A.spec.ntheta + k];   // pre-scaled by RN(1/theta_k): corr_quad_gauss_scaled
       }
       As[r * lda + k] = v;
     }
@@ -260,7 +261,9 @@ corr_tile_kernel(CorrArgs A) {
     for (int idx = tid; idx < TB * d; idx += CORR_THREADS) {
       int c = idx / d, k = idx - c * d;
       int gc = tj * TB + c;
-      Bt[k * TB + c] = (gc < A.n) ? A.X[(size_t)gc * d + k] : 0.0;
+      double v = (gc < A.n) ? A.X[(size_t)gc * d + k] : 0.0;
+      if (FAST && MODE == CORR_PREDICT && !KB200_PREDICT_EXACT_DIV) v *= cand[A.spec.ntheta + k];
+      Bt[k * TB + c] = v;
     }
     __syncthreads();
     double* tile;
@@ -1588,6 +1591,17 @@ constexpr int PS_MAXD = 8;
 // sum_k (a_k - b_k)^2 / theta_k^2 for two neighbouring samples, numpy's order for d <= 8
 __device__ __forceinline__ void gauss_pair_sum(int d, const double* th2, const double* a, const double* bt2,
                                                double& S0, double& S1) {
+  if (!KB200_PREDICT_EXACT_DIV) {   // coordinates pre-scaled by RN(1/theta_k) (kb200_corr.cuh:corr_quad_gauss_scaled)
+    S0 = 0.0; S1 = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double ak = a[k];
+      const double2 b = *reinterpret_cast<const double2*>(bt2 + k * 256);
+      const double d0 = ak - b.x, d1 = ak - b.y;
+      S0 = fma(d0, d0, S0);
+      S1 = fma(d1, d1, S1);
+    }
+    return;
+  }
   auto term = [&](int k, double& t0, double& t1) {
     const double ak = a[k];
     const double2 b = *reinterpret_cast<const double2*>(bt2 + k * 256);
@@ -1687,7 +1701,9 @@ predict_small_kernel(PredSmallArgs A) {
   for (int idx = tid; idx < nt * 1024; idx += CH_THREADS) W8s[idx] = A.W8[idx];
   for (int idx = tid; idx < d * 256; idx += CH_THREADS) {
     const int k = idx >> 8, c = idx & 255;
-    Bt[idx] = c < n ? A.X[(size_t)c * d + k] : 0.0;
+    double v = c < n ? A.X[(size_t)c * d + k] : 0.0;
+    if (!KB200_PREDICT_EXACT_DIV) v *= A.cand[A.ntheta + k];
+    Bt[idx] = v;
   }
   for (int idx = tid; idx < 256; idx += CH_THREADS) {
     alph[idx] = idx < nt * TB ? A.alpha[idx] : 0.0;
@@ -1757,6 +1773,7 @@ predict_small_kernel(PredSmallArgs A) {
       const long gp = (long)pt * TB + r;
       double v = 0.0;
       if (gp < A.npts) v = standardize1(A.xpts[(size_t)gp * d + k], A.normtype, A.norm_a ? A.norm_a[k] : 0.0, A.norm_b ? A.norm_b[k] : 1.0);
+      if (!KB200_PREDICT_EXACT_DIV) v *= A.cand[A.ntheta + k];
       As[r * lda + k] = v;
     }
     __syncthreads();

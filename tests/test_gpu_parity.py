@@ -328,7 +328,7 @@ def test_c2_every_candidate_against_live_reference(kb, c2, golden_c2_full, golde
                 "median_err_vs_truth_reference_in_cond_ulp": float(np.median(err_ref / (cond * ulp)))}
             assert not bad.any(), (pop, name, np.flatnonzero(bad)[:8], rel[bad][:8], err[bad][:8], err_ref[bad][:8])
             # and as a population the CUDA path is the more accurate of the two
-            assert np.median(err) <= np.median(err_ref) and err.max() <= max(err_ref.max(), TOL_NLL)
+            assert np.median(err) <= max(np.median(err_ref), 1e-15) and err.max() <= max(err_ref.max(), TOL_NLL)
     print("C2 parity counts:", json.dumps(counts))
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
@@ -998,7 +998,10 @@ def test_small_n_in_shared_memory_likelihood_against_oracle_and_tile_path(kb, mo
         pop = np.hstack([pop, rng.uniform(-1, 1, (P, 1))])
     if nk > 1:
         pop = np.hstack([pop, rng.uniform(0.1, 1.0, (P, nk))])
+    from kadal_b200.model import model_for
+    l0 = model_for(info).launch_count()
     nll, inf = kb.likelihood_batch(pop, info, tv)
+    assert model_for(info).launch_count() - l0 == 3          # decode, lik_small_kernel, lik_finalize_kernel
     assert np.all(inf == 0)
     ref = ko.likelihood_population(pop, copy.deepcopy(info), tv, check_pd=False)
     conds = conds_of(info, pop) if not tv else conds_of(info, np.delete(pop, d, 1))
@@ -1010,12 +1013,15 @@ def test_small_n_in_shared_memory_likelihood_against_oracle_and_tile_path(kb, mo
     assert np.array_equal(kb.likelihood_batch(pop[perm], info, tv)[0], nll[perm])
     assert kb.likelihood_batch(pop[7:8], info, tv)[0][0] == nll[7]
     monkeypatch.setenv("KB200_NO_SMALL_LIK", "1")
+    l0 = model_for(info).launch_count()
     tile, inf2 = kb.likelihood_batch(pop, info, tv)
+    assert model_for(info).launch_count() - l0 > 3           # assembly, diagonal / panel tiles, finalize
     monkeypatch.delenv("KB200_NO_SMALL_LIK")
     assert np.all(inf2 == 0)
     relt = np.abs(nll - tile) / np.maximum(np.abs(tile), 1.0)
     assert np.all(relt < np.array([nll_tol(c) for c in conds]))
-    assert not np.array_equal(nll, tile) or n <= 32          # (two different kernels really ran)
+    if n <= 128:      # one tile: the same blocked POTF2 on the same Psi bits -> the same result, bit for bit
+        assert np.array_equal(nll, tile)
 
 
 def test_small_n_path_reports_non_positive_definite_candidates(kb):

@@ -30,6 +30,23 @@ b = reliability.akmcs_reductions(xp, info, group=None) if world == 1 else None
 U = np.abs(one["pred"]) / one["s"]
 assert a["minUloc"] == int(np.argmin(U)) and abs(a["minU"] - U.min()) <= 1e-12 * U.min(), (a["minUloc"], int(np.argmin(U)))
 assert abs(a["Pf"] - np.mean(one["pred"] <= 0)) < 1e-15
+# the same population resident in HBM as row shards (kb200_akmcs_reduce_dev): identical scalars on every rank
+dp = reliability.DevicePopulation(xp[lo:hi])
+a2 = reliability.akmcs_reductions(dp, info, group=dist.group.WORLD)
+assert a2 == a, (a2, a)
+# Saltelli sums with A, B drawn on the device, rows sharded: equal (to summation order) to one rank doing all rows
+sets = [(k,) for k in range(d)]
+N = 200_003
+lo2, hi2 = -np.ones(2 * d), np.ones(2 * d)
+g = sensitivity.sobol_sums_generated(N, info, sets, lo2, hi2, group=dist.group.WORLD)
+if g is not None:
+    from kadal_b200 import sampling
+    _, S = sampling.sampling("sobolnew", 2 * d, N, result="real", upbound=hi2, lobound=lo2)
+    r0, r1 = parallel.shard_bounds(N, world, rank)
+    h = sensitivity.sobol_sums(np.ascontiguousarray(S[r0:r1, :d]), np.ascontiguousarray(S[r0:r1, d:]), info, sets,
+                               group=dist.group.WORLD)
+    for u, v in zip(g, h):
+        assert np.array_equal(u, v), "device-generated Saltelli sums differ from the host-generated plan"
 print("rank", rank, "of", world, "on", parallel.comm_device(), "ok: argmin", i, "Pf", a["Pf"], "minUloc", a["minUloc"], flush=True)
 dist.barrier()
 dist.destroy_process_group()
