@@ -818,6 +818,19 @@ def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
     pts = nc / (ms * 1e-3)
     out["c5_kpls_score"] = {"workload": "C5: pred + SSqr (EHVI inputs) over %d candidates per GPU" % nc, "pts_per_s_per_gpu": pts,
                             "ms": ms, "fp64_tflops_algorithmic": pts * (n * n + n * (3 * d + 6 * h + 20)) / 1e12}
+    # the batch a MOBO generation really scores: n_pop = 1500 candidates per objective (EHVIcomputation.py:169-172),
+    # right-looking sweep (few point tiles, 32 sample tiles); with the left-looking sweep forced beside it
+    nc2 = 1500
+    fn = lambda: m.predict_dev(xs.data_ptr(), nc2, _capi.OUT_PRED | _capi.OUT_SSQR, [o1.data_ptr(), o2.data_ptr(), 0, 0, 0, 0, 0],
+                               normtype=_capi.NORM_DEFAULT, norm_a=lb, norm_b=ub, stream=stream)
+    ms_rl = timed(fn, 5)
+    os.environ["KB200_PRED_RL"] = "0"
+    ms_ll = timed(fn, 5)
+    del os.environ["KB200_PRED_RL"]
+    out["c5_kpls_score_generation"] = {"workload": "C5: pred + SSqr of ONE generation of %d candidates per GPU (n=4000, d=100, h=3)" % nc2,
+                                       "ms": ms_rl, "pts_per_s_per_gpu": nc2 / (ms_rl * 1e-3),
+                                       "fp64_tflops_algorithmic": nc2 / (ms_rl * 1e-3) * (n * n + n * (3 * d + 6 * h + 20)) / 1e12,
+                                       "left_looking_sweep_ms": ms_ll}
     m.close()
     out["c5_ehvi3d"] = ehvi3d_bench(rank, local_rank, world, torch, timed, dev)
     return out

@@ -160,7 +160,7 @@ struct kb200_model {
   DevBuf tiles, W, Z, cand, xdev, nll, info, logdet, sigma2, beta, btb, resid, rhs2, sol2;
   // predictor state
   bool has_pred = false;
-  DevBuf pL, pW, palpha, pw, pcand;
+  DevBuf pL, pW, palpha, pw, pcand, pscale;
   double pbeta = 0, psigma2 = 0, pbtb = 0;
   // state of the last kb200_fit_state / kb200_fit_append that a one-sample append continues from:
   // Z = L^-1 [y F] ([nq][npad]) and sum ln L_ii
@@ -396,7 +396,7 @@ void kb200_model_destroy(kb200_model* m) {
   cudaSetDevice(m->device);
   DevBuf* bufs[] = {&m->X, &m->R, &m->pls, &m->pls2, &m->kplanes_sq, &m->kplanes_abs, &m->tiles, &m->W, &m->Z, &m->cand, &m->xdev,
                     &m->nll, &m->info, &m->logdet, &m->sigma2, &m->beta, &m->btb, &m->resid,
-                    &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand, &m->pZ, &m->plogdet, &m->appdiag, &m->appvec, &m->trwork,
+                    &m->rhs2, &m->sol2, &m->pL, &m->pW, &m->palpha, &m->pw, &m->pcand, &m->pscale, &m->pZ, &m->plogdet, &m->appdiag, &m->appvec, &m->trwork,
                     &m->norm_a, &m->norm_b, &m->stats, &m->akpart,
                     &m->Rw, &m->sobB, &m->sobC, &m->sobY, &m->sobAcc, &m->sobPart, &m->sobMask, &m->sobDir};
   cudaDeviceSynchronize();   // nothing of this model is in flight when its buffers go back to the pool
@@ -909,6 +909,11 @@ static int install_predictor(kb200_model* m, const double* tiles, const double* 
   if (W != m->pW.d()) CK(cudaMemcpyAsync(m->pW.p, W, wb, cudaMemcpyDeviceToDevice, st));
   if (d_cand_row != m->pcand.d())
     CK(cudaMemcpyAsync(m->pcand.p, d_cand_row, (size_t)m->cstride * 8, cudaMemcpyDeviceToDevice, st));
+  if (m->nkernel == 1 && m->kid[0] == K_GAUSS) {
+    CK(m->pscale.reserve((size_t)m->d * 8));
+    CK(launch_pred_scale(m->pcand.d(), m->pls2.d(), m->d, m->ntheta, m->h > 0 ? 1 : 0, m->pscale.d(), st));
+    m->launches++;
+  }
   CK(cudaMemcpyAsync(m->rhs2.d(), d_resid, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(m->rhs2.d() + m->npad, d_b, (size_t)m->npad * 8, cudaMemcpyDeviceToDevice, st));
   BackArgs b;
@@ -1276,6 +1281,7 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
   c.n = m->n; c.nt = m->nt; c.X = m->X.d();
   c.cand = m->pcand.d(); c.cand_stride = m->cstride;
   c.normtype = normtype; c.norm_a = m->norm_a.d(); c.norm_b = m->norm_b.d();
+  c.pscale = (m->nkernel == 1 && m->kid[0] == K_GAUSS) ? m->pscale.d() : nullptr;
   c.alpha = m->palpha.d();
   EpiArgs e;
   memset(&e, 0, sizeof(e));
@@ -1286,6 +1292,26 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     c.xpts = d_x; c.npts = npts; c.out = nullptr; c.wvec = nullptr;
     c.fdot = sl.fdot.d(); c.udot = nullptr;
     const long tiles = (npts + TB - 1) / TB;
+    if (m->nt >= 2 && tiles < m->sm_count) {
+      // few points, many sample tiles: one CTA per (point tile, sample tile) pair, partial sums added by the epilogue
+      const long pstride = (npts + 1) & ~1L;
+      CK(sl.fdot.reserve((size_t)m->nt * pstride * 8));
+      CorrArgs cc = c;
+      cc.fdot = sl.fdot.d();
+      cc.tj_split = 1;
+      cc.part_stride = pstride;
+      {
+        Timed t(m, KB200_PROF_PSI, st);
+        CK(launch_corr(cc, (int)tiles, m->nt, st));
+      }
+      e.npts = npts; e.fdot = sl.fdot.d(); e.pred = outs[0];
+      e.nparts = m->nt; e.part_stride = pstride;
+      {
+        Timed t(m, KB200_PROF_EPILOGUE, st);
+        CK(launch_epilogue(e, st));
+      }
+      return 0;
+    }
     for (long t0 = 0; t0 < tiles; t0 += 1 << 20) {   // grid.x limit is 2^31-1; keep launches bounded
       const long tn = std::min<long>(1 << 20, tiles - t0);
       CorrArgs cc = c;
@@ -1311,7 +1337,7 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     PredSmallArgs ps;
     memset(&ps, 0, sizeof(ps));
     ps.n = m->n; ps.d = m->d; ps.nt = m->nt; ps.ntheta = m->ntheta;
-    ps.X = m->X.d(); ps.cand = m->pcand.d(); ps.L = m->pL.d(); ps.W8 = m->pW.d();
+    ps.X = m->X.d(); ps.cand = m->pcand.d(); ps.pscale = m->pscale.d(); ps.L = m->pL.d(); ps.W8 = m->pW.d();
     ps.alpha = m->palpha.d(); ps.wvec = m->pw.d();
     ps.xpts = d_x; ps.npts = npts; ps.normtype = normtype;
     ps.norm_a = m->norm_a.d(); ps.norm_b = m->norm_b.d();
@@ -1328,29 +1354,63 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
   const long ct = std::min(chunk_tiles_for(m), (npts + TB - 1) / TB);
   const long cpts = ct * TB;
   CK(sl.chunk.reserve((size_t)ct * m->nt * TILE_ELEMS * 8));
-  CK(sl.udot.reserve((size_t)npts * 8));
   CK(sl.ssq.reserve((size_t)cpts * 8));
   CholArgs pa = chol_args(m, m->pL.d(), m->pW.d(), nullptr, nullptr, nullptr);
   pa.pred_mode = 1;
   pa.chunk = sl.chunk.d();
   pa.ssq = sl.ssq.d();
+  // Few point tiles against many sample tiles (candidate scoring: EHVIcomputation.py:169-172 predicts n_pop ~ 10^2..10^3
+  // candidates per generation on a model of n = 4000): the left-looking sweep has 2 x tiles CTAs per launch and a GEMM of
+  // depth 128 j in each -- a handful of SMs busy for nt sequential launches.  Right-looking instead: solve tile j, then
+  // update all nt - 1 - j later tiles of every point-tile row at once; and the psi kernel runs one CTA per (point tile,
+  // sample tile) pair with per-sample-tile partial sums of psi^T alpha, psi^T w added in order by the epilogue.
+  // Rounds differently from the left-looking sweep (~1e-13 relative on the variance); chosen by batch size only.
+  const int env_prl = getenv("KB200_PRED_RL") ? atoi(getenv("KB200_PRED_RL")) : -1;    // (read per call: A/B tests)
+  const bool half_ok = m->half_mode != 0 && !pa.naive;
   for (long p0 = 0; p0 < npts; p0 += cpts) {
     const long np = std::min(cpts, npts - p0);
     const int tiles = (int)((np + TB - 1) / TB);
+    const bool rl = half_ok && m->nt >= 3 && (env_prl >= 0 ? env_prl != 0 : 2 * tiles < 2 * m->sm_count);
+    const bool split = rl || (m->nt >= 2 && tiles < m->sm_count);
+    const long pstride = (np + 1) & ~1L;
+    CK(sl.udot.reserve((size_t)(split ? (size_t)m->nt * pstride : (size_t)npts) * 8));
+    if (split) CK(sl.fdot.reserve(std::max((size_t)npts, (size_t)m->nt * pstride) * 8));
     CorrArgs cc = c;
     cc.xpts = d_x + (size_t)p0 * m->d; cc.npts = np; cc.out = sl.chunk.d();
-    cc.wvec = m->pw.d(); cc.fdot = sl.fdot.d() + p0; cc.udot = sl.udot.d() + p0;
+    cc.wvec = m->pw.d();
+    cc.fdot = split ? sl.fdot.d() : sl.fdot.d() + p0;
+    cc.udot = split ? sl.udot.d() : sl.udot.d() + p0;
+    cc.tj_split = split ? 1 : 0;
+    cc.part_stride = pstride;
     {
       Timed t(m, KB200_PROF_PSI, st);
-      CK(launch_corr(cc, tiles, 1, st));
+      CK(launch_corr(cc, tiles, split ? m->nt : 1, st));
     }
     for (int j = 0; j < m->nt; ++j) {
+      if (rl) {
+        {
+          Timed t(m, KB200_PROF_PREDSOLVE, st);
+          pa.rl_mode = 1;
+          CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));
+        }
+        if (j + 1 < m->nt) {
+          Timed t(m, KB200_PROF_PREDSOLVE, st);
+          pa.rl_mode = 2;
+          CK(launch_chol_panel_half(pa, j, 2 * tiles * (m->nt - 1 - j), 1, st));
+        }
+        continue;
+      }
       Timed t(m, KB200_PROF_PREDSOLVE, st);
-      if (m->half_mode != 0 && !pa.naive) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // bit-identical to the full-SM kernel
+      if (half_ok) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // bit-identical to the full-SM kernel
       else CK(launch_chol_panel(pa, j, tiles, 1, st));
     }
     EpiArgs ee = e;
-    ee.npts = np; ee.fdot = sl.fdot.d() + p0; ee.udot = sl.udot.d() + p0; ee.ssq = sl.ssq.d();
+    ee.npts = np;
+    ee.fdot = split ? sl.fdot.d() : sl.fdot.d() + p0;
+    ee.udot = split ? sl.udot.d() : sl.udot.d() + p0;
+    ee.nparts = split ? m->nt : 1;
+    ee.part_stride = pstride;
+    ee.ssq = sl.ssq.d();
     ee.pred = outs[0] ? outs[0] + p0 : nullptr;
     ee.ssqr = outs[1] ? outs[1] + p0 : nullptr;
     ee.s = outs[2] ? outs[2] + p0 : nullptr;

@@ -686,7 +686,20 @@ chol_panel_half_kernel(CholArgs A, int j) {
   const double *rowA, *rowB, *Ljj, *W8j;
   double* Cij;
   long ssq_base = 0;
-  if (A.pred_mode) {
+  if (A.pred_mode && A.rl_mode >= 2) {
+    // prediction, right-looking (few point tiles, many sample tiles): after V_j = (psi_j - ...) L_jj^-T every later tile of
+    // the point-tile row is updated at once, psi_i -= V_j L_ij^T for i > j: (nt - 1 - j) x more CTAs than the left-looking
+    // launch of column j has.  blockIdx.x >> 1 = pt (nt - 1 - j) + a, i = j + 1 + a.
+    const int M = A.nt - 1 - j;
+    const long t = blockIdx.x >> 1, pt = t / M;
+    const int i = j + 1 + (int)(t - pt * M);
+    double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
+    rowA = base + (size_t)j * TILE_ELEMS;                            // V_j, 8 slabs
+    rowB = A.L + (size_t)tri_index(i, j) * TILE_ELEMS;               // L_ij, 8 slabs
+    Cij = base + (size_t)i * TILE_ELEMS;
+    Ljj = A.L;                                                       // unused
+    W8j = A.W8 + (size_t)j * 1024;                                   // fetched, unused
+  } else if (A.pred_mode) {
     const long pt = blockIdx.x >> 1;
     double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
     rowA = base;

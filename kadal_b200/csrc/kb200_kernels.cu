@@ -220,12 +220,12 @@ corr_tile_kernel(CorrArgs A) {
     m = blockIdx.y;
   } else {
     ti = blockIdx.x;  // point tile
-    tj0 = 0;
-    tj1 = A.nt;
+    tj0 = A.tj_split ? blockIdx.y : 0;
+    tj1 = A.tj_split ? blockIdx.y + 1 : A.nt;
     m = 0;
   }
   const double* cand = A.cand + m * A.cand_stride;
-  if (FAST && tid < 2 * d) {   // theta2 | rtheta2 are adjacent; second copy interleaved {theta2_k, rtheta2_k} for one 16-byte load
+  if (FAST && (MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV) && tid < 2 * d) {   // theta2 | rtheta2 are adjacent; second copy interleaved {theta2_k, rtheta2_k} for one 16-byte load
     const double v = cand[2 * A.spec.ntheta + tid];
     th2[tid] = v;
     th2[2 * d + 2 * (tid % d) + tid / d] = v;
@@ -247,7 +247,7 @@ corr_tile_kernel(CorrArgs A) {
       if (gp < A.npts) {
         v = A.xpts[(size_t)gp * d + k];
         v = standardize1(v, A.normtype, A.norm_a ? A.norm_a[k] : 0.0, A.norm_b ? A.norm_b[k] : 1.0);
-        if (FAST && !KB200_PREDICT_EXACT_DIV) v *= cand[A.spec.ntheta + k];   // pre-scaled by RN(1/theta_k): corr_quad_gauss_scaled
+        if (FAST && !KB200_PREDICT_EXACT_DIV) v *= A.pscale[k];   // pre-scaled (RN(1/theta_k)): corr_quad_gauss_scaled
       }
       As[r * lda + k] = v;
     }
@@ -262,7 +262,7 @@ corr_tile_kernel(CorrArgs A) {
       int c = idx / d, k = idx - c * d;
       int gc = tj * TB + c;
       double v = (gc < A.n) ? A.X[(size_t)gc * d + k] : 0.0;
-      if (FAST && MODE == CORR_PREDICT && !KB200_PREDICT_EXACT_DIV) v *= cand[A.spec.ntheta + k];
+      if (FAST && MODE == CORR_PREDICT && !KB200_PREDICT_EXACT_DIV) v *= A.pscale[k];
       Bt[k * TB + c] = v;
     }
     __syncthreads();
@@ -289,8 +289,9 @@ corr_tile_kernel(CorrArgs A) {
       const int row = 8 * (warp + 8 * rgi) + g;
       const long gp = (long)ti * TB + row;
       if (ch == 0 && gp < A.npts) {
-        A.fdot[gp] = f;
-        if (A.udot) A.udot[gp] = u;
+        const long o = A.tj_split ? (long)blockIdx.y * A.part_stride + gp : gp;
+        A.fdot[o] = f;
+        if (A.udot) A.udot[o] = u;
       }
     }
   }
@@ -1566,8 +1567,14 @@ __device__ __forceinline__ void epilogue_point(const EpiArgs& A, long i, double 
 __global__ void predict_epilogue_kernel(EpiArgs A) {
   long zero_ss = 0;
   int any = 0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.npts; i += (long)gridDim.x * blockDim.x)
-    epilogue_point(A, i, A.fdot[i], A.need_var ? A.udot[i] : 0.0, A.need_var ? A.ssq[i] : 0.0, zero_ss, any);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.npts; i += (long)gridDim.x * blockDim.x) {
+    double f = A.fdot[i], u = A.need_var ? A.udot[i] : 0.0;
+    for (int p = 1; p < A.nparts; ++p) {           // per-sample-tile partial sums, added in tile order (deterministic)
+      f += A.fdot[(long)p * A.part_stride + i];
+      if (A.need_var) u += A.udot[(long)p * A.part_stride + i];
+    }
+    epilogue_point(A, i, f, u, A.need_var ? A.ssq[i] : 0.0, zero_ss, any);
+  }
   if (A.stats) {
     if (zero_ss) atomicAdd(reinterpret_cast<unsigned long long*>(A.stats), (unsigned long long)zero_ss);
     if (any) atomicOr(reinterpret_cast<unsigned long long*>(A.stats + 1), 1ull);
@@ -1702,14 +1709,14 @@ predict_small_kernel(PredSmallArgs A) {
   for (int idx = tid; idx < d * 256; idx += CH_THREADS) {
     const int k = idx >> 8, c = idx & 255;
     double v = c < n ? A.X[(size_t)c * d + k] : 0.0;
-    if (!KB200_PREDICT_EXACT_DIV) v *= A.cand[A.ntheta + k];
+    if (!KB200_PREDICT_EXACT_DIV) v *= A.pscale[k];
     Bt[idx] = v;
   }
   for (int idx = tid; idx < 256; idx += CH_THREADS) {
     alph[idx] = idx < nt * TB ? A.alpha[idx] : 0.0;
     wv[idx] = idx < nt * TB ? A.wvec[idx] : 0.0;
   }
-  if (tid < d) { th2[tid] = A.cand[2 * A.ntheta + tid]; th2[PS_MAXD + tid] = A.cand[3 * A.ntheta + tid]; }
+  if (KB200_PREDICT_EXACT_DIV && tid < d) { th2[tid] = A.cand[2 * A.ntheta + tid]; th2[PS_MAXD + tid] = A.cand[3 * A.ntheta + tid]; }
   const double w0 = A.cand[4 * A.ntheta];
   __syncthreads();
 
@@ -1773,7 +1780,7 @@ predict_small_kernel(PredSmallArgs A) {
       const long gp = (long)pt * TB + r;
       double v = 0.0;
       if (gp < A.npts) v = standardize1(A.xpts[(size_t)gp * d + k], A.normtype, A.norm_a ? A.norm_a[k] : 0.0, A.norm_b ? A.norm_b[k] : 1.0);
-      if (!KB200_PREDICT_EXACT_DIV) v *= A.cand[A.ntheta + k];
+      if (!KB200_PREDICT_EXACT_DIV) v *= A.pscale[k];
       As[r * lda + k] = v;
     }
     __syncthreads();
@@ -2075,7 +2082,11 @@ cudaError_t launch_corr(const CorrArgs& a, int grid_x, int grid_y, cudaStream_t 
     }
     g_corr_attr[dev] = sm;
   }
-  const bool fast = a.spec.nkernel == 1 && a.spec.kid[0] == K_GAUSS && !a.spec.kpls;
+  // Gaussian fast path: the likelihood's assembly for plain distances only (numpy's operations bit for bit); prediction
+  // whenever the caller provides the per-dimension scales -- a KPLS-Gaussian correlation is a Gaussian in d dimensions with
+  // weights sum_c pls_kc^2 / theta_c^2 (kernelfunc.py:42-47), 2 d FP64 instructions per pair instead of d (2 + 3 h)
+  const bool fast = a.spec.nkernel == 1 && a.spec.kid[0] == K_GAUSS &&
+                    (a.mode == CORR_PREDICT ? (a.pscale != nullptr && !KB200_PREDICT_EXACT_DIV) || !a.spec.kpls : !a.spec.kpls);
   // One kernel per class of d where that measured faster (r1s A/B, profiles/r1s_ab_assembly_pairing.log): d < 8 both modes
   // (prediction at d = 6 2.09 -> 1.91 ms per 2e6 points), 8 <= d < 16 prediction (8.11 -> 7.91 ms); the kernel holding all
   // three summation schemes (4) elsewhere: specialised, ptxas spills in the assembly at 8 <= d < 16 (1.53 -> 1.65 ms) and
@@ -2252,7 +2263,25 @@ cudaError_t launch_predict_small(const PredSmallArgs& a, int sm_count, cudaStrea
 }
 
 bool predict_small_supported(int n, int d, int nkernel, int kid0, int kpls) {
-  return n <= 2 * TB && d <= PS_MAXD && nkernel == 1 && kid0 == K_GAUSS && !kpls;
+  return n <= 2 * TB && d <= PS_MAXD && nkernel == 1 && kid0 == K_GAUSS && (!kpls || !KB200_PREDICT_EXACT_DIV);
+}
+
+// scales of the pre-scaled prediction coordinates (kb200_corr.cuh:corr_quad_gauss_scaled)
+__global__ void pred_scale_kernel(const double* __restrict__ cand, const double* __restrict__ pls2, int d, int ntheta, int kpls,
+                                  double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d) return;
+  if (!kpls) {
+    out[k] = cand[ntheta + k];                       // RN(1 / theta_k)
+  } else {
+    double s = 0.0;                                  // sum_c pls_kc^2 * RN(1 / theta_c^2)
+    for (int c = 0; c < ntheta; ++c) s = fma(pls2[(size_t)k * ntheta + c], cand[3 * ntheta + c], s);
+    out[k] = sqrt(s);
+  }
+}
+cudaError_t launch_pred_scale(const double* cand_row, const double* pls2, int d, int ntheta, int kpls, double* out, cudaStream_t st) {
+  pred_scale_kernel<<<(d + 127) / 128, 128, 0, st>>>(cand_row, pls2, d, ntheta, kpls, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_fp64_probe(int blocks, int iters, int mode, double* sink, cudaStream_t st) {

@@ -25,10 +25,14 @@ struct CorrArgs {
   int normtype;          // 0 none, 1 'default' (lb,ub), 2 'std' (mean,std)
   const double* norm_a;
   const double* norm_b;
+  const double* pscale;  // [d] prediction, single Gaussian kernel: per-dimension scale of the pre-scaled coordinates
+                         //     (RN(1/theta_k); KPLS: sqrt(sum_c pls_kc^2 / theta_c^2)), or null (general path)
   const double* alpha;   // [nt*128] zero padded
   const double* wvec;    // [nt*128] zero padded, or null
-  double* fdot;          // [npts]  psi^T alpha
+  double* fdot;          // [npts]  psi^T alpha   (tj_split: [nt][part_stride] partial sums per sample tile)
   double* udot;          // [npts]  psi^T w
+  int tj_split;          // prediction: blockIdx.y = sample tile, one tile pair per CTA (few point tiles: fills the machine)
+  long part_stride;
 };
 
 struct CholArgs {
@@ -99,6 +103,8 @@ struct EpiArgs {
   int limit_ge, need_var;
   const double* fdot;
   const double* udot;
+  int nparts;            // > 1: fdot / udot are nparts partial sums, part_stride apart, added in order
+  long part_stride;
   const double* ssq;
   double *pred, *ssqr, *s, *ei, *poi, *pof, *ufun;
   unsigned long long* stats;   // [0] = #(SSqr == 0), [1] = any nonzero EI term
@@ -108,6 +114,7 @@ struct PredSmallArgs {
   int n, d, nt, ntheta;
   const double* X;       // [n][d] training inputs
   const double* cand;    // parameter row of the fitted model
+  const double* pscale;  // [d] per-dimension scale of the pre-scaled coordinates (see CorrArgs)
   const double* L;       // predictor tiles L_00, L_10, L_11
   const double* W8;      // [nt][1024]
   const double* alpha;   // [nt*128]
@@ -198,6 +205,8 @@ cudaError_t launch_append_row(double* tiles, const double* v, int n_prev, int nt
 cudaError_t launch_loo(const double* y, const double* alpha, const double* w, const double* ssq, double btb, int n,
                        long p0, int np, double* out, cudaStream_t st);
 cudaError_t launch_predict_small(const PredSmallArgs& a, int sm_count, cudaStream_t st);
+// per-dimension coordinate scales of a single-Gaussian-kernel predictor (pls2 = squared KPLS coefficients [d][h] or null)
+cudaError_t launch_pred_scale(const double* cand_row, const double* pls2, int d, int ntheta, int kpls, double* out, cudaStream_t st);
 bool predict_small_supported(int n, int d, int nkernel, int kid0, int kpls);
 cudaError_t launch_chol_diag(const CholArgs& a, int j, int nmat, cudaStream_t st);
 cudaError_t launch_chol_panel(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);

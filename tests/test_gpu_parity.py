@@ -919,6 +919,33 @@ def test_c4_full_model_prediction_against_oracle(kb):
     assert relerr(pv["ssqr"], rv[1].ravel(), 1e-6 * s2) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
 
 
+def test_small_batches_on_a_large_model_take_the_right_looking_sweep(kb, monkeypatch):
+    """Candidate scoring predicts a few hundred points on a model of many sample tiles (C4: nt = 7): one CTA per (point tile,
+    sample tile) pair for psi and a right-looking solve / update sweep instead of nt sequential left-looking launches on a
+    handful of SMs.  Both sweeps against the oracle, and against each other (same arithmetic, another order)."""
+    w = ko.workload("C4")
+    info = ko.make_kriginfo(w["X"], w["y"])
+    kb.likelihood(w["theta"].copy(), info, "all", False)
+    ref = copy.deepcopy(info)
+    ko.likelihood(w["theta"].copy(), ref, "all", False, check_pd=False)
+    cond = np.linalg.cond(ref["Psi"] + np.eye(800) * 1e-6)
+    s2 = float(np.asarray(ref["SigmaSqr"]).ravel()[0])
+    xp = np.random.default_rng(99).uniform(-1, 1, (777, 20))
+    rv = ko.prediction(xp, ref, ["pred", "SSqr"])
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KB200_PRED_RL", mode)
+        got[mode] = kb.predict_arrays(xp, info, ("pred", "ssqr"))
+        assert relerr(got[mode]["pred"], rv[0].ravel()) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+        assert relerr(got[mode]["ssqr"], rv[1].ravel(), 1e-6 * s2) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
+    monkeypatch.delenv("KB200_PRED_RL")
+    assert relerr(got["1"]["ssqr"], got["0"]["ssqr"], 1e-6 * s2) < 1e-9 and not np.array_equal(got["1"]["ssqr"], got["0"]["ssqr"])
+    auto = kb.predict_arrays(xp, info, ("pred", "ssqr"))                       # 7 point tiles: right-looking by default
+    assert np.array_equal(auto["ssqr"], got["1"]["ssqr"]) and np.array_equal(auto["pred"], got["1"]["pred"])
+    one = kb.predict_arrays(xp[:1], info, ("pred",))["pred"]                   # mean only, a single point: split psi kernel
+    assert relerr(one, rv[0].ravel()[:1]) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
+
+
 def test_c5_kpls_n4000_factor_and_candidate_scoring(kb):
     """C5: KPLS, d=100, n=4000 (32 tiles per dimension: 528 factor tiles, blocked tensor-core
     Cholesky), 3 PLS components.  The oracle needs a 12.8 GB temporary and ~1 min per evaluation at
