@@ -1364,7 +1364,8 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
   // depth 128 j in each -- a handful of SMs busy for nt sequential launches.  Right-looking instead: solve tile j, then
   // update all nt - 1 - j later tiles of every point-tile row at once; and the psi kernel runs one CTA per (point tile,
   // sample tile) pair with per-sample-tile partial sums of psi^T alpha, psi^T w added in order by the epilogue.
-  // Rounds differently from the left-looking sweep (~1e-13 relative on the variance); chosen by batch size only.
+  // The variance comes out bit-identical to the left-looking sweep (same products, accumulated from -psi in the same
+  // order); the mean's psi^T alpha is summed per sample tile first (~1e-15 relative).  Chosen by batch size only.
   const int env_prl = getenv("KB200_PRED_RL") ? atoi(getenv("KB200_PRED_RL")) : -1;    // (read per call: A/B tests)
   const bool half_ok = m->half_mode != 0 && !pa.naive;
   for (long p0 = 0; p0 < npts; p0 += cpts) {

@@ -922,7 +922,7 @@ def test_c4_full_model_prediction_against_oracle(kb):
 def test_small_batches_on_a_large_model_take_the_right_looking_sweep(kb, monkeypatch):
     """Candidate scoring predicts a few hundred points on a model of many sample tiles (C4: nt = 7): one CTA per (point tile,
     sample tile) pair for psi and a right-looking solve / update sweep instead of nt sequential left-looking launches on a
-    handful of SMs.  Both sweeps against the oracle, and against each other (same arithmetic, another order)."""
+    handful of SMs.  Both sweeps against the oracle, and against each other."""
     w = ko.workload("C4")
     info = ko.make_kriginfo(w["X"], w["y"])
     kb.likelihood(w["theta"].copy(), info, "all", False)
@@ -939,7 +939,10 @@ def test_small_batches_on_a_large_model_take_the_right_looking_sweep(kb, monkeyp
         assert relerr(got[mode]["pred"], rv[0].ravel()) < max(TOL_MEAN, 0.5 * cond * 2.0 ** -53)
         assert relerr(got[mode]["ssqr"], rv[1].ravel(), 1e-6 * s2) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
     monkeypatch.delenv("KB200_PRED_RL")
-    assert relerr(got["1"]["ssqr"], got["0"]["ssqr"], 1e-6 * s2) < 1e-9 and not np.array_equal(got["1"]["ssqr"], got["0"]["ssqr"])
+    # same products accumulated from -psi in the same order k = 0, 1, ... (in registers, or tile by tile through memory):
+    # the two sweeps give the same bits, so a point's variance does not depend on the size of the batch it came in
+    assert np.array_equal(got["1"]["ssqr"], got["0"]["ssqr"])
+    assert relerr(got["1"]["pred"], got["0"]["pred"]) < 1e-13      # psi^T alpha: per-sample-tile partial sums vs one running sum
     auto = kb.predict_arrays(xp, info, ("pred", "ssqr"))                       # 7 point tiles: right-looking by default
     assert np.array_equal(auto["ssqr"], got["1"]["ssqr"]) and np.array_equal(auto["pred"], got["1"]["pred"])
     one = kb.predict_arrays(xp[:1], info, ("pred",))["pred"]                   # mean only, a single point: split psi kernel
