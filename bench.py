@@ -786,8 +786,15 @@ def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
     out["c4_sobol_pred"] = {"workload": "C4: n=800, d=20, 'pred' over %d Saltelli points per GPU" % npts, "pts_per_s_per_gpu": pts,
                             "ms": ms, "fp64_tflops_algorithmic": pts * predict_flops_per_point(800, 20, False) / 1e12,
                             "hbm_gbs_algorithmic": pts * (8 * 20 + 8) / 1e9}
+    o2 = torch.empty(npts, dtype=torch.float64, device=dev)
+    npv = 1_000_000
+    ms = timed(lambda: m.predict_dev(xs.data_ptr(), npv, _capi.OUT_PRED | _capi.OUT_S, [o.data_ptr(), 0, o2.data_ptr(), 0, 0, 0, 0],
+                                     normtype=_capi.NORM_DEFAULT, norm_a=lb, norm_b=ub, stream=stream), 2)
+    out["c4_pred_s"] = {"workload": "C4 model (n=800, d=20): pred + s over %d points per GPU (general tiled path, n > 256)" % npv,
+                        "pts_per_s_per_gpu": npv / (ms * 1e-3), "ms": ms,
+                        "fp64_tflops_algorithmic": npv / (ms * 1e-3) * predict_flops_per_point(800, 20, True) / 1e12}
     m.close()
-    del xs, o
+    del xs, o, o2
     # ---- C5
     rng = np.random.default_rng(11)
     n, d, h = 4000, 100, 3

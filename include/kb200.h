@@ -229,6 +229,11 @@ int kb200_debug_psi(kb200_model* m, const double* x, int nbhyp, int trainvar,
  * last likelihood batch: tiles_per_mat * 16384 doubles */
 int kb200_debug_tiles(kb200_model* m, int cand, double* out);
 
+/* debug / parity: the exponential the PREDICTION kernels use for their (non-positive) arguments (which = 0: libm's
+ * algorithm and coefficients without its denormal path and branch, arguments clamped at -708) or libm's exp itself
+ * (which = 1), element-wise on n host doubles.  The likelihood's Psi always uses libm's exp. */
+int kb200_debug_exp(int device, const double* x, long long n, int which, double* y);
+
 /* Per-kernel-class device timing with CUDA events on the launching stream (bench.py's
  * roofline): enable, run, then read accumulated milliseconds and launch counts. */
 #define KB200_PROF_ASSEMBLE 0   /* corr_tile_kernel, Psi assembly            */

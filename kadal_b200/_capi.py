@@ -82,6 +82,7 @@ SIGNATURES = {
     "kb200_ehvi3d_dev": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p,
                                         ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
                                         ctypes.c_double, c_void_p, c_void_p]),
+    "kb200_debug_exp": (ctypes.c_int, [ctypes.c_int, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p]),
     "kb200_debug_tiles": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p]),
     "kb200_debug_psi": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        ctypes.c_int, c_void_p]),

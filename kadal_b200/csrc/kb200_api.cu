@@ -1980,6 +1980,20 @@ int kb200_debug_tiles(kb200_model* m, int cand, double* out) {
   return 0;
 }
 
+int kb200_debug_exp(int device, const double* x, long long n, int which, double* y) {
+  if (!x || !y) return fail_arg("kb200_debug_exp: null argument");
+  if (n < 1) return 0;
+  CK(cudaSetDevice(device));
+  double* d = nullptr;
+  CK(cudaMalloc((void**)&d, (size_t)2 * n * 8));
+  cudaError_t e = cudaMemcpy(d, x, (size_t)n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_debug_exp(d, (long)n, which, d + n, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(y, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail("kb200_debug_exp", e);
+  return 0;
+}
+
 int kb200_set_groups(kb200_model* m, int ngroups) {
   if (!m) return fail_arg("null model");
   if (ngroups < 1 || ngroups > kb200_model::MAXG) return fail_arg("kb200_set_groups: 1..8 groups");

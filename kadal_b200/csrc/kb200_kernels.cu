@@ -1595,17 +1595,34 @@ constexpr int PS_NST = 3;
 constexpr int PS_LOOK = 1;    // with the one-slab-late release below the ring needs NST >= LOOK + 2
 constexpr int PS_MAXD = 8;
 
+template <int D>
+__device__ __forceinline__ void scaled_pair_sum(const double* a, const double* bt2, double& S0, double& S1) {
+  S0 = 0.0;
+  S1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double ak = a[k];
+    const double2 b = *reinterpret_cast<const double2*>(bt2 + k * 256);
+    const double d0 = ak - b.x, d1 = ak - b.y;
+    S0 = fma(d0, d0, S0);
+    S1 = fma(d1, d1, S1);
+  }
+}
+
 // sum_k (a_k - b_k)^2 / theta_k^2 for two neighbouring samples, numpy's order for d <= 8
 __device__ __forceinline__ void gauss_pair_sum(int d, const double* th2, const double* a, const double* bt2,
                                                double& S0, double& S1) {
   if (!KB200_PREDICT_EXACT_DIV) {   // coordinates pre-scaled by RN(1/theta_k) (kb200_corr.cuh:corr_quad_gauss_scaled)
-    S0 = 0.0; S1 = 0.0;
-    for (int k = 0; k < d; ++k) {
-      const double ak = a[k];
-      const double2 b = *reinterpret_cast<const double2*>(bt2 + k * 256);
-      const double d0 = ak - b.x, d1 = ak - b.y;
-      S0 = fma(d0, d0, S0);
-      S1 = fma(d1, d1, S1);
+    // fully unrolled per d (a uniform switch): no loop counter, compare, branch or address arithmetic per dimension
+    switch (d) {
+      case 1: scaled_pair_sum<1>(a, bt2, S0, S1); break;
+      case 2: scaled_pair_sum<2>(a, bt2, S0, S1); break;
+      case 3: scaled_pair_sum<3>(a, bt2, S0, S1); break;
+      case 4: scaled_pair_sum<4>(a, bt2, S0, S1); break;
+      case 5: scaled_pair_sum<5>(a, bt2, S0, S1); break;
+      case 6: scaled_pair_sum<6>(a, bt2, S0, S1); break;
+      case 7: scaled_pair_sum<7>(a, bt2, S0, S1); break;
+      default: scaled_pair_sum<8>(a, bt2, S0, S1); break;
     }
     return;
   }
@@ -1759,8 +1776,13 @@ predict_small_kernel(PredSmallArgs A) {
         const int col = TB * tile + 8 * ct + 2 * tq;
         double S0, S1;
         gauss_pair_sum(d, th2, arow, Bt + col, S0, S1);
-        e0 = col < n ? __dmul_rn(w0, exp(-0.5 * S0)) : 0.0;
-        e1 = col + 1 < n ? __dmul_rn(w0, exp(-0.5 * S1)) : 0.0;
+        if (KB200_PREDICT_EXACT_DIV) {
+          e0 = col < n ? __dmul_rn(w0, exp(-0.5 * S0)) : 0.0;
+          e1 = col + 1 < n ? __dmul_rn(w0, exp(-0.5 * S1)) : 0.0;
+        } else {
+          e0 = col < n ? w0 * exp_nonpos(-0.5 * S0) : 0.0;
+          e1 = col + 1 < n ? w0 * exp_nonpos(-0.5 * S1) : 0.0;
+        }
         const double2 al = *reinterpret_cast<const double2*>(alph + col);
         const double2 ww = *reinterpret_cast<const double2*>(wv + col);
         fa = fma(e0, al.x, fa); fa = fma(e1, al.y, fa);
@@ -2281,6 +2303,16 @@ __global__ void pred_scale_kernel(const double* __restrict__ cand, const double*
 }
 cudaError_t launch_pred_scale(const double* cand_row, const double* pls2, int d, int ntheta, int kpls, double* out, cudaStream_t st) {
   pred_scale_kernel<<<(d + 127) / 128, 128, 0, st>>>(cand_row, pls2, d, ntheta, kpls, out);
+  return cudaGetLastError();
+}
+
+// debug / parity: the prediction kernels' exp (kb200_corr.cuh:exp_nonpos; mode 0) or libm's (mode 1), element-wise
+__global__ void debug_exp_kernel(const double* __restrict__ x, long n, int mode, double* __restrict__ y) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = mode == 0 ? exp_nonpos(x[i]) : exp(x[i]);
+}
+cudaError_t launch_debug_exp(const double* x, long n, int mode, double* y, cudaStream_t st) {
+  debug_exp_kernel<<<296, 256, 0, st>>>(x, n, mode, y);
   return cudaGetLastError();
 }
 

@@ -226,6 +226,7 @@ cudaError_t launch_add_diag(double* tiles, int n, const double* eps_ptr, cudaStr
 cudaError_t launch_forwardsolve(const BackArgs& a, cudaStream_t st);
 cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t st);
 cudaError_t launch_epilogue(const EpiArgs& a, cudaStream_t st);
+cudaError_t launch_debug_exp(const double* x, long n, int mode, double* y, cudaStream_t st);
 cudaError_t launch_fp64_probe(int blocks, int iters, int mode, double* sink, cudaStream_t st);
 
 }  // namespace kb200

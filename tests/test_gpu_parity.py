@@ -1007,6 +1007,26 @@ def test_c5_kpls_n4000_factor_and_candidate_scoring(kb):
     assert relerr(q[1], qr[1], 1e-6 * s2s) < max(TOL_VAR, 5 * cond * 2.0 ** -53)
 
 
+def test_prediction_exp_is_libm_exp_without_the_denormal_path(kb):
+    """kb200_corr.cuh:exp_nonpos (what the prediction kernels call: no branch, constants from the constant bank) against
+    libm's exp on the same device: bit-identical on [-708, 0], clamped below; and against numpy's exp to 1 ulp."""
+    from kadal_b200 import _capi
+    lib = _capi.require_gpu()
+    rng = np.random.default_rng(6)
+    x = np.concatenate([-rng.uniform(0, 708, 200_000), -10.0 ** rng.uniform(-300, 2.8, 100_000), [0.0, -708.0, -1e-320, -0.0],
+                        -rng.uniform(708, 1e12, 1000), [-np.inf]])
+    x = np.ascontiguousarray(x)
+    mine, ref = np.empty_like(x), np.empty_like(x)
+    _capi.check(lib.kb200_debug_exp(0, _capi.ptr(x), len(x), 0, _capi.ptr(mine)))
+    _capi.check(lib.kb200_debug_exp(0, _capi.ptr(x), len(x), 1, _capi.ptr(ref)))
+    inside = x >= -708.0
+    assert np.array_equal(mine[inside], ref[inside])
+    at_clamp = mine[np.flatnonzero(x == -708.0)[0]]
+    assert 3.3e-308 < at_clamp < 3.4e-308 and np.all(mine[~inside] == at_clamp) and np.all(ref[~inside] < 3.4e-308)
+    npx = np.exp(x[inside])
+    assert np.max(np.abs(mine[inside] - npx) / npx) < 2.3e-16
+
+
 # ------------------------------------------------------------------ small n: one CTA per matrix in shared memory
 @pytest.mark.parametrize("n,d,kernel,tv", [(50, 2, ("gaussian",), False), (64, 4, ("matern52",), False),
                                            (200, 6, ("gaussian",), False), (200, 6, ("gaussian",), True),
