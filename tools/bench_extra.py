@@ -84,6 +84,9 @@ def main():
                 r = pred_case(torch, c, X, y, th, 2_000_000, _capi.OUT_PRED)
             else:
                 r = pred_case(torch, c, X, y, th, 400_000, _capi.OUT_PRED | _capi.OUT_S)
+        elif c == "c3":      # C3 shape; $KB200_NO_FUSED_PREDICT=1 sends it through the general tiled path instead of predict_small_kernel
+            X, y, th = bench.c3_data()
+            r = pred_case(torch, c, X, y, th, 4_000_000, _capi.OUT_PRED | _capi.OUT_S)
         elif c == "c3n300":
             rng = np.random.default_rng(1)
             X = rng.uniform(-1, 1, (300, 6))
