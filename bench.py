@@ -743,7 +743,7 @@ def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
     # (n=50, d=2: 7 restarts x 3-point L-BFGS-B stencils = 21 candidates per batch) and C3 training (n=200, d=6, a CMA-ES
     # population of 512), each also through the tile path the same sizes took in round 1 ($KB200_NO_SMALL_LIK=1)
     small = {}
-    for tag, n_s, d_s, P_s, seed in (("c1_train_lik", 50, 2, 21, 21), ("c3_train_lik", 200, 6, 512, 22)):
+    for tag, n_s, d_s, P_s, seed in (("c1_train_lik", 50, 2, 21, 21), ("n128_lik", 128, 6, 512, 23), ("c3_train_lik", 200, 6, 512, 22)):
         rng = np.random.default_rng(seed)
         Xs = rng.uniform(-1, 1, (n_s, d_s))
         ys = (np.sin(Xs.sum(1)) + 0.3 * Xs[:, 0] ** 2)[:, None] + 3.0
@@ -753,11 +753,13 @@ def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
         nll = torch.empty(P_s, dtype=torch.float64, device=dev)
         info = torch.empty(P_s, dtype=torch.int32, device=dev)
         fn = lambda: ms_.lik_batch_dev(xd.data_ptr(), P_s, d_s, False, -6.0, nll.data_ptr(), info.data_ptr(), stream)
+        os.environ["KB200_SMALL_LIK_NMAX"] = "256"           # (bench only: n = 200 sits just above the size policy's cut)
         t_small = timed(fn, 20)
         v_small = nll.cpu().numpy().copy()
         os.environ["KB200_NO_SMALL_LIK"] = "1"
         t_tile = timed(fn, 20)
         del os.environ["KB200_NO_SMALL_LIK"]
+        del os.environ["KB200_SMALL_LIK_NMAX"]
         v_tile = nll.cpu().numpy()
         assert int((info != 0).sum().item()) == 0 and np.allclose(v_small, v_tile, rtol=1e-7, atol=1e-7)
         fl = lik_flops_per_eval(n_s, d_s) * P_s
@@ -765,7 +767,8 @@ def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
                       "kernel": "lik_small_kernel (assembly + blocked POTF2 + forward substitution of one candidate per CTA in shared memory)",
                       "evals_per_s_per_gpu": P_s / (t_small * 1e-3), "ms_per_batch": t_small,
                       "fp64_tflops_algorithmic": fl / (t_small * 1e-3) / 1e12,
-                      "tile_path": {"evals_per_s_per_gpu": P_s / (t_tile * 1e-3), "ms_per_batch": t_tile}}
+                      "tile_path": {"evals_per_s_per_gpu": P_s / (t_tile * 1e-3), "ms_per_batch": t_tile},
+                      "default_path": "lik_small_kernel" if n_s <= 192 else "tile path (n > 192: measured equal or faster, DESIGN.md section 4)"}
         ms_.close()
     out["small_n_likelihood"] = small
     # ---- C4

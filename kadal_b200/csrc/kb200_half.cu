@@ -21,6 +21,7 @@
 // the right-looking 8x8-inverse TRSM and the blocked POTF2 are the same algorithms).
 // Reference call sites replaced: likelihood_func.py:168-213 (maincalc), prediction.py:245-251.
 #include <cmath>
+#include <cstdlib>
 #include "kb200_kernels.h"
 
 namespace kb200 {
@@ -321,9 +322,12 @@ __host__ __device__ inline size_t lik_small_smem(int N, int d) {
   return ((size_t)N * (N + 1) / 2 + (stage > strip ? stage : strip) + N + 512 + 64 + 16 + 2) * 8;
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(HT)
+// NTHR: 256 threads while two CTAs fit an SM (N <= 128), 512 beyond (one CTA per SM anyway: the strips and the trailing
+// update of a panel then spread over 16 warps while warp 0 factors the next diagonal block)
+template <bool FAST, int NTHR>
+__global__ void __launch_bounds__(NTHR)
 lik_small_kernel(CorrArgs C, CholArgs A, int N) {
+  constexpr int NWARP = NTHR / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* S = reinterpret_cast<double*>(smem_raw);
   const int d = C.spec.d, lda = d | 1, n = C.n, tld = N + 4;
@@ -345,7 +349,7 @@ lik_small_kernel(CorrArgs C, CholArgs A, int N) {
   const double* cand = C.cand + m * C.cand_stride;
   const double w0 = cand[4 * C.spec.ntheta];
   const double eps = cand[4 * C.spec.ntheta + C.spec.nkernel];
-  for (int idx = tid; idx < d * N; idx += HT) {
+  for (int idx = tid; idx < d * N; idx += NTHR) {
     const int k = idx / N, c = idx - k * N;
     Bt[idx] = c < n ? C.X[(size_t)c * d + k] : 0.0;
   }
@@ -353,14 +357,14 @@ lik_small_kernel(CorrArgs C, CholArgs A, int N) {
   // ---- assembly: 32-row strips, lane = row of the strip, warps walk the column quads 4 q <= row
   for (int r0 = 0; r0 < N; r0 += 32) {
     __syncthreads();                            // Bt / th2 ready; previous strip's As consumed
-    for (int idx = tid; idx < 32 * d; idx += HT) {
+    for (int idx = tid; idx < 32 * d; idx += NTHR) {
       const int r = idx / d, k = idx - r * d;
       As[r * lda + k] = Bt[(size_t)k * N + r0 + r];
     }
     __syncthreads();
     const int row = r0 + lane;
     const int nq4 = (r0 + 32) >> 2;             // quads up to the end of the strip's diagonal block
-    for (int q = warp; q < nq4; q += HWARPS) {
+    for (int q = warp; q < nq4; q += NWARP) {
       const int c0 = 4 * q;
       if (c0 > row) continue;                   // strictly above the diagonal: not stored
       Quad v;
@@ -380,7 +384,7 @@ lik_small_kernel(CorrArgs C, CholArgs A, int N) {
     }
   }
   __syncthreads();                              // the staging area is dead: it becomes the RHS strip
-  for (int idx = tid; idx < 8 * tld; idx += HT) {
+  for (int idx = tid; idx < 8 * tld; idx += NTHR) {
     const int q = idx / tld, r = idx - q * tld;
     trow[idx] = (q < A.nq && r < n) ? A.R[(size_t)q * A.npad + r] : 0.0;
   }
@@ -397,18 +401,18 @@ lik_small_kernel(CorrArgs C, CholArgs A, int N) {
       inv8_warp_t(S, o, dinv, W8k, lane);
       if (lane == 0 && b && *s_bad == 0) *s_bad = b;
     } else if (kb > 0) {
-      trailing_update32_t(S, trow, o - 32, 3, 1 << 20, warp - 1, HWARPS - 1, lane, N, tld);
+      trailing_update32_t(S, trow, o - 32, 3, 1 << 20, warp - 1, NWARP - 1, lane, N, tld);
     }
     __syncthreads();
     const int nrow_strips = (N - o - 32) >> 3;
-    for (int st = warp; st <= nrow_strips; st += HWARPS) {
+    for (int st = warp; st <= nrow_strips; st += NWARP) {
       const int g = lane >> 2;
       if (st < nrow_strips) strip_trsm32_t(S + tri(o + 32 + 8 * st + g) + o, S, o, W8k, lane);
       else strip_trsm32_t(trow + g * tld + o, S, o, W8k, lane);
     }
     __syncthreads();
     if (kb + 1 < nblk) {
-      trailing_update32_t(S, trow, o, 0, 3, warp, HWARPS, lane, N, tld);
+      trailing_update32_t(S, trow, o, 0, 3, warp, NWARP, lane, N, tld);
       __syncthreads();
     }
   }
@@ -416,19 +420,19 @@ lik_small_kernel(CorrArgs C, CholArgs A, int N) {
   const int bad = *s_bad;
   if (tid == 0) A.info[m] = bad;
   double* z = A.Z + (size_t)m * A.nq * A.npad;
-  for (int idx = tid; idx < A.nq * A.npad; idx += HT) {
+  for (int idx = tid; idx < A.nq * A.npad; idx += NTHR) {
     const int q = idx / A.npad, r = idx - q * A.npad;
     z[idx] = r < N ? trow[q * tld + r] : 0.0;
   }
   double v = 0.0;
-  for (int i = tid; i < N; i += HT) v += log(fabs(S[tri(i) + i]));   // padded rows are exactly 1
+  for (int i = tid; i < N; i += NTHR) v += log(fabs(S[tri(i) + i]));   // padded rows are exactly 1
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
   if (lane == 0) s_red[warp] = v;
   __syncthreads();
   if (tid == 0) {
     double s = 0.0;
-    for (int i = 0; i < HWARPS; ++i) s += s_red[i];
+    for (int i = 0; i < NWARP; ++i) s += s_red[i];
     A.logdet[m] = s;
   }
 }
@@ -956,33 +960,43 @@ static cudaError_t half_attrs() {
 }
 
 // largest n the in-shared-memory likelihood kernel takes for this input dimension (0: none)
+// Measured on B200 against the tile path (tools/time_small.py, 512 candidates, d = 6; profiles/r2k_time_small.log):
+// n = 50: 0.054 vs 0.139 ms, n = 128: 0.131 vs 0.150, n = 160: 0.253 vs 0.382, n = 192: 0.329 vs 0.392 -- and
+// n = 200, 224 (seven 32-wide panels, one CTA per SM): 0.420 vs 0.401 / 0.406: from N = 224 on the tile path's two
+// half-SM CTAs per SM hide the strictly sequential pivots better than one 512-thread CTA can, so it keeps those sizes.
 int lik_small_pad(int n, int d) {
   const int N = (n + 31) & ~31;
-  if (N > 256 || lik_small_smem(N, d) > (size_t)227 * 1024) return 0;
+  const char* e = getenv("KB200_SMALL_LIK_NMAX");       // (read per call: bench.py measures n = 200 on both paths)
+  const int nmax = e ? atoi(e) : 192;
+  if (N > nmax || N > 256 || lik_small_smem(N, d) > (size_t)227 * 1024) return 0;
   return N;
+}
+
+template <bool FAST, int NTHR>
+static cudaError_t lik_small_launch(const CorrArgs& c, const CholArgs& a, int N, size_t sm, int nmat, cudaStream_t st) {
+  static size_t attr[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (sm > attr[dev]) {
+    const int want = (int)(sm > 48 * 1024 ? sm : 48 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(lik_small_kernel<FAST, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(lik_small_kernel<FAST, NTHR>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr[dev] = sm;
+  }
+  lik_small_kernel<FAST, NTHR><<<nmat, NTHR, sm, st>>>(c, a, N);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_lik_small(const CorrArgs& c, const CholArgs& a, int nmat, cudaStream_t st) {
   const int N = lik_small_pad(c.n, c.spec.d);
   if (N == 0) return cudaErrorInvalidValue;
   const size_t sm = lik_small_smem(N, c.spec.d);
-  static size_t attr[64][2] = {{0}};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
   const bool fast = c.spec.nkernel == 1 && c.spec.kid[0] == K_GAUSS && !c.spec.kpls;
-  if (sm > attr[dev][fast]) {
-    const int want = (int)(sm > 48 * 1024 ? sm : 48 * 1024);
-    cudaError_t e = fast ? cudaFuncSetAttribute(lik_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want)
-                         : cudaFuncSetAttribute(lik_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e != cudaSuccess) return e;
-    if (fast) cudaFuncSetAttribute(lik_small_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    else cudaFuncSetAttribute(lik_small_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr[dev][fast] = sm;
-  }
-  if (fast) lik_small_kernel<true><<<nmat, HT, sm, st>>>(c, a, N);
-  else lik_small_kernel<false><<<nmat, HT, sm, st>>>(c, a, N);
-  return cudaGetLastError();
+  const bool wide = N > 128;
+  if (fast) return wide ? lik_small_launch<true, 512>(c, a, N, sm, nmat, st) : lik_small_launch<true, 256>(c, a, N, sm, nmat, st);
+  return wide ? lik_small_launch<false, 512>(c, a, N, sm, nmat, st) : lik_small_launch<false, 256>(c, a, N, sm, nmat, st);
 }
 
 cudaError_t launch_chol_diag_half(const CholArgs& a, int j, int nmat, cudaStream_t st) {

@@ -1029,12 +1029,12 @@ def test_prediction_exp_is_libm_exp_without_the_denormal_path(kb):
 
 # ------------------------------------------------------------------ small n: one CTA per matrix in shared memory
 @pytest.mark.parametrize("n,d,kernel,tv", [(50, 2, ("gaussian",), False), (64, 4, ("matern52",), False),
-                                           (200, 6, ("gaussian",), False), (200, 6, ("gaussian",), True),
-                                           (97, 10, ("gaussian", "exponential"), False), (224, 3, ("exponential",), False),
+                                           (190, 6, ("gaussian",), False), (160, 6, ("gaussian",), True),
+                                           (97, 10, ("gaussian", "exponential"), False), (192, 3, ("exponential",), False),
                                            (33, 1, ("gaussian",), False)])
 def test_small_n_in_shared_memory_likelihood_against_oracle_and_tile_path(kb, monkeypatch, n, d, kernel, tv):
     """lik_small_kernel (north star (2): one CTA per matrix held in shared memory -- assembly, blocked POTF2 with warp
-    shuffles, fused forward substitution; n <= 224..256 depending on d) against the oracle at the north-star tolerance
+    shuffles, fused forward substitution; n <= 192, 256 threads and two CTAs per SM up to n = 128, 512 threads beyond) against the oracle at the north-star tolerance
     and against the tile path ($KB200_NO_SMALL_LIK=1) it replaces for these sizes: same Psi bits, another order of the
     factorisation's roundings."""
     rng = np.random.default_rng(1000 * n + d)
