@@ -531,16 +531,15 @@ chol_diag_half_kernel(CholArgs A, int j) {
     if (tid == 0 && q + DLOOK < nslab) issue(q + DLOOK);
     mbar_wait(&full[st], (uint32_t)((q / DNST) & 1));
     const double* As = ring + (size_t)st * SLAB_ELEMS;
-#pragma unroll
-    for (int kq = 0; kq < 4; ++kq) {
-      const int sw = ((kq ^ (g & 3)) << 2) + t;
-      const double a_hi = As[(8 * hiR + g) * KS + sw], a_lo = As[(8 * loR + g) * KS + sw];
-#pragma unroll
-      for (int u = 0; u < 17; ++u) {
-        const int C = u < nhi ? u : u - nhi;
-        const double b = As[(8 * C + g) * KS + sw];
-        dmma884(acc[u][0], acc[u][1], u < nhi ? a_hi : a_lo, b);
-      }
+    switch (warp) {   // the warp's two row blocks are compile-time constants inside: no per-DMMA selects (ncu r2d: 128 FSEL per slab)
+      case 0: syrk_slab<0>(acc, As, g, t); break;
+      case 1: syrk_slab<1>(acc, As, g, t); break;
+      case 2: syrk_slab<2>(acc, As, g, t); break;
+      case 3: syrk_slab<3>(acc, As, g, t); break;
+      case 4: syrk_slab<4>(acc, As, g, t); break;
+      case 5: syrk_slab<5>(acc, As, g, t); break;
+      case 6: syrk_slab<6>(acc, As, g, t); break;
+      default: syrk_slab<7>(acc, As, g, t); break;
     }
     // fused forward substitution: tacc[qq] += L_jk[rr][c] * Z_k[c]      (likelihood_func.py:183-193)
     // Z_k comes from a rolling two-tile shared-memory buffer: tile k + 1 is fetched into registers at the

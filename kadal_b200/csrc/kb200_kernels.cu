@@ -15,6 +15,7 @@
 // Reference call sites replaced: likelihood_func.py:93-102,168-213; kernelfunc.py:4-94;
 // prediction.py:159-171,208-314.  See DESIGN.md for the data layout and rooflines.
 #include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include "kb200_corr.cuh"
 #include "kb200_kernels.h"
