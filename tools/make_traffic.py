@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASS = {"corr_tile_kernel": "assemble", "chol_diag_kernel": "chol_diag", "chol_panel_kernel": "chol_panel",
          "chol_diag_half_kernel": "chol_diag", "chol_panel_half_kernel": "chol_panel",
-         "lik_finalize_kernel": "finalize", "predict_small_kernel": "predict_small"}
+         "lik_finalize_kernel": "finalize", "predict_small_kernel": "predict_small", "lik_small_kernel": "lik_small"}
 
 
 def scale(unit):

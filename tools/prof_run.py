@@ -3,6 +3,7 @@
     python tools/prof_run.py lik  [passes]     # C2: n=1000, d=10, 512 candidates
     python tools/prof_run.py pred [passes]     # C3: n=200, d=6, pred + s over 2^20 points
     python tools/prof_run.py pred4 [passes]    # C4: n=800, d=20, pred over 2^20 points
+    python tools/prof_run.py small [passes]    # n=128, d=6, 512 candidates: lik_small_kernel (one CTA per candidate in shared memory)
 """
 import os
 import sys
@@ -25,6 +26,15 @@ def main():
         for _ in range(passes):
             nll, info = m.lik_batch(pop, False, -6.0)
         print("lik ok", float(nll.min()), int((info != 0).sum()))
+    elif mode == "small":
+        rng = np.random.default_rng(23)
+        X = rng.uniform(-1, 1, (128, 6))
+        y = (np.sin(X.sum(1)) + 0.3 * X[:, 0] ** 2)[:, None] + 3.0
+        m = GpuModel(X, y, np.ones((128, 1)), [0])
+        pop = rng.uniform(-0.5, 1.0, (512, 6))
+        for _ in range(passes):
+            nll, info = m.lik_batch(pop, False, -6.0)
+        print("small ok", float(nll.min()), int((info != 0).sum()))
     else:
         if mode == "pred":
             X, y, th = bench.c3_data()
