@@ -1773,6 +1773,8 @@ int kb200_sobol_points_dev(int device, const unsigned long long* dirnum, int bit
   if (!dirnum || !d_out) return fail_arg("kb200_sobol_points_dev: null argument");
   if (bits < 1 || bits > 64 || dims < 1 || i0 < 0) return fail_arg("kb200_sobol_points_dev: bad bits / dims / i0");
   if (N < 1) return 0;
+  if (bits < 64 && (unsigned long long)(i0 + N) > (1ull << bits))
+    return fail_arg("kb200_sobol_points_dev: the sequence has only 2^bits points");
   CK(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* dv = nullptr;

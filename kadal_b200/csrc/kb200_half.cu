@@ -302,6 +302,23 @@ __device__ __forceinline__ void syrk_acc_init(double (&acc)[17][2], const double
   }
 }
 
+// one 16-wide slab of the SYRK for warp W: row blocks 15 - W (tiles C = 0 .. 15 - W) and W (C = 0 .. W)
+template <int W>
+__device__ __forceinline__ void syrk_slab(double (&acc)[17][2], const double* As, int g, int t) {
+  constexpr int NHI = 16 - W;
+#pragma unroll
+  for (int kq = 0; kq < 4; ++kq) {
+    const int sw = ((kq ^ (g & 3)) << 2) + t;
+    const double a_hi = As[(8 * (15 - W) + g) * KS + sw], a_lo = As[(8 * W + g) * KS + sw];
+#pragma unroll
+    for (int u = 0; u < 17; ++u) {
+      const int C = u < NHI ? u : u - NHI;
+      const double b = As[(8 * C + g) * KS + sw];
+      dmma884(acc[u][0], acc[u][1], u < NHI ? a_hi : a_lo, b);
+    }
+  }
+}
+
 }  // namespace
 
 

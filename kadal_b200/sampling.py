@@ -86,15 +86,19 @@ def sobol_direction_numbers(nvar, nsamp):
         return None
     except Exception:
         pass
-    from scipy.stats import qmc
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        eng = qmc.Sobol(nvar, scramble=False)
-    bits = int(eng.bits)
-    if nsamp + 1 > (1 << bits):
+    try:
+        from scipy.stats import qmc
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            eng = qmc.Sobol(nvar, scramble=False)
+        bits = int(eng.bits)
+        v = np.ascontiguousarray(eng._sv, dtype=np.uint64)      # (nvar, bits) direction numbers of scipy's generator
+    except Exception:                                           # another scipy layout: generate on the host instead
         return None
-    return np.ascontiguousarray(eng._sv, dtype=np.uint64), bits
+    if v.shape != (nvar, bits) or nsamp + 1 > (1 << bits):
+        return None
+    return v, bits
 
 
 def sobol_points_device(nsamp, nvar, lobound=None, upbound=None, first_row=1, device=None, out_ptr=None, stream=0):
