@@ -43,6 +43,14 @@ def _worker(rank, world, port, P, q):
         x = rng.uniform(-1, 1, (2 * P + 1, 3))
         full = parallel.predict_sharded(x, {}, ("pred", "s"), eval_fn=_fake_pred)
         mine = parallel.predict_sharded(x, {}, ("pred",), gather=False, eval_fn=_fake_pred)
+        # the device-side gather of the NCCL path (unequal shards padded, one all_gather_into_tensor), here on CPU tensors
+        import torch
+        lo, hi = parallel.shard_bounds(len(x), world, rank)
+        g = parallel._gather_device(torch.from_numpy(_fake_pred(x[lo:hi], {}, None)["pred"]), len(x), None).numpy()
+        assert np.array_equal(g, full["pred"])
+        gi = parallel._gather_device(torch.from_numpy(_fake_lik(pop, {}, False)[1][slice(*parallel.shard_bounds(P, world, rank))]),
+                                     P, None).numpy()
+        assert np.array_equal(gi, info) and gi.dtype == np.int32
         q.put((rank, nll, info, i, v, full["pred"], full["s"], mine["pred"], parallel.shard_bounds(len(x), world, rank)))
     finally:
         dist.destroy_process_group()
