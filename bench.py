@@ -771,6 +771,39 @@ def extra_configs(args, rank, local_rank, world, torch, dist, barrier):
                       "default_path": "lik_small_kernel" if n_s <= 192 else "tile path (n > 192: measured equal or faster, DESIGN.md section 4)"}
         ms_.close()
     out["small_n_likelihood"] = small
+    # ---- BASELINE configs[0], KrigDemo (KrigDemo.py:22-118): Ordinary Kriging, Gaussian kernel, Branin 2-D, 50 Sobol samples,
+    # L-BFGS-B from 7 start points, predict a 100 x 100 grid -- through the drop-in class, wall clock as the user sees it
+    if rank == 0:
+        try:
+            import contextlib
+            import io
+            from scipy.stats import qmc
+            from kadal_b200 import Kriging
+            lbk, ubk = np.array([-5.0, 0.0]), np.array([10.0, 15.0])
+            Xk = qmc.scale(qmc.Sobol(2, scramble=False).random(51)[1:], lbk, ubk)
+            x1, x2 = Xk[:, 0], Xk[:, 1]
+            yk = ((x2 - 5.1 / (4 * np.pi ** 2) * x1 ** 2 + 5 / np.pi * x1 - 6) ** 2 + 10 * (1 - 1 / (8 * np.pi)) * np.cos(x1) + 10)[:, None]
+            g1, g2 = np.meshgrid(np.linspace(lbk[0], ubk[0], 100), np.linspace(lbk[1], ubk[1], 100))
+            xg = np.column_stack([g1.ravel(), g2.ravel()])
+            times = []
+            for _ in range(3):
+                K = {"X": Xk, "y": yk, "lb": lbk, "ub": ubk, "nvar": 2, "problem": "branin", "nugget": -6, "nrestart": 7,
+                     "kernel": ["gaussian"], "optimizer": "lbfgsb"}
+                with contextlib.redirect_stdout(io.StringIO()):
+                    t0 = time.perf_counter()
+                    mk = Kriging(K, standardization=True, standtype="default", normy=False, trainvar=False)
+                    mk.train(disp=False)
+                    t1 = time.perf_counter()
+                    pk = mk.predict(xg, ["pred", "SSqr"])
+                    t2 = time.perf_counter()
+                times.append((t1 - t0, t2 - t1))
+            tr, pr = min(t[0] for t in times), min(t[1] for t in times)
+            out["c1_krigdemo"] = {"workload": "C1 KrigDemo: n=50, d=2, train (L-BFGS-B, 7 restarts in lock step) + predict a 100 x 100 grid (pred, SSqr), through kadal_b200.Kriging",
+                                  "train_ms": tr * 1e3, "predict_10k_ms": pr * 1e3, "likelihood_evals": mk.train_stats["evals"],
+                                  "gpu_batches": mk.train_stats["batches"], "NegLnLike": float(mk.KrigInfo["NegLnLike"]),
+                                  "reference_on_8_cores_s": {"train": 1.07, "predict_10k": 0.13, "source": "SURVEY.md section 6 (measured in the build container)"}}
+        except Exception as exc:      # scipy.stats.qmc missing etc.: the record is optional
+            out["c1_krigdemo"] = {"unavailable": str(exc)[:120]}
     # ---- C4
     rng = np.random.default_rng(7)
     X = rng.uniform(-1, 1, (800, 20))
