@@ -35,10 +35,10 @@ def timed(torch, fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
-def pred_case(torch, name, X, y, th, npts, want, pls=None, reps=3):
+def pred_case(torch, name, X, y, th, npts, want, pls=None, reps=3, kernels=(0,)):
     dev = torch.device("cuda", 0)
     n, d = X.shape
-    m = GpuModel(X, y, np.ones((n, 1)), [0], pls=pls)
+    m = GpuModel(X, y, np.ones((n, 1)), list(kernels), pls=pls)
     st = m.fit_state(th, False, -6.0, want_U=False, want_Psi=False)
     assert st["info"] == 0, st["info"]
     g = torch.Generator(device=dev)
@@ -87,6 +87,15 @@ def main():
         elif c == "c3":      # C3 shape; $KB200_NO_FUSED_PREDICT=1 sends it through the general tiled path instead of predict_small_kernel
             X, y, th = bench.c3_data()
             r = pred_case(torch, c, X, y, th, 4_000_000, _capi.OUT_PRED | _capi.OUT_S)
+        elif c in ("c3m52", "c3d10"):   # small models outside the fused predictor's envelope: Matern 5/2, or d = 10 -> general tiled path
+            if c == "c3m52":
+                X, y, th = bench.c3_data()
+                r = pred_case(torch, c, X, y, th, 4_000_000, _capi.OUT_PRED | _capi.OUT_S, kernels=(3,))
+            else:
+                rng = np.random.default_rng(1)
+                X = rng.uniform(-1, 1, (200, 10))
+                y = (np.sin(X.sum(1)) + 0.3 * X[:, 0] ** 2)[:, None] + 3.0
+                r = pred_case(torch, c, X, y, np.full(10, 0.3), 4_000_000, _capi.OUT_PRED | _capi.OUT_S)
         elif c == "c3n300":
             rng = np.random.default_rng(1)
             X = rng.uniform(-1, 1, (300, 6))
