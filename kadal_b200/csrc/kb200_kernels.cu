@@ -1596,34 +1596,18 @@ constexpr int PS_NST = 3;
 constexpr int PS_LOOK = 1;    // with the one-slab-late release below the ring needs NST >= LOOK + 2
 constexpr int PS_MAXD = 8;
 
-template <int D>
-__device__ __forceinline__ void scaled_pair_sum(const double* a, const double* bt2, double& S0, double& S1) {
-  S0 = 0.0;
-  S1 = 0.0;
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const double ak = a[k];
-    const double2 b = *reinterpret_cast<const double2*>(bt2 + k * 256);
-    const double d0 = ak - b.x, d1 = ak - b.y;
-    S0 = fma(d0, d0, S0);
-    S1 = fma(d1, d1, S1);
-  }
-}
-
 // sum_k (a_k - b_k)^2 / theta_k^2 for two neighbouring samples, numpy's order for d <= 8
 __device__ __forceinline__ void gauss_pair_sum(int d, const double* th2, const double* a, const double* bt2,
                                                double& S0, double& S1) {
   if (!KB200_PREDICT_EXACT_DIV) {   // coordinates pre-scaled by RN(1/theta_k) (kb200_corr.cuh:corr_quad_gauss_scaled)
-    // fully unrolled per d (a uniform switch): no loop counter, compare, branch or address arithmetic per dimension
-    switch (d) {
-      case 1: scaled_pair_sum<1>(a, bt2, S0, S1); break;
-      case 2: scaled_pair_sum<2>(a, bt2, S0, S1); break;
-      case 3: scaled_pair_sum<3>(a, bt2, S0, S1); break;
-      case 4: scaled_pair_sum<4>(a, bt2, S0, S1); break;
-      case 5: scaled_pair_sum<5>(a, bt2, S0, S1); break;
-      case 6: scaled_pair_sum<6>(a, bt2, S0, S1); break;
-      case 7: scaled_pair_sum<7>(a, bt2, S0, S1); break;
-      default: scaled_pair_sum<8>(a, bt2, S0, S1); break;
+    // a plain loop over d: the per-d unrolled switch this replaced was slower (code size, see psi_tile)
+    S0 = 0.0; S1 = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double ak = a[k];
+      const double2 b = *reinterpret_cast<const double2*>(bt2 + k * 256);
+      const double d0 = ak - b.x, d1 = ak - b.y;
+      S0 = fma(d0, d0, S0);
+      S1 = fma(d1, d1, S1);
     }
     return;
   }
@@ -1768,6 +1752,10 @@ predict_small_kernel(PredSmallArgs A) {
   // psi of sample tile `tile` for this thread's row: columns 8 ct + 2 tq (+1), ct < nct
   double x[16][2];
   double fa, ua;
+  // (The fused predictor's loop body is large enough for instruction fetch to show up in the stall samples -- ncu r2g:
+  // no_instruction 5-7 % -- and smaller code is faster here: pair sums as a loop over d instead of a per-d unrolled switch
+  // 3.42e8 -> 3.60e8 pts/s at C3.  Rolling this column-tile loop as well, with a switch steering the results into x[],
+  // shrinks the kernel from 12.6 k to 8.0 k instructions but makes ptxas spill x[]: 2.40e8.)
   auto psi_tile = [&](int tile, int nct) {
     const double* arow = As + row * lda;
 #pragma unroll
