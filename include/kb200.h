@@ -215,6 +215,11 @@ int kb200_ehvi3d_dev(int device, const double* d_front, int k, const double* ref
  * refitted without it at the same hyper-parameters (beta re-estimated) -- what
  * supports/krigloocv2.py:7-34 computes with n refits -- in closed form from the factor. */
 int kb200_loocv(kb200_model* m, double* loo /* n */);
+/* The 'fast' variant, supports/krigloocv.py:4-38: loo[i] = y[i] - (B^-1[:n,:n] y)[i] / B^-1[i][i] with the bordered matrix
+ * B = [[sigma2 * Psi, F], [F^T, 1]] -- as written in the reference: a ONE in the corner and KrigInfo['Psi'], i.e. WITHOUT the
+ * nugget.  The installed fit must therefore be that of Psi itself (kb200_fit_state with nugget_log10 = -300 on a model of the
+ * same samples); sigma2 = KrigInfo['SigmaSqr'] of the trained model.  Ordinary Kriging (p = 1).  Closed form over the factor. */
+int kb200_loocv_fast(kb200_model* m, double sigma2, double* loo /* n */);
 
 /* Introspection used by the tests / bench. */
 int kb200_model_dims(const kb200_model* m, int* n, int* d, int* p, int* ntheta, int* nkernel);

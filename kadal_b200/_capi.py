@@ -59,6 +59,7 @@ SIGNATURES = {
     "kb200_set_groups": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "kb200_set_schedule_population": (ctypes.c_int, [c_void_p, ctypes.c_longlong]),
     "kb200_loocv": (ctypes.c_int, [c_void_p, c_void_p]),
+    "kb200_loocv_fast": (ctypes.c_int, [c_void_p, ctypes.c_double, c_void_p]),
     "kb200_akmcs_reduce": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,
                                           c_double_p, ctypes.POINTER(ctypes.c_longlong), c_u64_p]),
     "kb200_akmcs_reduce_dev": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_int, c_void_p, c_void_p,

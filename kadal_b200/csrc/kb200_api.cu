@@ -1427,7 +1427,13 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
   return 0;
 }
 
-extern "C" int kb200_loocv(kb200_model* m, double* loo) {
+static int loocv_impl(kb200_model* m, double* loo, double fast_sigma2);
+extern "C" int kb200_loocv(kb200_model* m, double* loo) { return loocv_impl(m, loo, 0.0); }
+extern "C" int kb200_loocv_fast(kb200_model* m, double sigma2, double* loo) {
+  if (!(sigma2 > 0.0)) return fail_arg("kb200_loocv_fast: sigma2 must be positive");
+  return loocv_impl(m, loo, sigma2);
+}
+static int loocv_impl(kb200_model* m, double* loo, double fast_sigma2) {
   if (!m || !loo) return fail_arg("kb200_loocv: null argument");
   if (!m->has_pred) return fail_arg("kb200_loocv: no fit installed (call kb200_fit_state or kb200_predictor_load)");
   CK(cudaSetDevice(m->device));
@@ -1453,7 +1459,8 @@ extern "C" int kb200_loocv(kb200_model* m, double* loo) {
       if (m->half_mode != 0 && !pa.naive) CK(launch_chol_panel_half(pa, j, 2 * tiles, 1, st));   // bit-identical to the full-SM kernel
       else CK(launch_chol_panel(pa, j, tiles, 1, st));
     }
-    CK(launch_loo(m->R.d(), m->palpha.d(), m->pw.d(), sl.ssq.d(), m->pbtb, m->n, p0, (int)np, sl.out[0].d(), st));
+    CK(launch_loo(m->R.d(), m->palpha.d(), m->pw.d(), sl.ssq.d(), m->pbtb, m->n, p0, (int)np, sl.out[0].d(), st, fast_sigma2,
+                  m->pbeta));
     m->launches++;
   }
   CK(cudaMemcpyAsync(loo, sl.out[0].p, (size_t)m->n * 8, cudaMemcpyDeviceToHost, st));

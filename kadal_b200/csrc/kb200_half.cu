@@ -958,13 +958,25 @@ cudaError_t launch_rl_rhs_update(const CholArgs& a, int k, int nmat, cudaStream_
 }
 
 // ====================================================================== launchers
+// $KB200_DIAG_SMEM_KB: shared memory requested per diagonal CTA (KiB, experiments).  Above 113 only ONE diagonal CTA fits an
+// SM and its neighbour is a panel CTA of another candidate group (which has the tensor pipe to itself while the diagonal
+// CTA is in its strictly sequential pivots) instead of a second diagonal CTA in the same phase.
+static size_t diag_smem() {
+  static const size_t v = [] {
+    const char* e = getenv("KB200_DIAG_SMEM_KB");
+    const size_t kb = e ? (size_t)atoi(e) : 0;
+    return kb * 1024 > D_SMEM && kb <= 120 ? kb * 1024 : D_SMEM;
+  }();
+  return v;
+}
+
 static cudaError_t half_attrs() {
   static bool done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
   if (done[dev]) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(chol_diag_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(chol_diag_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem());
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(chol_panel_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
   if (e != cudaSuccess) return e;
@@ -1018,7 +1030,7 @@ cudaError_t launch_lik_small(const CorrArgs& c, const CholArgs& a, int nmat, cud
 cudaError_t launch_chol_diag_half(const CholArgs& a, int j, int nmat, cudaStream_t st) {
   cudaError_t e = half_attrs();
   if (e != cudaSuccess) return e;
-  chol_diag_half_kernel<<<nmat, HT, D_SMEM, st>>>(a, j);
+  chol_diag_half_kernel<<<nmat, HT, diag_smem(), st>>>(a, j);
   return cudaGetLastError();
 }
 

@@ -1885,12 +1885,24 @@ __global__ void identity_chunk_kernel(double* chunk, int nt, long pt0) {
     for (int r = threadIdx.x; r < TB; r += blockDim.x) T[tile_off(r, r)] = 1.0;
 }
 
+// fast_sigma2 <= 0: krigloocv2.py (the closed form of n refits).  fast_sigma2 > 0: krigloocv.py ('fast'): the bordered
+// matrix B = [[sigma^2 Psi, f], [f^T, 1]] (a ONE in the corner, Psi without nugget -- the installed factor must be that
+// of Psi itself) and LOO_i = y_i - (B^-1[:n,:n] y)_i / B^-1_ii.  With P = Psi^-1, w = P f, alpha = P (y - f beta),
+// s = 1 - f^T P f / sigma^2:  (B^-1 y)_i = [alpha_i + beta w_i + w_i (beta f^T P f / sigma^2) / s] / sigma^2,
+// B^-1_ii = [P_ii + w_i^2 / (sigma^2 s)] / sigma^2.
 __global__ void loo_kernel(const double* y, const double* alpha, const double* w, const double* ssq, double btb,
-                           int n, long p0, int np, double* out) {
+                           int n, long p0, int np, double* out, double fast_sigma2, double beta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= np) return;
   const long gi = p0 + i;
   if (gi >= n) return;
+  if (fast_sigma2 > 0.0) {
+    const double s = 1.0 - btb / fast_sigma2;
+    const double num = alpha[gi] + beta * w[gi] + w[gi] * ((beta * btb / fast_sigma2) / s);
+    const double den = ssq[i] + w[gi] * (w[gi] / (fast_sigma2 * s));
+    out[gi] = y[gi] - num / den;
+    return;
+  }
   const double q = ssq[i] - w[gi] * (w[gi] / btb);
   out[gi] = y[gi] - alpha[gi] / q;
 }
@@ -2056,8 +2068,8 @@ cudaError_t launch_identity_chunk(double* chunk, int tiles, int nt, long pt0, cu
 }
 
 cudaError_t launch_loo(const double* y, const double* alpha, const double* w, const double* ssq, double btb, int n,
-                       long p0, int np, double* out, cudaStream_t st) {
-  loo_kernel<<<(np + 255) / 256, 256, 0, st>>>(y, alpha, w, ssq, btb, n, p0, np, out);
+                       long p0, int np, double* out, cudaStream_t st, double fast_sigma2, double beta) {
+  loo_kernel<<<(np + 255) / 256, 256, 0, st>>>(y, alpha, w, ssq, btb, n, p0, np, out, fast_sigma2, beta);
   KB_LAUNCH_CHECK();
   return cudaSuccess;
 }

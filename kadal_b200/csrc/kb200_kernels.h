@@ -203,7 +203,7 @@ cudaError_t launch_append_row(double* tiles, const double* v, int n_prev, int nt
                               int npad, const double* Zprev, const double* R, double* Z, const double* logdet_prev,
                               double* logdet, int* info, const double* dnn, cudaStream_t st);
 cudaError_t launch_loo(const double* y, const double* alpha, const double* w, const double* ssq, double btb, int n,
-                       long p0, int np, double* out, cudaStream_t st);
+                       long p0, int np, double* out, cudaStream_t st, double fast_sigma2 = 0.0, double beta = 0.0);
 cudaError_t launch_predict_small(const PredSmallArgs& a, int sm_count, cudaStream_t st);
 // per-dimension coordinate scales of a single-Gaussian-kernel predictor (pls2 = squared KPLS coefficients [d][h] or null)
 cudaError_t launch_pred_scale(const double* cand_row, const double* pls2, int d, int ntheta, int kpls, double* out, cudaStream_t st);

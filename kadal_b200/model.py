@@ -232,6 +232,12 @@ class GpuModel:
         check(self.lib.kb200_loocv(self.handle, ptr(out)))
         return out
 
+    def loocv_fast(self, sigma2):
+        """krigloocv.py's 'fast' leave-one-out values (n,) from the installed fit of Psi WITHOUT nugget (kb200.h)."""
+        out = np.empty(self.n, dtype=np.float64)
+        check(self.lib.kb200_loocv_fast(self.handle, float(sigma2), ptr(out)))
+        return out
+
     def set_groups(self, ngroups):
         """Number of candidate groups (streams) of a likelihood batch; 1 serialises the kernels."""
         check(self.lib.kb200_set_groups(self.handle, int(ngroups)))

@@ -1119,10 +1119,35 @@ def test_loocv_standard_matches_n_refits(kb, n, d, kernel):
     assert pred.shape == (n, 1)
     assert relerr(pred, ref) < max(TOL_MEAN, 5 * cond * 2.0 ** -53)
     assert abs(err - errperf(y, ref, "rmse")) <= 1e-7 * max(1.0, abs(err))
-    with pytest.raises(NotImplementedError):
-        loocv(info, type="fast")
     with pytest.raises(ValueError):
         loocv(info, type="other")
+
+
+def _loocv_fast_restated(info):
+    """krigloocv.py:4-38 as written: inverse of [[sigma^2 Psi, F], [F^T, 1]] (a ONE in the corner, Psi without nugget)."""
+    n = info["nsamp"]
+    B = np.linalg.inv(np.block([[info["SigmaSqr"] * info["Psi"], info["F"]], [info["F"].T, np.ones((1, 1))]]))
+    y = info["y"][:, 0]
+    return (y - (B[:n, :n] @ y) / np.diag(B)[:n]).reshape(-1, 1)
+
+
+@pytest.mark.parametrize("n,d,kernel,lt", [(70, 3, "gaussian", -0.3), (150, 4, "matern52", 0.3), (260, 5, "gaussian", 0.0),
+                                           (90, 2, "exponential", 0.0)])
+def test_loocv_fast_matches_the_bordered_inverse(kb, n, d, kernel, lt):
+    """type='fast' (krigloocv.py): closed form over the factor of Psi WITHOUT nugget against the reference's dense inverse."""
+    from kadal_b200.loocv import loocv
+    from kadal_b200.errperf import errperf
+    rng = np.random.default_rng(n + 1)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(2 * X.sum(1, keepdims=True)) + X[:, :1] ** 2 + 3.0
+    info = ko.make_kriginfo(X, y, kernel=(kernel,))
+    kb.likelihood(np.full(d, lt), info, "all", False)
+    err, pred = loocv(info, errtype="rmse", type="fast")
+    ref = _loocv_fast_restated(info)
+    cond = np.linalg.cond(info["Psi"])
+    assert pred.shape == (n, 1)
+    assert relerr(pred, ref) < max(TOL_MEAN, 5 * cond * 2.0 ** -53)
+    assert abs(err - errperf(y, ref, "rmse")) <= 1e-7 * max(1.0, abs(err))
 
 
 # ------------------------------------------------------------------ AK-MCS reductions (SURVEY §8 row f3)

@@ -28,7 +28,7 @@ print("%s  %.3f ms/generation  assemble %.3f ms  diag %.3f  panel %.3f  bad %d  
 
 # mean-only prediction through corr_tile_kernel (predict mode): d = 6 (n = 300) and d = 10 (the C2 model)
 m.set_groups(2); m.profile(False)
-for (nn, dd) in ((300, 6), (1000, 10)):
+for (nn, dd) in (() if os.environ.get("KB200_TIME_C2_ONLY") else ((300, 6), (1000, 10))):
     rng = np.random.default_rng(3)
     Xs = rng.uniform(-1, 1, (nn, dd)); ys = np.sin(Xs.sum(1)) + 3.0
     mm = GpuModel(Xs, ys, np.ones((nn, 1)), [0])
