@@ -27,6 +27,9 @@
 namespace kb200 {
 namespace {
 
+#ifndef KB200_RAGGED          // skip the identity padding of the ragged last tile (n % 128 != 0); 0: A/B builds
+#define KB200_RAGGED 1
+#endif
 constexpr int HT = 256;                       // threads per CTA
 constexpr int HWARPS = HT / 32;
 constexpr int HROWS = 64;                     // rows of a half tile
@@ -73,20 +76,56 @@ __device__ __forceinline__ void sqrt_rsqrt(double x, double& s, double& h_out) {
   h_out = h;
 }
 
-// ------------------------------------------------------------------ GEMM core (8 warps: 2 x 4 of 32x32)
-__device__ __forceinline__ void mma_slab_h(double (&acc)[4][4][2], const double* As, const double* Bs, const WarpPos& w) {
+// ------------------------------------------------------------------ GEMM core (8 warps: 2 x 4, 4 x 4 blocks of 8 x 8 each)
+// Block ownership is INTERLEAVED: warp (wm, wn) owns the row blocks 2 mt + wm and the column blocks 4 nt + wn
+// (mt, nt = 0..3).  For a full tile this is the same work as contiguous 32 x 32 warp tiles (8 rows of a slab are 1 KiB
+// apart whichever block they belong to: no change in bank conflicts).  For the RAGGED last tile of a matrix whose n is not
+// a multiple of 128 the real row / column blocks 0 .. nrb-1 / 0 .. ncb-1 are spread evenly over the warps: the padded
+// blocks (identity rows: exact zeros in every product) are skipped and the remaining work stays balanced -- n = 1000:
+// the last half tile of every tile column has 40 real rows of 64 (5 blocks: 3 + 2 per warp instead of 4 + 4).
+__device__ __forceinline__ int blk_row(const WarpPos& w, int mt) { return 8 * (2 * mt + w.wm); }
+__device__ __forceinline__ int blk_col(const WarpPos& w, int nt) { return 8 * (4 * nt + w.wn); }
+
+template <int NMT, int NNT>
+__device__ __forceinline__ void mma_slab_h_t(double (&acc)[4][4][2], const double* As, const double* Bs, const WarpPos& w) {
 #pragma unroll
   for (int kq = 0; kq < 4; ++kq) {
     const int sw = ((kq ^ (w.g & 3)) << 2) + w.t;
-    double a[4], b[4];
+    double a[NMT], b[NNT];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) a[mt] = As[(32 * w.wm + 8 * mt + w.g) * KS + sw];
+    for (int mt = 0; mt < NMT; ++mt) a[mt] = As[(blk_row(w, mt) + w.g) * KS + sw];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[(32 * w.wn + 8 * nt + w.g) * KS + sw];
+    for (int nt = 0; nt < NNT; ++nt) b[nt] = Bs[(blk_col(w, nt) + w.g) * KS + sw];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < NMT; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+      for (int nt = 0; nt < NNT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+__device__ __forceinline__ void mma_slab_h(double (&acc)[4][4][2], const double* As, const double* Bs, const WarpPos& w) {
+  mma_slab_h_t<4, 4>(acc, As, Bs, w);
+}
+
+// the same for a ragged tile: only the warp's first nmt row blocks and nnt column blocks are real (warp-uniform switch
+// over compile-time shapes: predicating the 64 DMMAs of the full shape one by one measured slower than the padding it saves)
+template <int NMT>
+__device__ __forceinline__ void mma_slab_h_cols(double (&acc)[4][4][2], const double* As, const double* Bs, const WarpPos& w, int nnt) {
+  switch (nnt) {
+    case 4: mma_slab_h_t<NMT, 4>(acc, As, Bs, w); break;
+    case 3: mma_slab_h_t<NMT, 3>(acc, As, Bs, w); break;
+    case 2: mma_slab_h_t<NMT, 2>(acc, As, Bs, w); break;
+    case 1: mma_slab_h_t<NMT, 1>(acc, As, Bs, w); break;
+    default: break;
+  }
+}
+__device__ __forceinline__ void mma_slab_h_part(double (&acc)[4][4][2], const double* As, const double* Bs, const WarpPos& w,
+                                                int nmt, int nnt) {
+  switch (nmt) {
+    case 4: mma_slab_h_cols<4>(acc, As, Bs, w, nnt); break;
+    case 3: mma_slab_h_cols<3>(acc, As, Bs, w, nnt); break;
+    case 2: mma_slab_h_cols<2>(acc, As, Bs, w, nnt); break;
+    case 1: mma_slab_h_cols<1>(acc, As, Bs, w, nnt); break;
+    default: break;
   }
 }
 
@@ -302,16 +341,17 @@ __device__ __forceinline__ void syrk_acc_init(double (&acc)[17][2], const double
   }
 }
 
-// one 16-wide slab of the SYRK for warp W: row blocks 15 - W (tiles C = 0 .. 15 - W) and W (C = 0 .. W)
-template <int W>
+// one 16-wide slab of the SYRK for warp W: row blocks 15 - W (tiles C = 0 .. 15 - W) and W (C = 0 .. W).
+// HI = false: the high row block is identity padding (ragged last tile of the matrix) and is skipped.
+template <int W, bool HI = true>
 __device__ __forceinline__ void syrk_slab(double (&acc)[17][2], const double* As, int g, int t) {
   constexpr int NHI = 16 - W;
 #pragma unroll
   for (int kq = 0; kq < 4; ++kq) {
     const int sw = ((kq ^ (g & 3)) << 2) + t;
-    const double a_hi = As[(8 * (15 - W) + g) * KS + sw], a_lo = As[(8 * W + g) * KS + sw];
+    const double a_hi = HI ? As[(8 * (15 - W) + g) * KS + sw] : 0.0, a_lo = As[(8 * W + g) * KS + sw];
 #pragma unroll
-    for (int u = 0; u < 17; ++u) {
+    for (int u = HI ? 0 : NHI; u < 17; ++u) {
       const int C = u < NHI ? u : u - NHI;
       const double b = As[(8 * C + g) * KS + sw];
       dmma884(acc[u][0], acc[u][1], u < NHI ? a_hi : a_lo, b);
@@ -528,6 +568,9 @@ chol_diag_half_kernel(CholArgs A, int j) {
   }
 
   const int nslab = A.rl_mode ? 0 : NSLAB * j;      // right-looking: tile (j, j) and the RHS are already updated
+  // ragged last tile (n % 128 != 0): row blocks >= nrb are identity padding, their rows of L_j,0..j-1 are zero
+  const int nrb = KB200_RAGGED ? (min(TB, A.n - j * TB) + 7) >> 3 : 16;
+  const bool hi_on = hiR < nrb, lo_on = loR < nrb;
   auto issue = [&](int q) {
     const int st = q % DNST, use = q / DNST;
     if (use > 0) mbar_wait(&empty[st], (uint32_t)((use - 1) & 1));
@@ -548,15 +591,28 @@ chol_diag_half_kernel(CholArgs A, int j) {
     if (tid == 0 && q + DLOOK < nslab) issue(q + DLOOK);
     mbar_wait(&full[st], (uint32_t)((q / DNST) & 1));
     const double* As = ring + (size_t)st * SLAB_ELEMS;
-    switch (warp) {   // the warp's two row blocks are compile-time constants inside: no per-DMMA selects (ncu r2d: 128 FSEL per slab)
-      case 0: syrk_slab<0>(acc, As, g, t); break;
-      case 1: syrk_slab<1>(acc, As, g, t); break;
-      case 2: syrk_slab<2>(acc, As, g, t); break;
-      case 3: syrk_slab<3>(acc, As, g, t); break;
-      case 4: syrk_slab<4>(acc, As, g, t); break;
-      case 5: syrk_slab<5>(acc, As, g, t); break;
-      case 6: syrk_slab<6>(acc, As, g, t); break;
-      default: syrk_slab<7>(acc, As, g, t); break;
+    if (hi_on) {
+      switch (warp) {   // the warp's two row blocks are compile-time constants inside: no per-DMMA selects (ncu r2d: 128 FSEL per slab)
+        case 0: syrk_slab<0>(acc, As, g, t); break;
+        case 1: syrk_slab<1>(acc, As, g, t); break;
+        case 2: syrk_slab<2>(acc, As, g, t); break;
+        case 3: syrk_slab<3>(acc, As, g, t); break;
+        case 4: syrk_slab<4>(acc, As, g, t); break;
+        case 5: syrk_slab<5>(acc, As, g, t); break;
+        case 6: syrk_slab<6>(acc, As, g, t); break;
+        default: syrk_slab<7>(acc, As, g, t); break;
+      }
+    } else if (lo_on) {   // ragged last tile: the high row block of this warp is padding
+      switch (warp) {
+        case 0: syrk_slab<0, false>(acc, As, g, t); break;
+        case 1: syrk_slab<1, false>(acc, As, g, t); break;
+        case 2: syrk_slab<2, false>(acc, As, g, t); break;
+        case 3: syrk_slab<3, false>(acc, As, g, t); break;
+        case 4: syrk_slab<4, false>(acc, As, g, t); break;
+        case 5: syrk_slab<5, false>(acc, As, g, t); break;
+        case 6: syrk_slab<6, false>(acc, As, g, t); break;
+        default: syrk_slab<7, false>(acc, As, g, t); break;
+      }
     }
     // fused forward substitution: tacc[qq] += L_jk[rr][c] * Z_k[c]      (likelihood_func.py:183-193)
     // Z_k comes from a rolling two-tile shared-memory buffer: tile k + 1 is fetched into registers at the
@@ -689,9 +745,56 @@ __host__ __device__ constexpr int wslab_base(int s) {                           
 }
 static_assert(wslab_base(NSLAB) <= P_CS, "trimmed slabs 2..7 must fit in the dead Cs area");
 
-__global__ void __launch_bounds__(HT, 2)
-chol_panel_half_kernel(CholArgs A, int j) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+// the right-looking solve of one warp's 8 rows (C-fragment layout, 16 column tiles) against the resident L_jj:
+// finished tile x 8x8 inverse = 2 DMMA, then DMMA updates to its right.  RAGGED: only the first ncb column blocks are real.
+template <bool RAGGED>
+__device__ __forceinline__ void panel_solve_rows(double (&x)[16][2], const double* stages, const double* W8s, uint64_t* wbar,
+                                                 int lane, int ncb) {
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int s = 0; s < NSLAB; ++s) {
+    if (RAGGED && 2 * s >= ncb) break;
+    mbar_wait(&wbar[s], 0);
+    // virtual slab base: row r of slab s at Ls[r * KS + ...] (rows < 16 s of the trimmed slabs are not there)
+    const double* Ls = s < 2 ? stages + P_WS01 + s * SLAB_ELEMS : stages + wslab_base(s) - KS * s * KS;
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt) {
+      const int t = 2 * s + tt;
+      if (RAGGED && t >= ncb) break;
+      double a0, a1;
+      cfrag_to_afrag(x[t][0], x[t][1], a0, a1, lane);
+      double y0 = 0.0, y1 = 0.0;
+      dmma884(y0, y1, a0, W8s[t * 64 + g * 8 + tq]);
+      dmma884(y0, y1, a1, W8s[t * 64 + g * 8 + 4 + tq]);
+      x[t][0] = y0;
+      x[t][1] = y1;
+      if (t < 15) {
+        cfrag_to_afrag(y0, y1, a0, a1, lane);
+        a0 = -a0;
+        a1 = -a1;
+#pragma unroll
+        for (int ct = t + 1; ct < 16; ++ct) {
+          if (RAGGED && ct >= ncb) break;
+          const double* lrow = Ls + (8 * ct + g) * KS + tq;
+          const double b0 = lrow[((2 * tt) ^ (g & 3)) << 2];
+          const double b1 = lrow[((2 * tt + 1) ^ (g & 3)) << 2];
+          dmma884(x[ct][0], x[ct][1], a0, b0);
+          dmma884(x[ct][0], x[ct][1], a1, b1);
+        }
+      }
+    }
+  }
+}
+
+struct PanelPtrs {
+  const double *rowA, *rowB, *Ljj, *W8j;
+  double* Cij;
+  long ssq_base;
+  int hr, rows_real, cols_real;
+};
+
+template <bool RAGGED>
+__device__ __forceinline__ void panel_half_body(const CholArgs& A, int j, const PanelPtrs& P, unsigned char* smem_raw) {
   double* stages = reinterpret_cast<double*>(smem_raw);
   double* Cs = stages;
   double* W8s = stages + P_W8;
@@ -699,68 +802,15 @@ chol_panel_half_kernel(CholArgs A, int j) {
   uint64_t* empty = full + HNST;
   uint64_t* wbar = empty + HNST;        // [NSLAB]
   uint64_t* w8bar = wbar + NSLAB;
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const WarpPos w{warp & 1, warp >> 1, lane >> 2, lane & 3};
-  const int hr = blockIdx.x & 1;                     // which 64 rows of the tile
-  const double *rowA, *rowB, *Ljj, *W8j;
-  double* Cij;
-  long ssq_base = 0;
-  if (A.pred_mode && A.rl_mode >= 2) {
-    // prediction, right-looking (few point tiles, many sample tiles): after V_j = (psi_j - ...) L_jj^-T every later tile of
-    // the point-tile row is updated at once, psi_i -= V_j L_ij^T for i > j: (nt - 1 - j) x more CTAs than the left-looking
-    // launch of column j has.  blockIdx.x >> 1 = pt (nt - 1 - j) + a, i = j + 1 + a.
-    const int M = A.nt - 1 - j;
-    const long t = blockIdx.x >> 1, pt = t / M;
-    const int i = j + 1 + (int)(t - pt * M);
-    double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
-    rowA = base + (size_t)j * TILE_ELEMS;                            // V_j, 8 slabs
-    rowB = A.L + (size_t)tri_index(i, j) * TILE_ELEMS;               // L_ij, 8 slabs
-    Cij = base + (size_t)i * TILE_ELEMS;
-    Ljj = A.L;                                                       // unused
-    W8j = A.W8 + (size_t)j * 1024;                                   // fetched, unused
-  } else if (A.pred_mode) {
-    const long pt = blockIdx.x >> 1;
-    double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
-    rowA = base;
-    Cij = base + (size_t)j * TILE_ELEMS;
-    rowB = A.L + (size_t)tri_index(j, 0) * TILE_ELEMS;
-    Ljj = A.L + (size_t)tri_index(j, j) * TILE_ELEMS;
-    W8j = A.W8 + (size_t)j * 1024;
-    ssq_base = pt * TB + hr * HROWS;
-  } else if (A.rl_mode >= 2) {
-    // right-looking trailing update after column k = j: C_ib -= L_ik L_bk^T for k < b <= i.
-    // mode 2: all pairs from row/column k + 1 + i0 on: blockIdx.x >> 1 = a (a + 1) / 2 + c enumerates
-    //         (i, b) = (k + 1 + i0 + a, k + 1 + i0 + c), c <= a;  mode 3: the strip b = k + 1 only (look-ahead)
-    const int t = blockIdx.x >> 1;
-    int a, c;
-    if (A.rl_mode == 3) {
-      a = t;
-      c = 0;
-    } else {
-      a = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
-      while ((a + 1) * (a + 2) / 2 <= t) ++a;
-      while (a * (a + 1) / 2 > t) --a;
-      c = t - a * (a + 1) / 2;
-    }
-    const int i = j + 1 + A.i0 + a, b = j + 1 + A.i0 + c;
-    const long m = blockIdx.y;
-    double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
-    rowA = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;       // the 8 slabs of tile (i, k)
-    rowB = tiles + (size_t)tri_index(b, j) * TILE_ELEMS;       // the 8 slabs of tile (b, k)
-    Cij = tiles + (size_t)tri_index(i, b) * TILE_ELEMS;
-    Ljj = tiles;                                               // unused
-    W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;                // fetched, unused
-  } else {
-    const int i = j + 1 + A.i0 + (blockIdx.x >> 1);
-    const long m = blockIdx.y;
-    double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
-    rowA = tiles + (size_t)tri_index(i, 0) * TILE_ELEMS;
-    rowB = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
-    Cij = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;
-    Ljj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
-    W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;
-  }
+  const double *rowA = P.rowA, *rowB = P.rowB, *Ljj = P.Ljj, *W8j = P.W8j;
+  double* Cij = P.Cij;
+  const long ssq_base = P.ssq_base;
+  const int hr = P.hr, rows_real = P.rows_real, cols_real = P.cols_real;
+  const int nrb = (rows_real + 7) >> 3, ncb = (cols_real + 7) >> 3;      // real 8-row / 8-column blocks: 1..8, 1..16
+  const int nmt = (nrb - w.wm + 1) >> 1, nnt = (ncb - w.wn + 3) >> 2;    // ... of this warp (blocks 2 mt + wm, 4 nt + wn)
+  constexpr bool ragged = RAGGED;                    // CTA-uniform: nrb < 8 || ncb < 16
   const double* gA = rowA + hr * HALF_SLAB;          // rows 64 hr .. of every slab are 8 KiB contiguous
   if (tid == 0) {
     for (int i = 0; i < HNST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], HWARPS); }
@@ -778,8 +828,9 @@ chol_panel_half_kernel(CholArgs A, int j) {
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
-      const double2 p = *reinterpret_cast<const double2*>(Cij + tile_off(HROWS * hr + r, c));
+      const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
+      double2 p = make_double2(0.0, 0.0);
+      if (!ragged || (mt < nmt && nt < nnt)) p = *reinterpret_cast<const double2*>(Cij + tile_off(HROWS * hr + r, c));
       acc[mt][nt][0] = -p.x;
       acc[mt][nt][1] = -p.y;
     }
@@ -803,7 +854,8 @@ chol_panel_half_kernel(CholArgs A, int j) {
     if (tid == 0 && q + HLOOK < nslab) issue(q + HLOOK);
     mbar_wait(&full[st], (uint32_t)((q / HNST) & 1));
     const double* As = stages + (size_t)st * HSTAGE;
-    mma_slab_h(acc, As, As + HALF_SLAB, w);
+    if (!ragged) mma_slab_h(acc, As, As + HALF_SLAB, w);
+    else mma_slab_h_part(acc, As, As + HALF_SLAB, w, nmt, nnt);
     // Consumer release, one slab late: the stage of slab q - 1 is handed back here.  The bulk copy that
     // re-fills a stage runs in the async proxy and is not ordered behind generic-proxy loads that are
     // merely *issued* (an arrive right behind the last LDS of slab q let the copy land under pending loads
@@ -820,8 +872,9 @@ chol_panel_half_kernel(CholArgs A, int j) {
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
-        *reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
+        const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
+        if (!ragged || (mt < nmt && nt < nnt))
+          *reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
       }
     return;
   }
@@ -839,7 +892,7 @@ chol_panel_half_kernel(CholArgs A, int j) {
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      const int r = 32 * w.wm + 8 * mt + w.g, c = 32 * w.wn + 8 * nt + 2 * w.t;
+      const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
       *reinterpret_cast<double2*>(Cs + half_off(r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
     }
   __syncthreads();
@@ -865,40 +918,23 @@ chol_panel_half_kernel(CholArgs A, int j) {
     }
   }
   mbar_wait(w8bar, 0);
-#pragma unroll
-  for (int s = 0; s < NSLAB; ++s) {
-    mbar_wait(&wbar[s], 0);
-    // virtual slab base: row r of slab s at Ls[r * KS + ...] (rows < 16 s of the trimmed slabs are not there)
-    const double* Ls = s < 2 ? stages + P_WS01 + s * SLAB_ELEMS : stages + wslab_base(s) - KS * s * KS;
-#pragma unroll
-    for (int tt = 0; tt < 2; ++tt) {
-      const int t = 2 * s + tt;
-      double a0, a1;
-      cfrag_to_afrag(x[t][0], x[t][1], a0, a1, lane);
-      double y0 = 0.0, y1 = 0.0;
-      dmma884(y0, y1, a0, W8s[t * 64 + g * 8 + tq]);
-      dmma884(y0, y1, a1, W8s[t * 64 + g * 8 + 4 + tq]);
-      x[t][0] = y0;
-      x[t][1] = y1;
-      if (t < 15) {
-        cfrag_to_afrag(y0, y1, a0, a1, lane);
-        a0 = -a0;
-        a1 = -a1;
-#pragma unroll
-        for (int ct = t + 1; ct < 16; ++ct) {
-          const double* lrow = Ls + (8 * ct + g) * KS + tq;
-          const double b0 = lrow[((2 * tt) ^ (g & 3)) << 2];
-          const double b1 = lrow[((2 * tt + 1) ^ (g & 3)) << 2];
-          dmma884(x[ct][0], x[ct][1], a0, b0);
-          dmma884(x[ct][0], x[ct][1], a1, b1);
-        }
-      }
+  if (!ragged) {
+    panel_solve_rows<false>(x, stages, W8s, wbar, lane, 16);
+  } else {
+    if (8 * warp < rows_real) {
+      if (ncb == 16) panel_solve_rows<false>(x, stages, W8s, wbar, lane, 16);     // ragged rows only: the plain sweep
+      else panel_solve_rows<true>(x, stages, W8s, wbar, lane, ncb);
     }
+    // (a ragged solve does not wait for the slabs it does not read: every copy has to land before the CTA may exit)
+#pragma unroll
+    for (int s = 0; s < NSLAB; ++s) mbar_wait(&wbar[s], 0);
   }
   // ---- store X and, for prediction, accumulate ||x_row||^2
+  if (ragged && 8 * warp >= rows_real) return;     // padded rows: the zeros in place stay (likelihood; points are never padded)
   double rs = 0.0;
 #pragma unroll
   for (int ct = 0; ct < 16; ++ct) {
+    if (ragged && ct >= ncb) break;                // padded columns: zeros in place
     *reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + xr, 8 * ct + 2 * tq)) = make_double2(x[ct][0], x[ct][1]);
     rs = fma(x[ct][0], x[ct][0], rs);
     rs = fma(x[ct][1], x[ct][1], rs);
@@ -911,6 +947,87 @@ chol_panel_half_kernel(CholArgs A, int j) {
       *dst = (j == 0 ? 0.0 : *dst) + rs;
     }
   }
+}
+
+__global__ void __launch_bounds__(HT, 2)
+chol_panel_half_kernel(CholArgs A, int j) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int hr = blockIdx.x & 1;                     // which 64 rows of the tile
+  const double *rowA, *rowB, *Ljj, *W8j;
+  double* Cij;
+  long ssq_base = 0;
+  // real rows of this half tile / real columns of the output tile (ragged last tile of a matrix with n % 128 != 0: the
+  // rest is identity padding -- zero rows of L, zero columns of psi -- and is skipped, see mma_slab_h)
+  int rows_real = HROWS, cols_real = TB;
+  if (A.pred_mode && A.rl_mode >= 2) {
+    // prediction, right-looking (few point tiles, many sample tiles): after V_j = (psi_j - ...) L_jj^-T every later tile of
+    // the point-tile row is updated at once, psi_i -= V_j L_ij^T for i > j: (nt - 1 - j) x more CTAs than the left-looking
+    // launch of column j has.  blockIdx.x >> 1 = pt (nt - 1 - j) + a, i = j + 1 + a.
+    const int M = A.nt - 1 - j;
+    const long t = blockIdx.x >> 1, pt = t / M;
+    const int i = j + 1 + (int)(t - pt * M);
+    double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
+    rowA = base + (size_t)j * TILE_ELEMS;                            // V_j, 8 slabs
+    rowB = A.L + (size_t)tri_index(i, j) * TILE_ELEMS;               // L_ij, 8 slabs
+    Cij = base + (size_t)i * TILE_ELEMS;
+    Ljj = A.L;                                                       // unused
+    W8j = A.W8 + (size_t)j * 1024;                                   // fetched, unused
+    cols_real = min(TB, A.n - i * TB);
+  } else if (A.pred_mode) {
+    const long pt = blockIdx.x >> 1;
+    double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
+    rowA = base;
+    Cij = base + (size_t)j * TILE_ELEMS;
+    rowB = A.L + (size_t)tri_index(j, 0) * TILE_ELEMS;
+    Ljj = A.L + (size_t)tri_index(j, j) * TILE_ELEMS;
+    W8j = A.W8 + (size_t)j * 1024;
+    ssq_base = pt * TB + hr * HROWS;
+    cols_real = min(TB, A.n - j * TB);
+  } else if (A.rl_mode >= 2) {
+    // right-looking trailing update after column k = j: C_ib -= L_ik L_bk^T for k < b <= i.
+    // mode 2: all pairs from row/column k + 1 + i0 on: blockIdx.x >> 1 = a (a + 1) / 2 + c enumerates
+    //         (i, b) = (k + 1 + i0 + a, k + 1 + i0 + c), c <= a;  mode 3: the strip b = k + 1 only (look-ahead)
+    const int t = blockIdx.x >> 1;
+    int a, c;
+    if (A.rl_mode == 3) {
+      a = t;
+      c = 0;
+    } else {
+      a = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+      while ((a + 1) * (a + 2) / 2 <= t) ++a;
+      while (a * (a + 1) / 2 > t) --a;
+      c = t - a * (a + 1) / 2;
+    }
+    const int i = j + 1 + A.i0 + a, b = j + 1 + A.i0 + c;
+    const long m = blockIdx.y;
+    double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+    rowA = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;       // the 8 slabs of tile (i, k)
+    rowB = tiles + (size_t)tri_index(b, j) * TILE_ELEMS;       // the 8 slabs of tile (b, k)
+    Cij = tiles + (size_t)tri_index(i, b) * TILE_ELEMS;
+    Ljj = tiles;                                               // unused
+    W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;                // fetched, unused
+    rows_real = min(HROWS, A.n - i * TB - hr * HROWS);
+    cols_real = min(TB, A.n - b * TB);
+  } else {
+    const int i = j + 1 + A.i0 + (blockIdx.x >> 1);
+    const long m = blockIdx.y;
+    double* tiles = A.L + (size_t)m * A.tiles_per_mat * TILE_ELEMS;
+    rowA = tiles + (size_t)tri_index(i, 0) * TILE_ELEMS;
+    rowB = tiles + (size_t)tri_index(j, 0) * TILE_ELEMS;
+    Cij = tiles + (size_t)tri_index(i, j) * TILE_ELEMS;
+    Ljj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
+    W8j = A.W8 + ((size_t)m * A.nt + j) * 1024;
+    rows_real = min(HROWS, A.n - i * TB - hr * HROWS);
+  }
+#if !KB200_RAGGED
+  rows_real = HROWS;
+  cols_real = TB;
+#endif
+  if (rows_real <= 0) return;                        // a half tile of padding only: zeros stay zeros (whole CTA, before any barrier)
+  const PanelPtrs P{rowA, rowB, Ljj, W8j, Cij, ssq_base, hr, rows_real, cols_real};
+  // CTA-uniform dispatch: the full-tile body is compiled without any trace of the ragged one
+  if (rows_real < HROWS || cols_real < TB) panel_half_body<true>(A, j, P, smem_raw);
+  else panel_half_body<false>(A, j, P, smem_raw);
 }
 
 // right-looking RHS update after column k: rw_i -= L_ik z_k for the tiles i > k (nq right-hand sides);
