@@ -539,9 +539,9 @@ chol_diag_half_kernel(CholArgs A, int j) {
   }
   __syncthreads();
 
+  const int hiR = 15 - warp, loR = warp, nhi = hiR + 1;
   // ---- SYRK: warp w owns the 8-row blocks hiR = 15 - w (tiles C = 0..hiR) and loR = w (C = 0..w):
   //      17 of the 136 lower 8x8 tiles each.  acc[u]: u < nhi -> (hiR, u), else (loR, u - nhi).
-  const int hiR = 15 - warp, loR = warp, nhi = hiR + 1;
   // The accumulators start at -Psi_jj (and -R_j), not at zero: the partial sums then walk from the entry down
   // to the (much smaller) Schur complement exactly as a right-looking update would, and every rounding is
   // relative to the current partial value instead of to the O(1) products that cancel at the end.  On
@@ -822,19 +822,6 @@ __device__ __forceinline__ void panel_half_body(const CholArgs& A, int j, const 
   }
   __syncthreads();
 
-  // acc starts at -C_ij (see chol_diag_half_kernel: rounding relative to the shrinking partial value)
-  double acc[4][4][2];
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
-      double2 p = make_double2(0.0, 0.0);
-      if (!ragged || (mt < nmt && nt < nnt)) p = *reinterpret_cast<const double2*>(Cij + tile_off(HROWS * hr + r, c));
-      acc[mt][nt][0] = -p.x;
-      acc[mt][nt][1] = -p.y;
-    }
-
   // ---- GEMM: acc = -C + A(64 x 128 j) B(128 x 128 j)^T, operands streamed slab by slab
   // (right-looking variant: no accumulation before the solve (T), one tile of depth for the update (U))
   const int nslab = A.rl_mode == 1 ? 0 : (A.rl_mode >= 2 ? NSLAB : NSLAB * j);
@@ -846,75 +833,110 @@ __device__ __forceinline__ void panel_half_body(const CholArgs& A, int j, const 
     bulk_g2s(dst, gA + (size_t)q * SLAB_ELEMS, HALF_BYTES, &full[st]);
     bulk_g2s(dst + HALF_SLAB, rowB + (size_t)q * SLAB_ELEMS, SLAB_BYTES, &full[st]);
   };
+  // (the first slabs are in flight while the C tile is fetched)
   if (tid == 0)
     for (int q = 0; q < HLOOK && q < nslab; ++q) issue(q);
-#pragma unroll 1
-  for (int q = 0; q < nslab; ++q) {
-    const int st = q % HNST;
-    if (tid == 0 && q + HLOOK < nslab) issue(q + HLOOK);
-    mbar_wait(&full[st], (uint32_t)((q / HNST) & 1));
-    const double* As = stages + (size_t)st * HSTAGE;
-    if (!ragged) mma_slab_h(acc, As, As + HALF_SLAB, w);
-    else mma_slab_h_part(acc, As, As + HALF_SLAB, w, nmt, nnt);
-    // Consumer release, one slab late: the stage of slab q - 1 is handed back here.  The bulk copy that
-    // re-fills a stage runs in the async proxy and is not ordered behind generic-proxy loads that are
-    // merely *issued* (an arrive right behind the last LDS of slab q let the copy land under pending loads
-    // with two CTAs per SM, profiles/r1k_half_race.md).  Every DMMA of slab q - 1 precedes this point in
-    // the instruction stream, and a DMMA cannot issue before the loads of its operands have returned, so
-    // nothing of slab q - 1 is still being read.  The ring has a slab of slack for it (refill = slab q - 2).
-    if (q > 0) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[(q - 1) % HNST]);
-    }
-  }
-  if (A.rl_mode >= 2) {   // trailing update: C -= acc in place, nothing to solve
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
-        if (!ragged || (mt < nmt && nt < nnt))
-          *reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
-      }
-    return;
-  }
-  fence_proxy_async();
-  __syncthreads();       // ring drained: Cs and the first two L_jj slabs may overwrite it
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      mbar_expect_tx(&wbar[s], SLAB_BYTES);
-      bulk_g2s(stages + P_WS01 + s * SLAB_ELEMS, Ljj + (size_t)s * SLAB_ELEMS, SLAB_BYTES, &wbar[s]);
-    }
-  }
-  // ---- C = -acc = Psi_ij - sum -> Cs
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
-      *reinterpret_cast<double2*>(Cs + half_off(r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
-    }
-  __syncthreads();
+
   // ---- every warp takes 8 complete rows (C-fragment layout, 16 column tiles) and solves them
   const int g = w.g, tq = w.t;
   const int xr = 8 * warp + g;
   double x[16][2];
+  if (nslab == 0) {
+    // pure solve (tile column 0; every solve of the right-looking schedule): nothing to accumulate, so no detour through
+    // the accumulators and shared memory -- the rows come straight from the tile, the whole of L_jj is requested at once
+    if (tid == 0) {
 #pragma unroll
-  for (int ct = 0; ct < 16; ++ct) {
-    const double2 p = *reinterpret_cast<const double2*>(Cs + half_off(xr, 8 * ct + 2 * tq));
-    x[ct][0] = p.x;
-    x[ct][1] = p.y;
-  }
-  // Cs is dead: the rest of L_jj (rows >= 16 s of slab s) goes where it was
-  fence_proxy_async();
-  __syncthreads();
-  if (tid == 0) {
+      for (int s = 0; s < NSLAB; ++s) {
+        const uint32_t bytes = s < 2 ? SLAB_BYTES : (uint32_t)wslab_rows(s) * KS * 8;
+        mbar_expect_tx(&wbar[s], bytes);
+        if (s < 2) bulk_g2s(stages + P_WS01 + s * SLAB_ELEMS, Ljj + (size_t)s * SLAB_ELEMS, bytes, &wbar[s]);
+        else bulk_g2s(stages + wslab_base(s), Ljj + (size_t)s * SLAB_ELEMS + (size_t)KS * s * KS, bytes, &wbar[s]);
+      }
+    }
 #pragma unroll
-    for (int s = 2; s < NSLAB; ++s) {
-      const uint32_t bytes = (uint32_t)wslab_rows(s) * KS * 8;
-      mbar_expect_tx(&wbar[s], bytes);
-      bulk_g2s(stages + wslab_base(s), Ljj + (size_t)s * SLAB_ELEMS + (size_t)KS * s * KS, bytes, &wbar[s]);
+    for (int ct = 0; ct < 16; ++ct) {
+      const double2 p = *reinterpret_cast<const double2*>(Cij + tile_off(HROWS * hr + xr, 8 * ct + 2 * tq));
+      x[ct][0] = p.x;
+      x[ct][1] = p.y;
+    }
+  } else {
+    // acc starts at -C_ij (see chol_diag_half_kernel: rounding relative to the shrinking partial value)
+    double acc[4][4][2];
+  #pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+  #pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
+        double2 p = make_double2(0.0, 0.0);
+        if (!ragged || (mt < nmt && nt < nnt)) p = *reinterpret_cast<const double2*>(Cij + tile_off(HROWS * hr + r, c));
+        acc[mt][nt][0] = -p.x;
+        acc[mt][nt][1] = -p.y;
+      }
+
+  #pragma unroll 1
+    for (int q = 0; q < nslab; ++q) {
+      const int st = q % HNST;
+      if (tid == 0 && q + HLOOK < nslab) issue(q + HLOOK);
+      mbar_wait(&full[st], (uint32_t)((q / HNST) & 1));
+      const double* As = stages + (size_t)st * HSTAGE;
+      if (!ragged) mma_slab_h(acc, As, As + HALF_SLAB, w);
+      else mma_slab_h_part(acc, As, As + HALF_SLAB, w, nmt, nnt);
+      // Consumer release, one slab late: the stage of slab q - 1 is handed back here.  The bulk copy that
+      // re-fills a stage runs in the async proxy and is not ordered behind generic-proxy loads that are
+      // merely *issued* (an arrive right behind the last LDS of slab q let the copy land under pending loads
+      // with two CTAs per SM, profiles/r1k_half_race.md).  Every DMMA of slab q - 1 precedes this point in
+      // the instruction stream, and a DMMA cannot issue before the loads of its operands have returned, so
+      // nothing of slab q - 1 is still being read.  The ring has a slab of slack for it (refill = slab q - 2).
+      if (q > 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[(q - 1) % HNST]);
+      }
+    }
+    if (A.rl_mode >= 2) {   // trailing update: C -= acc in place, nothing to solve
+  #pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+  #pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
+          if (!ragged || (mt < nmt && nt < nnt))
+            *reinterpret_cast<double2*>(Cij + tile_off(HROWS * hr + r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
+        }
+      return;
+    }
+    fence_proxy_async();
+    __syncthreads();       // ring drained: Cs and the first two L_jj slabs may overwrite it
+    if (tid == 0) {
+  #pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        mbar_expect_tx(&wbar[s], SLAB_BYTES);
+        bulk_g2s(stages + P_WS01 + s * SLAB_ELEMS, Ljj + (size_t)s * SLAB_ELEMS, SLAB_BYTES, &wbar[s]);
+      }
+    }
+    // ---- C = -acc = Psi_ij - sum -> Cs
+  #pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+  #pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = blk_row(w, mt) + w.g, c = blk_col(w, nt) + 2 * w.t;
+        *reinterpret_cast<double2*>(Cs + half_off(r, c)) = make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
+      }
+    __syncthreads();
+  #pragma unroll
+    for (int ct = 0; ct < 16; ++ct) {
+      const double2 p = *reinterpret_cast<const double2*>(Cs + half_off(xr, 8 * ct + 2 * tq));
+      x[ct][0] = p.x;
+      x[ct][1] = p.y;
+    }
+    // Cs is dead: the rest of L_jj (rows >= 16 s of slab s) goes where it was
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+  #pragma unroll
+      for (int s = 2; s < NSLAB; ++s) {
+        const uint32_t bytes = (uint32_t)wslab_rows(s) * KS * 8;
+        mbar_expect_tx(&wbar[s], bytes);
+        bulk_g2s(stages + wslab_base(s), Ljj + (size_t)s * SLAB_ELEMS + (size_t)KS * s * KS, bytes, &wbar[s]);
+      }
     }
   }
   mbar_wait(w8bar, 0);

@@ -1,8 +1,8 @@
 """Monkey-patch a live ``kadal`` package so that its Kriging hot path runs on the GPU.
 
 KADAL binds ``likelihood`` and ``prediction`` by name at import time in three modules
-(kriging_model.py:9-10, optim_tools/MOBO.py:11, surrogate_models/supports/krigloocv2.py:3-4);
-replacing those module globals is the whole integration.  The EHVI scorers are bound
+(kriging_model.py:9-10, optim_tools/MOBO.py:11, surrogate_models/supports/krigloocv2.py:3-4) and the two LOOCV
+routines in kriging_model.py:7-8; replacing those module globals is the whole integration.  The EHVI scorers are bound
 the same way (optim_tools/acquifunc_opt.py:5 imports ``ehvicalc, ehvicalc_vec, ehvicalc_kmac3d`` from
 optim_tools/ehvi/EHVIcomputation.py, which itself needs the compiled extension ``kmac``,
 EHVIcomputation.py:3-12): ``install`` puts a ``kmac`` stand-in over ``kb200_ehvi3d`` in place when the
@@ -21,10 +21,12 @@ def _replacements():
     from .likelihood_func import likelihood
     from .prediction import prediction
     from . import ehvi
+    from .loocv import loocv2, loocv_fast
     hot = {"likelihood": likelihood, "prediction": prediction}
     scorers = {"ehvicalc": ehvi.ehvicalc, "ehvicalc_vec": ehvi.ehvicalc_vec, "ehvicalc_kmac3d": ehvi.ehvicalc_kmac3d}
     return (
-        ("kadal.surrogate_models.kriging_model", hot),
+        # loocvcalc (kriging_model.py:291-294) looks `loocv` / `loocv2` up at call time: both become one closed-form pass
+        ("kadal.surrogate_models.kriging_model", dict(hot, loocv=loocv_fast, loocv2=loocv2)),
         ("kadal.surrogate_models.kpls_model", hot),
         ("kadal.surrogate_models.supports.krigloocv2", hot),
         ("kadal.surrogate_models.supports.likelihood_func", {"likelihood": likelihood}),

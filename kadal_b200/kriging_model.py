@@ -372,7 +372,8 @@ class Kriging:
     def loocvcalc(self, metrictype="mape", type="standard"):
         """Leave-one-out cross validation (kriging_model.py:260-297).  'standard'
         (krigloocv2.py: n refits in the reference) is one closed-form GPU pass over the factor;
-        'fast' (krigloocv.py) is not built (see :mod:`kadal_b200.loocv`)."""
+        'fast' (krigloocv.py: the bordered inverse, Psi without nugget) is a closed form over a second factor
+        (see :mod:`kadal_b200.loocv`)."""
         if type not in ("fast", "standard"):
             raise ValueError('"type" only accept fast or standard')
         from .loocv import loocv

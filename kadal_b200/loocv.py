@@ -54,3 +54,15 @@ def _loocv_fast(KrigInfo, errtype):
         m.close()
     yv = np.asarray(KrigInfo["y"], dtype=float).reshape(-1, 1)
     return errperf(yv, pred, errtype), pred
+
+
+def loocv2(KrigInfo, errtype="rmse"):
+    """Drop-in for ``krigloocv2.loocv2(KrigInfo, errtype)`` (bound in kriging_model.py:8): the closed form."""
+    return loocv(KrigInfo, errtype=errtype, type="standard")
+
+
+def loocv_fast(KrigInfo, errtype="rmse", num=None):
+    """Drop-in for ``krigloocv.loocv(KrigInfo, errtype, num)`` (bound in kriging_model.py:7)."""
+    if num is not None:
+        raise NotImplementedError("kadal_b200: num= (multi-objective list layout of KrigInfo) is not supported")
+    return loocv(KrigInfo, errtype=errtype, type="fast")

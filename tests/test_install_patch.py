@@ -19,6 +19,7 @@ def _fake_kadal(name):
     lf.likelihood = lambda *a, **k: "ref-lik"
     pr.prediction = lambda *a, **k: "ref-pred"
     km.likelihood, km.prediction = lf.likelihood, pr.prediction
+    km.loocv = km.loocv2 = lambda *a, **k: "ref-loocv"
     km.tune = lambda: km.likelihood()      # looks the global up at call time, like tune_hyperparameters
     root.surrogate_models, sm.supports, sm.kriging_model = sm, sup, km
     return km, lf, pr
@@ -33,8 +34,10 @@ def test_install_patches_and_restores():
     assert ("fakekadal.surrogate_models.kriging_model", "likelihood") in done
     assert km.likelihood is kadal_b200.likelihood and km.prediction is kadal_b200.prediction
     assert lf.likelihood is kadal_b200.likelihood and pr.prediction is kadal_b200.prediction
+    from kadal_b200 import loocv as lo
+    assert km.loocv is lo.loocv_fast and km.loocv2 is lo.loocv2          # kriging_model.py:7-8, used by loocvcalc
     inst.uninstall()
-    assert km.tune() == "ref-lik" and pr.prediction() == "ref-pred"
+    assert km.tune() == "ref-lik" and pr.prediction() == "ref-pred" and km.loocv() == "ref-loocv"
 
 
 def test_install_supplies_kmac_and_patches_the_ehvi_scorers():
