@@ -1330,8 +1330,13 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     }
     return 0;
   }
-  // small models: everything in one fused kernel, nothing of size n x npred in HBM
-  static const bool no_fused = getenv("KB200_NO_FUSED_PREDICT") != nullptr;
+  // Small models (n <= 256, Gaussian, d <= 8) have a fused kernel with nothing of size n x npred in HBM (predict_small_kernel,
+  // round 1).  Since the tiled path skips the identity padding of the last sample tile and solves sample tile 0 with the
+  // resident-factor kernel (solve_rows_half_kernel) it is the faster one at every size measured (tools/time_pred_small.py,
+  // pred + s over 4e6 points: n = 40 1.8e9 vs 1.0e9 pts/s, n = 128 9.1e8 vs 8.5e8, n = 200 (C3) 3.85e8 vs 3.60e8, n = 256
+  // 2.97e8 vs 2.85e8), and it takes every kernel and any d: the fused kernel runs only on request ($KB200_FUSED_PREDICT=1).
+  const char* ef = getenv("KB200_FUSED_PREDICT");                            // (read per call: A/B tests)
+  const bool no_fused = !(ef && atoi(ef) != 0) || getenv("KB200_NO_FUSED_PREDICT") != nullptr;
   if (!no_fused && !(m->flags & KB200_FLAG_NAIVE) &&
       predict_small_supported(m->n, m->d, m->nkernel, m->kid[0], m->h > 0 ? 1 : 0)) {
     PredSmallArgs ps;
@@ -1383,6 +1388,7 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     cc.udot = split ? sl.udot.d() : sl.udot.d() + p0;
     cc.tj_split = split ? 1 : 0;
     cc.part_stride = pstride;
+    cc.skip_pad = half_ok && half_kernels_skip_padding() ? 1 : 0;
     {
       Timed t(m, KB200_PROF_PSI, st);
       CK(launch_corr(cc, tiles, split ? m->nt : 1, st));

@@ -20,6 +20,7 @@
 // phase.  Same data layout, same arithmetic per element as the full-tile kernels (the GEMM core,
 // the right-looking 8x8-inverse TRSM and the blocked POTF2 are the same algorithms).
 // Reference call sites replaced: likelihood_func.py:168-213 (maincalc), prediction.py:245-251.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include "kb200_kernels.h"
@@ -1052,6 +1053,128 @@ chol_panel_half_kernel(CholArgs A, int j) {
   else panel_half_body<false>(A, j, P, smem_raw);
 }
 
+// ============================================================================ pure solves
+// X = C L_jj^-T with nothing to accumulate first: tile column 0 of the left-looking schedule, every solve of the
+// right-looking one, sample tile 0 (or every sample tile, right-looking) of a prediction.  chol_panel_half_kernel spends more
+// than half of such a CTA's life outside the tensor pipe (fetching the 64 x 128 rows, fetching 94 KiB of L_jj and W8 for
+// 1 Mflop of work, storing; ncu r2y: 56 % DMMA pipe).  Here L_jj and its 8x8 inverses are fetched ONCE per CTA and stay
+// resident while the CTA walks a list of half tiles that share them (all point tiles of a prediction; the tiles below the
+// diagonal tile of one candidate); there is no CTA-wide barrier after that, every warp streams 8-row strips
+// (load -> 272 DMMA -> store) at its own pace, so the sixteen warps of an SM drift out of phase and the pipe always has a
+// few strips in their DMMA-rich early steps.  Same arithmetic per row as the panel kernel (panel_solve_rows): bit-identical.
+// grid: (CTAs per matrix, matrices); half tile h of the matrix: tile j + 1 + i0 + (h >> 1) (likelihood) / point tile h >> 1.
+__global__ void __launch_bounds__(HT, 2)
+solve_rows_half_kernel(CholArgs A, int j, int nhalf) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  double* W8s = stages + P_W8;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(stages + P_BAR);   // [NSLAB]
+  uint64_t* w8bar = wbar + NSLAB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+  const long m = blockIdx.y;
+  double* tiles = A.L + (A.pred_mode ? 0 : (size_t)m * A.tiles_per_mat * TILE_ELEMS);
+  const double* Ljj = tiles + (size_t)tri_index(j, j) * TILE_ELEMS;
+  const double* W8j = A.W8 + ((A.pred_mode ? 0 : (size_t)m * A.nt) + j) * 1024;
+  if (tid == 0) {
+    for (int i = 0; i < NSLAB; ++i) mbar_init(&wbar[i], 1);
+    mbar_init(w8bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(w8bar, 8192);
+    bulk_g2s(W8s, W8j, 8192, w8bar);
+#pragma unroll
+    for (int s = 0; s < NSLAB; ++s) {
+      const uint32_t bytes = s < 2 ? SLAB_BYTES : (uint32_t)wslab_rows(s) * KS * 8;
+      mbar_expect_tx(&wbar[s], bytes);
+      if (s < 2) bulk_g2s(stages + P_WS01 + s * SLAB_ELEMS, Ljj + (size_t)s * SLAB_ELEMS, bytes, &wbar[s]);
+      else bulk_g2s(stages + wslab_base(s), Ljj + (size_t)s * SLAB_ELEMS + (size_t)KS * s * KS, bytes, &wbar[s]);
+    }
+  }
+  __syncthreads();
+  const int cols_real = A.pred_mode && KB200_RAGGED ? min(TB, A.n - j * TB) : TB;
+  const int ncb = (cols_real + 7) >> 3;
+  // this warp's strips: rows 8 warp .. 8 warp + 7 of the half tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the rows of
+  // the next strip are prefetched into L2 before the current one is solved
+  const int xr = 8 * warp + g;
+  auto strip = [&](int h, int& t) -> double* {       // first element of the strip's tile, or null: padded rows / past the end
+    if (h >= nhalf) return nullptr;
+    const int hr = h & 1;
+    t = h >> 1;
+    if (A.pred_mode) return A.chunk + ((size_t)t * A.nt + j) * TILE_ELEMS + tile_off(HROWS * hr + xr, 2 * tq);
+    const int i = j + 1 + A.i0 + t;
+    if (KB200_RAGGED && 8 * warp >= A.n - i * TB - hr * HROWS) return nullptr;
+    return tiles + (size_t)tri_index(i, j) * TILE_ELEMS + tile_off(HROWS * hr + xr, 2 * tq);
+  };
+  auto next_strip = [&](int& h, int& t) -> double* {  // advances h to the warp's next real strip
+    for (h += gridDim.x; h < nhalf; h += gridDim.x) {
+      double* p = strip(h, t);
+      if (p) return p;
+    }
+    return nullptr;
+  };
+  // (tile_off(r, c + 8 ct) = tile_off(r, c) + (ct >> 1) * SLAB_ELEMS + swizzle: recomputed per column tile below)
+  auto load = [&](double (&x)[16][2], const double* p0, int hr) {
+    const double* base = p0 - tile_off(HROWS * hr + xr, 2 * tq);
+#pragma unroll
+    for (int ct = 0; ct < 16; ++ct) {
+      const double2 p = *reinterpret_cast<const double2*>(base + tile_off(HROWS * hr + xr, 8 * ct + 2 * tq));
+      x[ct][0] = p.x;
+      x[ct][1] = p.y;
+    }
+  };
+  auto finish = [&](double (&x)[16][2], double* p0, int hr, int t) {
+    if (ncb == 16) panel_solve_rows<false>(x, stages, W8s, wbar, lane, 16);
+    else panel_solve_rows<true>(x, stages, W8s, wbar, lane, ncb);
+    double* base = p0 - tile_off(HROWS * hr + xr, 2 * tq);
+    double rs = 0.0;
+#pragma unroll
+    for (int ct = 0; ct < 16; ++ct) {
+      if (ct >= ncb) break;                          // padded columns: zeros in place
+      *reinterpret_cast<double2*>(base + tile_off(HROWS * hr + xr, 8 * ct + 2 * tq)) = make_double2(x[ct][0], x[ct][1]);
+      rs = fma(x[ct][0], x[ct][0], rs);
+      rs = fma(x[ct][1], x[ct][1], rs);
+    }
+    if (A.pred_mode) {
+      rs += __shfl_xor_sync(FULLMASK, rs, 1);
+      rs += __shfl_xor_sync(FULLMASK, rs, 2);
+      if (tq == 0) {
+        double* dst = A.ssq + (long)t * TB + hr * HROWS + xr;
+        *dst = (j == 0 ? 0.0 : *dst) + rs;
+      }
+    }
+  };
+  // (a second register set for the next strip's rows spills at the 128-register cap of two CTAs per SM: the next strip is
+  //  pulled into L2 instead -- its rows come from HBM, written by the psi kernel / the assembly long before)
+  auto prefetch = [&](const double* p0, int hr) {
+    const char* tile0 = reinterpret_cast<const char*>(p0 - tile_off(HROWS * hr + xr, 2 * tq));
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int line = lane + 32 * e;                // 64 lines of 128 B: slab line >> 3, row 8 warp + (line & 7)
+      const char* q = tile0 + (size_t)(line >> 3) * SLAB_BYTES + (size_t)(HROWS * hr + 8 * warp + (line & 7)) * (KS * 8);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+  };
+  double x[16][2];
+  int h = blockIdx.x - gridDim.x, t = 0;
+  double* p = next_strip(h, t);
+  bool first = true;
+  while (p) {
+    const int hc = h, tc = t;
+    load(x, p, hc & 1);
+    double* pn = next_strip(h, t);
+    if (pn) prefetch(pn, h & 1);
+    if (first) {
+      mbar_wait(w8bar, 0);
+      first = false;
+    }
+    finish(x, p, hc & 1, tc);
+    p = pn;
+  }
+  // every copy has to land before the CTA may exit (a warp without a real strip, a ragged solve that stops early)
+  mbar_wait(w8bar, 0);
+#pragma unroll
+  for (int s = 0; s < NSLAB; ++s) mbar_wait(&wbar[s], 0);
+}
+
 // right-looking RHS update after column k: rw_i -= L_ik z_k for the tiles i > k (nq right-hand sides);
 // one CTA per (i, candidate), thread = row; column k == -1 initialises rw = R
 __global__ void __launch_bounds__(TB)
@@ -1119,6 +1242,9 @@ static cudaError_t half_attrs() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(chol_panel_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(solve_rows_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
+  if (e != cudaSuccess) return e;
+  cudaFuncSetAttribute(solve_rows_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   // ask for the largest shared-memory carve-out so that two CTAs fit
   cudaFuncSetAttribute(chol_diag_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(chol_panel_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1131,6 +1257,8 @@ static cudaError_t half_attrs() {
 // n = 50: 0.054 vs 0.139 ms, n = 128: 0.131 vs 0.150, n = 160: 0.253 vs 0.382, n = 192: 0.329 vs 0.392 -- and
 // n = 200, 224 (seven 32-wide panels, one CTA per SM): 0.420 vs 0.401 / 0.406: from N = 224 on the tile path's two
 // half-SM CTAs per SM hide the strictly sequential pivots better than one 512-thread CTA can, so it keeps those sizes.
+bool half_kernels_skip_padding() { return KB200_RAGGED != 0; }
+
 int lik_small_pad(int n, int d) {
   const int N = (n + 31) & ~31;
   const char* e = getenv("KB200_SMALL_LIK_NMAX");       // (read per call: bench.py measures n = 200 on both paths)
@@ -1178,6 +1306,15 @@ cudaError_t launch_chol_panel_half(const CholArgs& a, int j, int grid_x, int gri
   cudaError_t e = half_attrs();
   if (e != cudaSuccess) return e;
   if (grid_x <= 0 || grid_y <= 0) return cudaSuccess;
+  // pure solves (nothing to accumulate before the solve) have a kernel of their own; $KB200_PURE_SOLVE=0: the panel kernel
+  static const bool pure_on = !(getenv("KB200_PURE_SOLVE") && atoi(getenv("KB200_PURE_SOLVE")) == 0);
+  if (pure_on && (a.rl_mode == 1 || (a.rl_mode == 0 && j == 0))) {
+    // CTAs per matrix: about four waves of half-SM CTAs in all, every CTA at least one half tile
+    static const int per_launch = getenv("KB200_PURE_SOLVE_CTAS") ? std::max(1, atoi(getenv("KB200_PURE_SOLVE_CTAS"))) : 1184;
+    const int nsplit = std::max(1, std::min(grid_x, (per_launch + grid_y - 1) / grid_y));
+    solve_rows_half_kernel<<<dim3(nsplit, grid_y), HT, P_SMEM, st>>>(a, j, grid_x);
+    return cudaGetLastError();
+  }
   chol_panel_half_kernel<<<dim3(grid_x, grid_y), HT, P_SMEM, st>>>(a, j);
   return cudaGetLastError();
 }

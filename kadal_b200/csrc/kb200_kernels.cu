@@ -177,7 +177,8 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
           }
         }
       }
-      if (MODE == CORR_ASSEMBLE || tile) {
+      // (prediction: the variance kernels never read the columns of the padded 8-column blocks of the last sample tile)
+      if (MODE == CORR_ASSEMBLE || (tile && (INTERIOR || !A.skip_pad || gc0 < ((A.n + 7) & ~7)))) {
         double2* dst = reinterpret_cast<double2*>(tile + s * SLAB_ELEMS + row * KS + ((ch ^ (row & 3)) << 2));
         dst[0] = make_double2(q.v[0], q.v[1]);
         dst[1] = make_double2(q.v[2], q.v[3]);
@@ -255,6 +256,7 @@ corr_tile_kernel(CorrArgs A) {
   }
 
   double facc[2] = {0.0, 0.0}, uacc[2] = {0.0, 0.0};
+  double ftot[2] = {0.0, 0.0}, utot[2] = {0.0, 0.0};
   const double eps = cand[4 * A.spec.ntheta + A.spec.nkernel];
 
   for (int tj = tj0; tj < tj1; ++tj) {
@@ -278,15 +280,27 @@ corr_tile_kernel(CorrArgs A) {
     }
     if (interior) corr_pair<FAST, MODE, true>(A, cand, th2, w0, eps, As, Bt, lda, ti, tj, tile, warp, g, ch, facc, uacc);
     else corr_pair<FAST, MODE, false>(A, cand, th2, w0, eps, As, Bt, lda, ti, tj, tile, warp, g, ch, facc, uacc);
+    if (MODE == CORR_PREDICT) {
+      // psi^T alpha, psi^T w per SAMPLE TILE, the tiles added in order: the same bits whether this CTA walks all sample
+      // tiles or one CTA per (point tile, sample tile) pair leaves the partial sums to the epilogue (tj_split, small batches)
+#pragma unroll
+      for (int rgi = 0; rgi < 2; ++rgi) {
+        double f = facc[rgi], u = uacc[rgi];
+        f += __shfl_xor_sync(0xffffffffu, f, 1);
+        f += __shfl_xor_sync(0xffffffffu, f, 2);
+        u += __shfl_xor_sync(0xffffffffu, u, 1);
+        u += __shfl_xor_sync(0xffffffffu, u, 2);
+        ftot[rgi] = tj == tj0 ? f : ftot[rgi] + f;
+        utot[rgi] = tj == tj0 ? u : utot[rgi] + u;
+        facc[rgi] = 0.0;
+        uacc[rgi] = 0.0;
+      }
+    }
   }
   if (MODE == CORR_PREDICT) {
 #pragma unroll
     for (int rgi = 0; rgi < 2; ++rgi) {
-      double f = facc[rgi], u = uacc[rgi];
-      f += __shfl_xor_sync(0xffffffffu, f, 1);
-      f += __shfl_xor_sync(0xffffffffu, f, 2);
-      u += __shfl_xor_sync(0xffffffffu, u, 1);
-      u += __shfl_xor_sync(0xffffffffu, u, 2);
+      const double f = ftot[rgi], u = utot[rgi];
       const int row = 8 * (warp + 8 * rgi) + g;
       const long gp = (long)ti * TB + row;
       if (ch == 0 && gp < A.npts) {

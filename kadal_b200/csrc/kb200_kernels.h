@@ -33,6 +33,8 @@ struct CorrArgs {
   double* udot;          // [npts]  psi^T w
   int tj_split;          // prediction: blockIdx.y = sample tile, one tile pair per CTA (few point tiles: fills the machine)
   long part_stride;
+  int skip_pad;          // prediction: do not store the padded 8-column blocks of the last sample tile (the half-SM variance
+                         // kernels never read them, kb200_half.cu; the full-SM kernels do: leave 0 for those)
 };
 
 struct CholArgs {
@@ -215,6 +217,7 @@ cudaError_t launch_chol_diag_half(const CholArgs& a, int j, int nmat, cudaStream
 cudaError_t launch_chol_panel_half(const CholArgs& a, int j, int grid_x, int grid_y, cudaStream_t st);
 // small n: assembly + factorisation + forward substitution of one candidate per CTA in shared memory (kb200_half.cu)
 int lik_small_pad(int n, int d);
+bool half_kernels_skip_padding();   // the half-SM kernels skip the identity padding of a ragged last tile (KB200_RAGGED)
 cudaError_t launch_lik_small(const CorrArgs& c, const CholArgs& a, int nmat, cudaStream_t st);
 cudaError_t launch_rl_rhs_update(const CholArgs& a, int k, int nmat, cudaStream_t st, int ntiles = -1);
 cudaError_t launch_w8_from_tiles(const CholArgs& a, int nmat, cudaStream_t st);
