@@ -665,17 +665,25 @@ def predict_bench(args, rank, local_rank, world, torch, dist, barrier):
         k_ms, k_cnt = prof["pred_solve"]
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("predict_small")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("predict_tiled")
         except Exception:
             pass
         if k_cnt:
-            tf = fl * npts * steps / (k_ms * 1e-3) / 1e12
-            rec["roofline"] = {"bound": "tensor", "kernel": "predict_small_kernel (fused standardise + psi + mean + DMMA TRSM variance + epilogue, n <= 256)",
+            # dominant kernel class of the step: the variance solve v = L^-1 psi (n^2 + 2 n flops per point); the psi kernel
+            # (n (3 d + 20) + 2 n flops per point, FP64 FMA pipe) and the epilogue are in `kernel_ms` and in `whole_frac`
+            fl_solve = float(n * n + 2 * n)
+            tf = fl_solve * npts * steps / (k_ms * 1e-3) / 1e12
+            rec["roofline"] = {"bound": "tensor",
+                               "kernel": "variance solve of the tiled predictor: solve_rows_half_kernel (sample tile 0: resident L_00, "
+                                         "8-row strips per warp) + chol_panel_half_kernel in prediction mode (sample tile 1: DMMA "
+                                         "GEMM update + solve, padded columns of the ragged tile skipped)",
                                "achieved": tf, "peak": dmma_tf, "unit": "TFLOP/s", "frac": tf / dmma_tf, "traffic": traffic,
                                "launches": k_cnt, "avg_launch_ms": k_ms / k_cnt,
-                               "flops_per_point": fl, "points_per_launch": npts,
+                               "flops_per_point": fl_solve, "points_per_launch": npts * steps * (n + 127) // 128 / max(1, k_cnt),
+                               "whole_frac": pts / world * fl / 1e12 / dmma_tf,
+                               "whole_note": "all kernels of the step (psi + solve + epilogue), %d algorithmic flops per point" % fl,
                                "peak_source": "kb200_fp64_probe (DMMA, this run)",
-                               "hbm_view": {"achieved": npts * steps * (8 * d + 16) / (k_ms * 1e-3) / 1e9,
+                               "hbm_view": {"achieved": npts * steps * (8 * d + 16) / (ms * 1e-3) / 1e9,
                                             "peak": peaks["hbm_gbs"] if peaks else 6650.0, "unit": "GB/s",
                                             "note": "algorithmic bytes 8 d + 16 per point; arithmetic intensity %.0f flop/B against a machine "
                                                     "balance of ~5.7: the FP64 pipe binds, not HBM (SURVEY.md section 8d)" % (fl / (8 * d + 16))}}
