@@ -131,42 +131,71 @@ __device__ __forceinline__ void mma_slab_h_part(double (&acc)[4][4][2], const do
 }
 
 // ------------------------------------------------------------------ POTF2 on a packed lower triangle
-// warp-level Cholesky of the 32x32 block at (o, o): lane r owns row o + r in registers; column k is
-// broadcast through lbuf (2 x 32 doubles).  dinv[k] = 1 / L_kk.  Returns first bad pivot + 1 or 0.
+// warp-level Cholesky of the 32x32 block at (o, o) (lane r owns row o + r); dinv[k] = 1 / L_kk.  Returns first bad pivot + 1 or 0.
+//
+// Blocked by 8 inside the warp: panel b (columns 8 b .. 8 b + 7 of the block) is factorised with the lane's 8 entries of it in
+// registers -- 8 strictly sequential pivots, column k broadcast through lbuf (2 x 32 doubles) -- written back, and the panels to
+// its right receive their rank-8 update from shared memory on DMMA (10 8x8 blocks per 32x32 block in all).  The loop over b is
+// NOT unrolled: ~500 instructions that stay in the instruction cache.  (Round 2 first had all 32 pivots unrolled with the whole
+// row in registers: ~3300 straight-line instructions run once per call by a single warp; ncu r2y attributed 38 % of that warp's
+// stalls to instruction fetch (`no_inst`) and the call took ~10 us -- 64 % of the lifetime of a diagonal CTA at tile column 0
+// with seven warps at the barrier.)
+// The lane's own diagonal entry is tracked in a register of its own: its update by column k is -l * l with the lane's OWN l
+// (the same fma, the same bits as a[lane] -= l * lb[lane]), so the chain from one pivot to the next is shuffle -> rsqrt +
+// Newton -> l -> one fma, without the shared-memory round trip of the column broadcast.
 __device__ __noinline__ int potf2_32_warp_t(double* S, int o, double* dinv, double* lbuf, int lane) {
-  double a[32];
-  double* row = S + tri(o + lane) + o;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? row[c] : 0.0;
-  // The lane's own diagonal entry is tracked in a register of its own: its update by column k is -l * l with the
-  // lane's OWN l (the same fma, the same bits as a[lane] -= l * lb[lane]), so the chain from one pivot to the next
-  // is shuffle -> rsqrt + Newton -> l -> one fma, without the shared-memory round trip of the column broadcast
-  // (which only feeds the off-diagonal entries and runs beside the next pivot's square root): ~350 -> ~200 cycles
-  // per pivot, 128 strictly sequential pivots per diagonal tile.
-  double dg = row[lane];
+  const int g = lane >> 2, tq = lane & 3;
+  double* rowp = S + tri(o + lane) + o;       // element (o + lane, o)
   int bad = 0;
+#pragma unroll 1
+  for (int b = 0; b < 4; ++b) {
+    const int c0 = 8 * b;
+    const int rl = lane - c0;                 // row relative to the panel's diagonal block; < 0: row above the panel (idle)
+    double a[8];
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    double piv = __shfl_sync(FULLMASK, dg, k);
-    const bool ok = piv > 0.0;
-    bad = (!ok && bad == 0) ? o + k + 1 : bad;
-    piv = ok ? piv : 1.0;
-    const double a2 = a[k] + a[k];
-    double dk, h;
-    sqrt_rsqrt(piv, dk, h);
-    const double l = a2 * h;
-    dg = fma(-l, l, dg);
-    double* lb = lbuf + (k & 1) * 32;
-    lb[lane] = l;
+    for (int c = 0; c < 8; ++c) a[c] = (rl >= c) ? rowp[c0 + c] : 0.0;
+    double dg = (rl >= 0 && rl < 8) ? rowp[lane] : 1.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double piv = __shfl_sync(FULLMASK, dg, c0 + k);
+      const bool ok = piv > 0.0;
+      bad = (!ok && bad == 0) ? o + c0 + k + 1 : bad;
+      piv = ok ? piv : 1.0;
+      const double a2 = a[k] + a[k];
+      double dk, h;
+      sqrt_rsqrt(piv, dk, h);
+      const double l = a2 * h;
+      dg = fma(-l, l, dg);
+      double* lb = lbuf + (k & 1) * 32;
+      lb[lane] = l;
+      __syncwarp();
+#pragma unroll
+      for (int c = k + 1; c < 8; ++c) a[c] = fma(-l, lb[c0 + c], a[c]);
+      a[k] = (rl == k) ? dk : l;
+      if (rl == k) dinv[o + c0 + k] = h + h;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (rl >= c) rowp[c0 + c] = a[c];
     __syncwarp();
-#pragma unroll
-    for (int c = k + 1; c < 32; ++c) a[c] = fma(-l, lb[c], a[c]);
-    a[k] = (lane == k) ? dk : l;
-    if (lane == k) dinv[o + k] = h + h;
+    // rank-8 update of the panels to the right inside the block: C(q, p) -= L(q, b) L(p, b)^T, b < p <= q <= 3
+    for (int p = b + 1; p < 4; ++p) {
+      const double* br = S + tri(o + 8 * p + g) + o;
+      const double b0 = br[c0 + tq], b1 = br[c0 + 4 + tq];
+      const int cc = 8 * p + 2 * tq;
+      for (int q = p; q < 4; ++q) {
+        double* cr = S + tri(o + 8 * q + g) + o;
+        // (q == p: entries above the diagonal do not exist in the packed layout -- whatever is read there is not stored)
+        double v0 = cr[cc], v1 = cr[cc + 1];
+        dmma884(v0, v1, -cr[c0 + tq], b0);
+        dmma884(v0, v1, -cr[c0 + 4 + tq], b1);
+        const int r = 8 * q + g;
+        if (cc <= r) cr[cc] = v0;
+        if (cc + 1 <= r) cr[cc + 1] = v1;
+      }
+    }
+    __syncwarp();
   }
-#pragma unroll
-  for (int c = 0; c < 32; ++c)
-    if (c <= lane) row[c] = a[c];
   return bad;
 }
 
