@@ -724,6 +724,9 @@ chol_diag_half_kernel(CholArgs A, int j) {
   for (int idx = tid; idx < TILE_ELEMS / 4; idx += HT) {
     const int ch = idx & 3, row = (idx >> 2) & (TB - 1), s = idx >> 9;
     const int c0 = s * KS + 4 * ch;
+    // quads strictly above the diagonal: zero since the assembly and never touched on the left-looking schedule (the
+    // trailing updates of the right-looking one compute whole diagonal tiles: there the zeros are written back)
+    if (c0 > row && !A.rl_mode) continue;
     double l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) l[e] = (c0 + e <= row) ? S[tri(row) + c0 + e] : 0.0;
