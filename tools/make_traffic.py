@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASS = {"corr_tile_kernel": "assemble", "chol_diag_kernel": "chol_diag", "chol_panel_kernel": "chol_panel",
-         "chol_diag_half_kernel": "chol_diag", "chol_panel_half_kernel": "chol_panel",
+         "chol_diag_half_kernel": "chol_diag", "chol_panel_half_kernel": "chol_panel", "solve_rows_half_kernel": "chol_panel",
          "lik_finalize_kernel": "finalize", "predict_small_kernel": "predict_small", "lik_small_kernel": "lik_small"}
 
 
@@ -28,9 +28,16 @@ def main():
         hdr, units = rows[0], rows[1]
         kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         acc = {}
+        # a capture of the tiled predictor (prof_pred_*): its variance-solve launches (solve_rows_half_kernel + chol_panel_half_kernel
+        # in prediction mode) form the class bench.py's predict.roofline reports; psi and epilogue launches are listed beside them
+        pred = os.path.basename(rep).startswith("prof_pred_")
         for r in rows[2:]:
             name = r[kn].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
             cls = CLASS.get(name)
+            if pred:
+                cls = {"solve_rows_half_kernel": "predict_tiled", "chol_panel_half_kernel": "predict_tiled",
+                       "corr_tile_kernel": "predict_tiled_psi", "predict_epilogue_kernel": "predict_tiled_epilogue",
+                       "predict_small_kernel": "predict_small"}.get(name)
             if cls is None:
                 continue
             b = float(r[rd].replace(",", "")) * scale(units[rd]) + float(r[wr].replace(",", "")) * scale(units[wr])
