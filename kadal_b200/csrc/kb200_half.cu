@@ -28,6 +28,9 @@
 namespace kb200 {
 namespace {
 
+#ifndef KB200_PANEL_PREFETCH  // panel CTAs prefetch the C half tile of the CTA this many blocks ahead into L2 (A/B builds).  Measured
+#define KB200_PANEL_PREFETCH 0 // without gain at 296 / 592 (C2 7.80 / 7.81 vs 7.79 ms, C3 solve 7.41 vs 7.45 ms, C4 pred + s 8.62 vs 8.54): off
+#endif
 #ifndef KB200_RAGGED          // skip the identity padding of the ragged last tile (n % 128 != 0); 0: A/B builds
 #define KB200_RAGGED 1
 #endif
@@ -1077,6 +1080,26 @@ chol_panel_half_kernel(CholArgs A, int j) {
 #if !KB200_RAGGED
   rows_real = HROWS;
   cols_real = TB;
+#endif
+#if KB200_PANEL_PREFETCH
+  // Left-looking launches: pull the C half tile of the CTA that will take this slot about one wave later (CTAs start in
+  // block order, 2 x 148 are resident) into L2.  ncu r2zz: a prediction CTA of sample tile 1 spent 20 % of its life waiting
+  // for its 64 x 128 rows of psi to come from HBM before the first DMMA could issue.
+  if (A.rl_mode == 0) {
+    const long lin = (long)blockIdx.y * gridDim.x + blockIdx.x + KB200_PANEL_PREFETCH;
+    if (lin < (long)gridDim.x * gridDim.y) {
+      const int bx = (int)(lin % gridDim.x);
+      const long by = lin / gridDim.x;
+      const double* Cn = A.pred_mode
+                             ? A.chunk + ((size_t)(bx >> 1) * A.nt + j) * TILE_ELEMS
+                             : A.L + ((size_t)by * A.tiles_per_mat + tri_index(j + 1 + A.i0 + (bx >> 1), j)) * TILE_ELEMS;
+      const int nsl = (cols_real + KS - 1) / KS;       // slabs with real columns (the same tile column: the same count)
+      for (int line = threadIdx.x; line < nsl * HROWS; line += HT) {   // one 128-byte line = one row of one slab
+        const double* q = Cn + (size_t)(line >> 6) * SLAB_ELEMS + (size_t)(HROWS * (bx & 1) + (line & 63)) * KS;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      }
+    }
+  }
 #endif
   if (rows_real <= 0) return;                        // a half tile of padding only: zeros stay zeros (whole CTA, before any barrier)
   const PanelPtrs P{rowA, rowB, Ljj, W8j, Cij, ssq_base, hr, rows_real, cols_real};

@@ -40,6 +40,9 @@ constexpr int CORR_THREADS = 256;
 #ifndef KB200_CORR_PAIR2
 #define KB200_CORR_PAIR2 1
 #endif
+#ifndef KB200_CORR_PAIR2_RAGGED   // prediction: the fully real slabs of the ragged last sample tile take the paired path too
+#define KB200_CORR_PAIR2_RAGGED 1
+#endif
 #ifndef KB200_CORR_PAIR2_EDGE   // the same on diagonal tiles / the last tile row of the assembly: measured 1.52 -> 1.82 ms (ptxas spills
 #define KB200_CORR_PAIR2_EDGE 0 // 864 instead of 228 bytes at the 85-register cap), off
 #endif
@@ -63,14 +66,17 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
                                           int ti, int tj, double* tile, int warp, int g, int ch,
                                           double (&facc)[2], double (&uacc)[2]) {
   const int d = A.spec.d;
+  int s_begin = 0;          // first slab of the one-row-at-a-time loop below
 #if KB200_CORR_PAIR2
-  if (FAST && INTERIOR) {
+  if (FAST && (INTERIOR || (KB200_CORR_PAIR2_RAGGED && MODE == CORR_PREDICT))) {
     // both rows of the thread per column quad (corr_quad_gauss2); per entry and per row the same operations in the
-    // same order as the loop below
+    // same order as the loop below.  Prediction against the ragged last sample tile: the slabs whose 16 columns are all real
+    // samples take this path too (n = 200: 4 of the 4.5 real slabs of sample tile 1), the rest the loop below.
+    const int s_full = INTERIOR ? NSLAB : max(0, min(NSLAB, (A.n - tj * TB) / KS));
     const int row0 = 8 * warp + g, row1 = row0 + 64;
     const double2* thi = reinterpret_cast<const double2*>(th2 + 2 * d);
 #pragma unroll 1
-    for (int s = 0; s < NSLAB; ++s) {
+    for (int s = 0; s < s_full; ++s) {
       const int c0 = s * KS + 4 * ch;
       Quad q0, q1;
       corr_quad_gauss2<MODE == CORR_ASSEMBLE || KB200_PREDICT_EXACT_DIV, FAST & 3>(d, th2, th2 + d, thi, w0, As + row0 * lda,
@@ -101,7 +107,8 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
         facc[1] += fa1; uacc[1] += ua1;
       }
     }
-    return;
+    if (INTERIOR) return;
+    s_begin = s_full;
   }
   if (KB200_CORR_PAIR2_EDGE && FAST && !INTERIOR && MODE == CORR_ASSEMBLE) {
     // diagonal tiles and the last tile row: the same pairing where both rows of the thread need the quad, then the
@@ -145,7 +152,7 @@ __device__ __forceinline__ void corr_pair(const CorrArgs& A, const double* __res
     const int row = 8 * (warp + 8 * rgi) + g;
     const long grow = (long)ti * TB + row;
 #pragma unroll 1
-    for (int s = 0; s < NSLAB; ++s) {
+    for (int s = s_begin; s < NSLAB; ++s) {
       const int c0 = s * KS + 4 * ch;
       const int gc0 = tj * TB + c0;
       Quad q;
