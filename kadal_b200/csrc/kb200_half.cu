@@ -1118,8 +1118,13 @@ chol_panel_half_kernel(CholArgs A, int j) {
 // (load -> 272 DMMA -> store) at its own pace, so the sixteen warps of an SM drift out of phase and the pipe always has a
 // few strips in their DMMA-rich early steps.  Same arithmetic per row as the panel kernel (panel_solve_rows): bit-identical.
 // grid: (CTAs per matrix, matrices); half tile h of the matrix: tile j + 1 + i0 + (h >> 1) (likelihood) / point tile h >> 1.
-__global__ void __launch_bounds__(HT, 2)
+// NTHR: 256 (two CTAs per SM, default) or one wide CTA per SM ($KB200_PURE_SOLVE_THREADS=640: 20 strips in flight per copy of
+// L_jj at 96 registers; measured SLOWER -- C3 variance solve 7.78 vs 7.44 ms per 4e6 points, 768 threads 7.83: more warps do
+// not help, the strips are bound by the pipe and by their 16 KB of HBM traffic each, not by latency).
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1)
 solve_rows_half_kernel(CholArgs A, int j, int nhalf) {
+  constexpr int NW = NTHR / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);
   double* W8s = stages + P_W8;
@@ -1147,44 +1152,45 @@ solve_rows_half_kernel(CholArgs A, int j, int nhalf) {
   __syncthreads();
   const int cols_real = A.pred_mode && KB200_RAGGED ? min(TB, A.n - j * TB) : TB;
   const int ncb = (cols_real + 7) >> 3;
-  // this warp's strips: rows 8 warp .. 8 warp + 7 of the half tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the rows of
-  // the next strip are prefetched into L2 before the current one is solved
-  const int xr = 8 * warp + g;
-  auto strip = [&](int h, int& t) -> double* {       // first element of the strip's tile, or null: padded rows / past the end
-    if (h >= nhalf) return nullptr;
-    const int hr = h & 1;
+  // The CTA's half tiles are blockIdx.x, blockIdx.x + gridDim.x, ...; its strips (8 rows each, 8 per half tile) are numbered
+  // through them and dealt to the warps round robin: strip k = rows 8 (k & 7) .. of half tile blockIdx.x + (k >> 3) gridDim.x.
+  const int nh = blockIdx.x < nhalf ? (nhalf - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int nstrip = 8 * nh;
+  // first element (row g of the strip, columns 2 tq ..) of strip k in its tile, or null: padded rows; rb = row of the half tile
+  auto strip = [&](int k, int& t, int& rb) -> double* {
+    const int h = blockIdx.x + (k >> 3) * gridDim.x, hr = h & 1;
     t = h >> 1;
-    if (A.pred_mode) return A.chunk + ((size_t)t * A.nt + j) * TILE_ELEMS + tile_off(HROWS * hr + xr, 2 * tq);
+    rb = HROWS * hr + 8 * (k & 7);
+    if (A.pred_mode) return A.chunk + ((size_t)t * A.nt + j) * TILE_ELEMS + tile_off(rb + g, 2 * tq);
     const int i = j + 1 + A.i0 + t;
-    if (KB200_RAGGED && 8 * warp >= A.n - i * TB - hr * HROWS) return nullptr;
-    return tiles + (size_t)tri_index(i, j) * TILE_ELEMS + tile_off(HROWS * hr + xr, 2 * tq);
+    if (KB200_RAGGED && rb >= A.n - i * TB) return nullptr;
+    return tiles + (size_t)tri_index(i, j) * TILE_ELEMS + tile_off(rb + g, 2 * tq);
   };
-  auto next_strip = [&](int& h, int& t) -> double* {  // advances h to the warp's next real strip
-    for (h += gridDim.x; h < nhalf; h += gridDim.x) {
-      double* p = strip(h, t);
+  auto next_strip = [&](int& k, int& t, int& rb) -> double* {  // advances k to the warp's next real strip
+    for (k += NW; k < nstrip; k += NW) {
+      double* p = strip(k, t, rb);
       if (p) return p;
     }
     return nullptr;
   };
-  // (tile_off(r, c + 8 ct) = tile_off(r, c) + (ct >> 1) * SLAB_ELEMS + swizzle: recomputed per column tile below)
-  auto load = [&](double (&x)[16][2], const double* p0, int hr) {
-    const double* base = p0 - tile_off(HROWS * hr + xr, 2 * tq);
+  auto load = [&](double (&x)[16][2], const double* p0, int rb) {
+    const double* base = p0 - tile_off(rb + g, 2 * tq);
 #pragma unroll
     for (int ct = 0; ct < 16; ++ct) {
-      const double2 p = *reinterpret_cast<const double2*>(base + tile_off(HROWS * hr + xr, 8 * ct + 2 * tq));
+      const double2 p = *reinterpret_cast<const double2*>(base + tile_off(rb + g, 8 * ct + 2 * tq));
       x[ct][0] = p.x;
       x[ct][1] = p.y;
     }
   };
-  auto finish = [&](double (&x)[16][2], double* p0, int hr, int t) {
+  auto finish = [&](double (&x)[16][2], double* p0, int rb, int t) {
     if (ncb == 16) panel_solve_rows<false>(x, stages, W8s, wbar, lane, 16);
     else panel_solve_rows<true>(x, stages, W8s, wbar, lane, ncb);
-    double* base = p0 - tile_off(HROWS * hr + xr, 2 * tq);
+    double* base = p0 - tile_off(rb + g, 2 * tq);
     double rs = 0.0;
 #pragma unroll
     for (int ct = 0; ct < 16; ++ct) {
       if (ct >= ncb) break;                          // padded columns: zeros in place
-      *reinterpret_cast<double2*>(base + tile_off(HROWS * hr + xr, 8 * ct + 2 * tq)) = make_double2(x[ct][0], x[ct][1]);
+      *reinterpret_cast<double2*>(base + tile_off(rb + g, 8 * ct + 2 * tq)) = make_double2(x[ct][0], x[ct][1]);
       rs = fma(x[ct][0], x[ct][0], rs);
       rs = fma(x[ct][1], x[ct][1], rs);
     }
@@ -1192,36 +1198,36 @@ solve_rows_half_kernel(CholArgs A, int j, int nhalf) {
       rs += __shfl_xor_sync(FULLMASK, rs, 1);
       rs += __shfl_xor_sync(FULLMASK, rs, 2);
       if (tq == 0) {
-        double* dst = A.ssq + (long)t * TB + hr * HROWS + xr;
+        double* dst = A.ssq + (long)t * TB + rb + g;
         *dst = (j == 0 ? 0.0 : *dst) + rs;
       }
     }
   };
-  // (a second register set for the next strip's rows spills at the 128-register cap of two CTAs per SM: the next strip is
-  //  pulled into L2 instead -- its rows come from HBM, written by the psi kernel / the assembly long before)
-  auto prefetch = [&](const double* p0, int hr) {
-    const char* tile0 = reinterpret_cast<const char*>(p0 - tile_off(HROWS * hr + xr, 2 * tq));
+  // (a second register set for the next strip's rows spills at the register cap: the next strip is pulled into L2 instead --
+  //  its rows come from HBM, written by the psi kernel / the assembly long before)
+  auto prefetch = [&](const double* p0, int rb) {
+    const char* tile0 = reinterpret_cast<const char*>(p0 - tile_off(rb + g, 2 * tq));
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int line = lane + 32 * e;                // 64 lines of 128 B: slab line >> 3, row 8 warp + (line & 7)
-      const char* q = tile0 + (size_t)(line >> 3) * SLAB_BYTES + (size_t)(HROWS * hr + 8 * warp + (line & 7)) * (KS * 8);
+      const int line = lane + 32 * e;                // 64 lines of 128 B: slab line >> 3, row rb + (line & 7)
+      const char* q = tile0 + (size_t)(line >> 3) * SLAB_BYTES + (size_t)(rb + (line & 7)) * (KS * 8);
       asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
     }
   };
   double x[16][2];
-  int h = blockIdx.x - gridDim.x, t = 0;
-  double* p = next_strip(h, t);
+  int k = warp - NW, t = 0, rb = 0;
+  double* p = next_strip(k, t, rb);
   bool first = true;
   while (p) {
-    const int hc = h, tc = t;
-    load(x, p, hc & 1);
-    double* pn = next_strip(h, t);
-    if (pn) prefetch(pn, h & 1);
+    const int tc = t, rc = rb;
+    load(x, p, rc);
+    double* pn = next_strip(k, t, rb);
+    if (pn) prefetch(pn, rb);
     if (first) {
       mbar_wait(w8bar, 0);
       first = false;
     }
-    finish(x, p, hc & 1, tc);
+    finish(x, p, rc, tc);
     p = pn;
   }
   // every copy has to land before the CTA may exit (a warp without a real strip, a ragged solve that stops early)
@@ -1297,9 +1303,12 @@ static cudaError_t half_attrs() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(chol_panel_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(solve_rows_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
+  e = cudaFuncSetAttribute(solve_rows_half_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
   if (e != cudaSuccess) return e;
-  cudaFuncSetAttribute(solve_rows_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(solve_rows_half_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(solve_rows_half_kernel<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
+  if (e != cudaSuccess) return e;
+
   // ask for the largest shared-memory carve-out so that two CTAs fit
   cudaFuncSetAttribute(chol_diag_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(chol_panel_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1366,8 +1375,11 @@ cudaError_t launch_chol_panel_half(const CholArgs& a, int j, int grid_x, int gri
   if (pure_on && (a.rl_mode == 1 || (a.rl_mode == 0 && j == 0))) {
     // CTAs per matrix: about four waves of half-SM CTAs in all, every CTA at least one half tile
     static const int per_launch = getenv("KB200_PURE_SOLVE_CTAS") ? std::max(1, atoi(getenv("KB200_PURE_SOLVE_CTAS"))) : 1184;
-    const int nsplit = std::max(1, std::min(grid_x, (per_launch + grid_y - 1) / grid_y));
-    solve_rows_half_kernel<<<dim3(nsplit, grid_y), HT, P_SMEM, st>>>(a, j, grid_x);
+    static const int thr = getenv("KB200_PURE_SOLVE_THREADS") ? atoi(getenv("KB200_PURE_SOLVE_THREADS")) : 256;
+    const int per = thr > 256 ? per_launch / 2 : per_launch;     // one wide CTA per SM instead of two
+    const int nsplit = std::max(1, std::min(grid_x, (per + grid_y - 1) / grid_y));
+    if (thr == 640) solve_rows_half_kernel<640><<<dim3(nsplit, grid_y), 640, P_SMEM, st>>>(a, j, grid_x);
+    else solve_rows_half_kernel<256><<<dim3(nsplit, grid_y), HT, P_SMEM, st>>>(a, j, grid_x);
     return cudaGetLastError();
   }
   chol_panel_half_kernel<<<dim3(grid_x, grid_y), HT, P_SMEM, st>>>(a, j);
