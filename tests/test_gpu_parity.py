@@ -377,6 +377,43 @@ def test_tile_boundaries_likelihood_and_predict(kb, n):
             assert relerr(pb[1], pa[1], max(1e-6 * s2, 1e-300)) < TOL_VAR
 
 
+@pytest.mark.parametrize("n", [131, 136, 200, 250, 391, 520])
+def test_ragged_last_tile_against_oracle(kb, n):
+    """n % 128 != 0: the kernels skip the identity padding of the last tile (rows of the panel GEMM / solve and of the
+    diagonal SYRK, columns of the prediction solve, psi stores).  Likelihood on the left-looking (P = 40) and the
+    right-looking (P = 3) schedule and a bulk prediction (many point tiles: the pure-solve kernel + the ragged panel
+    kernel) against the oracle; a 3-point-tile batch (per-tile-pair psi CTAs, right-looking sweep from 3 sample tiles
+    on) must give the same bits as the same points inside the bulk call."""
+    rng = np.random.default_rng(1000 + n)
+    d = 4
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.3 * X[:, :1] ** 2 + 3.0
+    info = ko.make_kriginfo(X, y)
+    pop = rng.uniform(-0.2, 0.5, (40, d))
+    nll, inf = kb.likelihood_batch(pop, info, False)
+    nll3, inf3 = kb.likelihood_batch(pop[:3], info, False)
+    assert not inf.any() and not inf3.any()
+    for i in (0, 1, 2, 17, 39):
+        ref = ko.likelihood(pop[i].copy(), copy.deepcopy(info), "default", False, check_pd=False)
+        assert relerr(nll[i], ref) < TOL_NLL
+        if i < 3:
+            assert relerr(nll3[i], ref) < TOL_NLL
+    A, B = copy.deepcopy(info), copy.deepcopy(info)
+    ko.likelihood(pop[0].copy(), A, "all", False, check_pd=False)
+    kb.likelihood(pop[0].copy(), B, "all", False)
+    assert relerr(B["U"], A["U"]) < TOL_MEAN
+    xp = rng.uniform(-1, 1, (30_011, d))
+    out = kb.predict_arrays(xp, B, ("pred", "ssqr"))
+    sel = np.r_[0:200, 15_000:15_200, 29_811:30_011]
+    pa = ko.prediction(xp[sel], A, ["pred", "SSqr"])
+    s2 = float(np.asarray(A["SigmaSqr"]).ravel()[0])
+    assert relerr(out["pred"][sel], pa[0].ravel()) < TOL_MEAN
+    assert relerr(out["ssqr"][sel], pa[1].ravel(), 1e-6 * s2) < TOL_VAR
+    sub = kb.predict_arrays(xp[128 * 100:128 * 103], B, ("pred", "ssqr"))
+    assert np.array_equal(sub["pred"], out["pred"][128 * 100:128 * 103])
+    assert np.array_equal(sub["ssqr"], out["ssqr"][128 * 100:128 * 103])
+
+
 def test_predict_crosses_chunk_boundary(kb, golden_c3):
     """npred larger than one variance chunk (296 tiles x 128 points at n=200) and not a
     multiple of the tile size; mean-only and mean+variance paths must agree on the mean."""
