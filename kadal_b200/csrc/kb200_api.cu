@@ -134,6 +134,10 @@ struct DevBuf {
 struct PredSlot {
   cudaStream_t stream = nullptr;
   DevBuf x, chunk, fdot, udot, ssq, out[7];
+  // variance chunks rotate over the call's stream and up to two side streams ($KB200_PRED_STREAMS)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  DevBuf chunk2[2], ssq2[2];
 };
 
 struct kb200_model {
@@ -406,6 +410,12 @@ void kb200_model_destroy(kb200_model* m) {
     sl.x.release(true); sl.chunk.release(true); sl.fdot.release(true); sl.udot.release(true); sl.ssq.release(true);
     for (auto& o : sl.out) o.release(true);
     if (sl.stream) cudaStreamDestroy(sl.stream);
+    for (int k = 0; k < 2; ++k) {
+      if (sl.side[k]) cudaStreamDestroy(sl.side[k]);
+      if (sl.ev_join[k]) cudaEventDestroy(sl.ev_join[k]);
+      sl.chunk2[k].release(true); sl.ssq2[k].release(true);
+    }
+    if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
   }
   for (int g = 0; g < kb200_model::MAXG; ++g) {
     if (m->gstream[g]) cudaStreamDestroy(m->gstream[g]);
@@ -1257,15 +1267,29 @@ static cudaError_t h2d_bulk(void* dst, const void* src, size_t bytes, int device
 }
 
 // --------------------------------------------------------------------- prediction
-static long chunk_tiles_for(const kb200_model* m) {
-  // point tiles per variance chunk: a multiple of the SM count.  One wave per launch left a quarter of the
-  // time in launch gaps and tails (C4 pred+s: 17.8 ms at 1 wave, 15.4 at 8; with the half-SM panel kernel
-  // 14.2); 8 waves, capped so that the psi chunk stays below ~2.5 GB ($KB200_CHUNK_WAVES overrides).
+// variance streams of a bulk prediction: chunks of point tiles rotate over the call's stream and nstr - 1 side streams
+static int pred_streams_for(const kb200_model* m) {
+  static const int env = getenv("KB200_PRED_STREAMS") ? std::max(1, std::min(3, atoi(getenv("KB200_PRED_STREAMS")))) : 2;
+  return (m->prof_on || m->half_mode == 0 || (m->flags & KB200_FLAG_NAIVE)) ? 1 : env;   // per-kernel timings want one stream
+}
+
+static long chunk_tiles_for(const kb200_model* m, long tiles_total = -1) {   // -1: the single-stream cap (host-path super-chunks, LOOCV)
+  // Point tiles per variance chunk.  One wave of point tiles per launch left a quarter of the time in launch gaps and
+  // tails (C4 pred+s: 17.8 ms at 1 wave, 15.4 at 8; with the half-SM panel kernel 14.2), and a chunk small enough to
+  // stay in the 126 MB L2 is slower for the same reason (section 4 of DESIGN.md).  Late round 2: the chunks of a bulk
+  // call rotate over TWO streams, so the tail of every launch of one chunk is filled by the other chunk's kernels (C3
+  // 3.91e8 -> 4.2e8 pts/s, C4 pred + s 3.88e7 -> 4.1e7, C5 scoring 1.71e6 -> 1.82e6): the call is cut into an even number
+  // of equal chunks of at most 16 waves / 2.5 GB of psi each ($KB200_CHUNK_WAVES, $KB200_PRED_STREAMS override).
   static const long env_waves = getenv("KB200_CHUNK_WAVES") ? std::max(1L, atol(getenv("KB200_CHUNK_WAVES"))) : 0;
   const long per_wave = 148L * std::max(1L, 4L / m->nt);
   const long bytes_per_wave = per_wave * m->nt * (long)TILE_ELEMS * 8;
-  long waves = env_waves ? env_waves : std::max(1L, std::min(8L, (long)(2.5 * (1L << 30)) / bytes_per_wave));
-  return per_wave * waves;
+  const int nstr = tiles_total < 0 ? 1 : pred_streams_for(m);
+  const long wmax = nstr > 1 ? 16L : 8L;
+  const long waves = env_waves ? env_waves : std::max(1L, std::min(wmax, (long)(2.5 * (1L << 30)) / bytes_per_wave));
+  const long cap = per_wave * waves;
+  if (nstr == 1 || tiles_total < 4 * 148L) return cap;                    // small batches: one chunk (split / right-looking paths)
+  const long nchunks = (long)nstr * ((tiles_total + nstr * cap - 1) / (nstr * cap));
+  return (tiles_total + nchunks - 1) / nchunks;
 }
 
 static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long npts, int normtype,
@@ -1356,7 +1380,7 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     }
     return 0;
   }
-  const long ct = std::min(chunk_tiles_for(m), (npts + TB - 1) / TB);
+  const long ct = std::min(chunk_tiles_for(m, (npts + TB - 1) / TB), (npts + TB - 1) / TB);
   const long cpts = ct * TB;
   CK(sl.chunk.reserve((size_t)ct * m->nt * TILE_ELEMS * 8));
   CK(sl.ssq.reserve((size_t)cpts * 8));
@@ -1373,16 +1397,42 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
   // order); the mean's psi^T alpha is summed per sample tile first (~1e-15 relative).  Chosen by batch size only.
   const int env_prl = getenv("KB200_PRED_RL") ? atoi(getenv("KB200_PRED_RL")) : -1;    // (read per call: A/B tests)
   const bool half_ok = m->half_mode != 0 && !pa.naive;
-  for (long p0 = 0; p0 < npts; p0 += cpts) {
+  // The chunks of a bulk call rotate over the call's stream and the side stream(s) (chunk_tiles_for): the launch tails of
+  // one chunk's four kernels are filled by the other chunk's.  Fork / join by events: the call stays ordered on `st`.
+  const int nstr = (npts > cpts && half_ok) ? pred_streams_for(m) : 1;
+  const bool pingpong = nstr > 1;
+  cudaStream_t st0 = st;
+  if (pingpong) {
+    if (!sl.ev_fork) CK(cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventRecord(sl.ev_fork, st0));
+    for (int k = 0; k + 1 < nstr; ++k) {
+      if (!sl.side[k]) {
+        CK(cudaStreamCreateWithFlags(&sl.side[k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&sl.ev_join[k], cudaEventDisableTiming));
+      }
+      CK(sl.chunk2[k].reserve((size_t)ct * m->nt * TILE_ELEMS * 8));
+      CK(sl.ssq2[k].reserve((size_t)cpts * 8));
+      CK(cudaStreamWaitEvent(sl.side[k], sl.ev_fork, 0));
+    }
+    CK(sl.udot.reserve((size_t)npts * 8));
+  }
+  long ci = 0;
+  for (long p0 = 0; p0 < npts; p0 += cpts, ++ci) {
     const long np = std::min(cpts, npts - p0);
     const int tiles = (int)((np + TB - 1) / TB);
-    const bool rl = half_ok && m->nt >= 3 && (env_prl >= 0 ? env_prl != 0 : 2 * tiles < 2 * m->sm_count);
-    const bool split = rl || (m->nt >= 2 && tiles < m->sm_count);
+    if (pingpong) {
+      const int k = (int)(ci % nstr);
+      st = k ? sl.side[k - 1] : st0;
+      pa.chunk = k ? sl.chunk2[k - 1].d() : sl.chunk.d();
+      pa.ssq = k ? sl.ssq2[k - 1].d() : sl.ssq.d();
+    }
+    const bool rl = !pingpong && half_ok && m->nt >= 3 && (env_prl >= 0 ? env_prl != 0 : 2 * tiles < 2 * m->sm_count);
+    const bool split = !pingpong && (rl || (m->nt >= 2 && tiles < m->sm_count));
     const long pstride = (np + 1) & ~1L;
     CK(sl.udot.reserve((size_t)(split ? (size_t)m->nt * pstride : (size_t)npts) * 8));
     if (split) CK(sl.fdot.reserve(std::max((size_t)npts, (size_t)m->nt * pstride) * 8));
     CorrArgs cc = c;
-    cc.xpts = d_x + (size_t)p0 * m->d; cc.npts = np; cc.out = sl.chunk.d();
+    cc.xpts = d_x + (size_t)p0 * m->d; cc.npts = np; cc.out = pa.chunk;
     cc.wvec = m->pw.d();
     cc.fdot = split ? sl.fdot.d() : sl.fdot.d() + p0;
     cc.udot = split ? sl.udot.d() : sl.udot.d() + p0;
@@ -1417,7 +1467,7 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
     ee.udot = split ? sl.udot.d() : sl.udot.d() + p0;
     ee.nparts = split ? m->nt : 1;
     ee.part_stride = pstride;
-    ee.ssq = sl.ssq.d();
+    ee.ssq = pa.ssq;
     ee.pred = outs[0] ? outs[0] + p0 : nullptr;
     ee.ssqr = outs[1] ? outs[1] + p0 : nullptr;
     ee.s = outs[2] ? outs[2] + p0 : nullptr;
@@ -1429,6 +1479,10 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
       Timed t(m, KB200_PROF_EPILOGUE, st);
       CK(launch_epilogue(ee, st));
     }
+  }
+  for (int k = 0; pingpong && k + 1 < nstr; ++k) {
+    CK(cudaEventRecord(sl.ev_join[k], sl.side[k]));
+    CK(cudaStreamWaitEvent(st0, sl.ev_join[k], 0));
   }
   return 0;
 }
