@@ -1733,17 +1733,26 @@ static int sobol_core(kb200_model* m, const SobolSource& src, long long N, int n
   CK(call_enter(m, st));
   int rc = predict_prepare(m, normtype, norm_a, norm_b, KB200_OUT_PRED, dummy, st);
   if (rc) return rc;
-  const long sc = std::min<long>((long)N, 1L << 18);
+  static const int sc_log2 = getenv("KB200_SOBOL_CHUNK_LOG2") ? std::max(12, std::min(24, atoi(getenv("KB200_SOBOL_CHUNK_LOG2")))) : 18;
+  const long sc = std::min<long>((long)N, 1L << sc_log2);
   const size_t cb = (size_t)sc * m->d * 8;
   PredSlot& sl = m->slot[0];
   if (src.kind != 1) {
     CK(sl.x.reserve(cb));
     CK(m->sobB.reserve(cb));
   }
-  CK(m->sobC.reserve(cb));
-  CK(m->sobY.reserve((size_t)3 * sc * 8));
+  // The nsets + 2 prediction sets of a super-chunk are independent given A and B: the C_i sets alternate between the call's
+  // stream and the second prediction slot's stream (own C buffer, y_C, partial sums and psi^T alpha scratch), so the launch
+  // tails and the small compose / dot kernels of one set run under the psi kernel of the other ($KB200_SOBOL_STREAMS=1: off).
+  static const bool two = !(getenv("KB200_SOBOL_STREAMS") && atoi(getenv("KB200_SOBOL_STREAMS")) < 2);
+  const bool dual = two && nsets >= 2 && !m->prof_on;
+  PredSlot& sl2 = m->slot[1];
+  CK(m->sobC.reserve((dual ? 2 : 1) * cb));
+  CK(m->sobY.reserve((size_t)4 * sc * 8));
   CK(m->sobAcc.reserve((size_t)(4 + 2 * nsets) * 8));
-  CK(m->sobPart.reserve((size_t)2 * SOBOL_BLOCKS * 8));
+  CK(m->sobPart.reserve((size_t)4 * SOBOL_BLOCKS * 8));
+  if (dual && !sl.ev_fork) CK(cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
+  if (dual && !sl.ev_join[0]) CK(cudaEventCreateWithFlags(&sl.ev_join[0], cudaEventDisableTiming));
   CK(m->sobMask.reserve((size_t)std::max(1, nsets) * m->d));
   if (nsets) CK(cudaMemcpyAsync(m->sobMask.p, from_a, (size_t)nsets * m->d, cudaMemcpyHostToDevice, st));
   if (src.kind == 2) {
@@ -1787,13 +1796,26 @@ static int sobol_core(kb200_model* m, const SobolSource& src, long long N, int n
     CK(launch_sobol_dot(ya, nullptr, nullptr, np, 1, part, acc + 0, acc + 1, st));
     CK(launch_sobol_dot(yb, nullptr, nullptr, np, 1, part, acc + 2, acc + 3, st));
     m->launches += 4;
+    if (dual) {
+      CK(cudaEventRecord(sl.ev_fork, st));                     // A, B, y_A, y_B of this super-chunk are ready
+      CK(cudaStreamWaitEvent(sl2.stream, sl.ev_fork, 0));
+    }
     for (int q = 0; q < nsets; ++q) {
-      CK(launch_sobol_compose(dA, dB, masks + (size_t)q * m->d, np, m->d, m->sobC.d(), st));
-      outs[0] = yc;
-      rc = predict_core(m, sl, m->sobC.d(), np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, st);
+      const bool side = dual && (q & 1);
+      cudaStream_t sq = side ? sl2.stream : st;
+      double* Cq = m->sobC.d() + (side ? (size_t)sc * m->d : 0);
+      double* ycq = side ? yc + sc : yc;
+      double* partq = side ? part + 2 * SOBOL_BLOCKS : part;
+      CK(launch_sobol_compose(dA, dB, masks + (size_t)q * m->d, np, m->d, Cq, sq));
+      outs[0] = ycq;
+      rc = predict_core(m, side ? sl2 : sl, Cq, np, normtype, KB200_OUT_PRED, 0.0, 0.0, 1, outs, sq);
       if (rc) return rc;
-      CK(launch_sobol_dot(ya, yb, yc, np, 0, part, acc + 4 + 2 * q, acc + 5 + 2 * q, st));
+      CK(launch_sobol_dot(ya, yb, ycq, np, 0, partq, acc + 4 + 2 * q, acc + 5 + 2 * q, sq));
       m->launches += 3;
+    }
+    if (dual) {                                                // the next super-chunk overwrites what the side stream reads
+      CK(cudaEventRecord(sl.ev_join[0], sl2.stream));
+      CK(cudaStreamWaitEvent(st, sl.ev_join[0], 0));
     }
   }
   std::vector<double> h((size_t)4 + 2 * nsets);
