@@ -1443,7 +1443,23 @@ static int predict_core(kb200_model* m, PredSlot& sl, const double* d_x, long np
       Timed t(m, KB200_PROF_PSI, st);
       CK(launch_corr(cc, tiles, split ? m->nt : 1, st));
     }
+    // right-looking sweep: solve tile 0, then ONE launch per tile column j: the CTAs of tile j + 1 apply column j's update and
+    // go on to solve their (now final) tile, the CTAs of the later tiles only update ($KB200_PRED_RL_FUSED=0: two launches
+    // per column, the first form; same bits either way)
+    const bool rl_fused = rl && !(getenv("KB200_PRED_RL_FUSED") && atoi(getenv("KB200_PRED_RL_FUSED")) == 0);
     for (int j = 0; j < m->nt; ++j) {
+      if (rl_fused) {
+        Timed t(m, KB200_PROF_PREDSOLVE, st);
+        if (j == 0) {
+          pa.rl_mode = 1;
+          CK(launch_chol_panel_half(pa, 0, 2 * tiles, 1, st));
+        }
+        if (j + 1 < m->nt) {
+          pa.rl_mode = 4;
+          CK(launch_chol_panel_half(pa, j, 2 * tiles * (m->nt - 1 - j), 1, st));
+        }
+        continue;
+      }
       if (rl) {
         {
           Timed t(m, KB200_PROF_PREDSOLVE, st);

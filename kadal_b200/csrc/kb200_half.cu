@@ -827,6 +827,7 @@ struct PanelPtrs {
   double* Cij;
   long ssq_base;
   int hr, rows_real, cols_real;
+  int solve_after;       // prediction, right-looking, fused sweep (rl_mode 4): this CTA's tile is final after its update: solve it
 };
 
 template <bool RAGGED>
@@ -928,7 +929,7 @@ __device__ __forceinline__ void panel_half_body(const CholArgs& A, int j, const 
         if (lane == 0) mbar_arrive(&empty[(q - 1) % HNST]);
       }
     }
-    if (A.rl_mode >= 2) {   // trailing update: C -= acc in place, nothing to solve
+    if (A.rl_mode >= 2 && !P.solve_after) {   // trailing update: C -= acc in place, nothing to solve
   #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
   #pragma unroll
@@ -1002,7 +1003,7 @@ __device__ __forceinline__ void panel_half_body(const CholArgs& A, int j, const 
     rs += __shfl_xor_sync(FULLMASK, rs, 2);
     if (tq == 0) {
       double* dst = A.ssq + ssq_base + xr;
-      *dst = (j == 0 ? 0.0 : *dst) + rs;
+      *dst = (j == 0 && !P.solve_after ? 0.0 : *dst) + rs;
     }
   }
 }
@@ -1016,7 +1017,7 @@ chol_panel_half_kernel(CholArgs A, int j) {
   long ssq_base = 0;
   // real rows of this half tile / real columns of the output tile (ragged last tile of a matrix with n % 128 != 0: the
   // rest is identity padding -- zero rows of L, zero columns of psi -- and is skipped, see mma_slab_h)
-  int rows_real = HROWS, cols_real = TB;
+  int rows_real = HROWS, cols_real = TB, solve_after = 0;
   if (A.pred_mode && A.rl_mode >= 2) {
     // prediction, right-looking (few point tiles, many sample tiles): after V_j = (psi_j - ...) L_jj^-T every later tile of
     // the point-tile row is updated at once, psi_i -= V_j L_ij^T for i > j: (nt - 1 - j) x more CTAs than the left-looking
@@ -1031,6 +1032,14 @@ chol_panel_half_kernel(CholArgs A, int j) {
     Ljj = A.L;                                                       // unused
     W8j = A.W8 + (size_t)j * 1024;                                   // fetched, unused
     cols_real = min(TB, A.n - i * TB);
+    if (A.rl_mode == 4 && i == j + 1) {
+      // fused sweep: sample tile j + 1 is final once column j has updated it -- this CTA goes on to solve it (V_{j+1}) instead of
+      // leaving that to a launch of its own: one launch per tile column instead of two in a chain of nt columns
+      solve_after = 1;
+      Ljj = A.L + (size_t)tri_index(i, i) * TILE_ELEMS;
+      W8j = A.W8 + (size_t)i * 1024;
+      ssq_base = pt * TB + hr * HROWS;
+    }
   } else if (A.pred_mode) {
     const long pt = blockIdx.x >> 1;
     double* base = A.chunk + (size_t)pt * A.nt * TILE_ELEMS;
@@ -1102,7 +1111,7 @@ chol_panel_half_kernel(CholArgs A, int j) {
   }
 #endif
   if (rows_real <= 0) return;                        // a half tile of padding only: zeros stay zeros (whole CTA, before any barrier)
-  const PanelPtrs P{rowA, rowB, Ljj, W8j, Cij, ssq_base, hr, rows_real, cols_real};
+  const PanelPtrs P{rowA, rowB, Ljj, W8j, Cij, ssq_base, hr, rows_real, cols_real, solve_after};
   // CTA-uniform dispatch: the full-tile body is compiled without any trace of the ragged one
   if (rows_real < HROWS || cols_real < TB) panel_half_body<true>(A, j, P, smem_raw);
   else panel_half_body<false>(A, j, P, smem_raw);

@@ -50,7 +50,8 @@ struct CholArgs {
   int* info;             // [P]
   int naive;             // debug: plain-FMA GEMM instead of the DMMA pipeline
   int i0;                // half-SM panel: first tile row of this launch is j + 1 + i0
-  int rl_mode;           // right-looking variant (large matrices): 0 off, 1 solve-only (T), 2 trailing update (U)
+  int rl_mode;           // right-looking variant: 0 off, 1 solve-only (T), 2 trailing update (U), 3 U of the next tile column only
+                         // (look-ahead), 4 prediction: U, and the CTAs of the next sample tile go on to solve it
   double* Rw;            // [P][nq][npad] working right-hand sides of the right-looking variant
   int fuse_diag;         // panel CTA (j+1, j) also finishes diagonal tile j+1 (no diag launches for j >= 1)
   // prediction-as-extra-rows
