@@ -28,6 +28,9 @@
 namespace kb200 {
 namespace {
 
+#ifndef KB200_POTF2_UNROLL    // warp POTF2: the rank-8 updates of the panels to the right unrolled over their blocks (A/B builds)
+#define KB200_POTF2_UNROLL 1
+#endif
 #ifndef KB200_PANEL_PREFETCH  // panel CTAs prefetch the C half tile of the CTA this many blocks ahead into L2 (A/B builds).  Measured
 #define KB200_PANEL_PREFETCH 0 // without gain at 296 / 592 (C2 7.80 / 7.81 vs 7.79 ms, C3 solve 7.41 vs 7.45 ms, C4 pred + s 8.62 vs 8.54): off
 #endif
@@ -182,6 +185,35 @@ __device__ __noinline__ int potf2_32_warp_t(double* S, int o, double* dinv, doub
       if (rl >= c) rowp[c0 + c] = a[c];
     __syncwarp();
     // rank-8 update of the panels to the right inside the block: C(q, p) -= L(q, b) L(p, b)^T, b < p <= q <= 3
+#if KB200_POTF2_UNROLL
+    // (unrolled over the 3 + 2 + 1 possible blocks, skipped by warp-uniform tests: the blocks of one column are independent and
+    //  their loads / DMMAs overlap instead of running one block after the other)
+#pragma unroll
+    for (int p = 1; p < 4; ++p) {
+      if (p <= b) continue;
+      const double* br = S + tri(o + 8 * p + g) + o;
+      const double b0 = br[c0 + tq], b1 = br[c0 + 4 + tq];
+      const int cc = 8 * p + 2 * tq;
+      double v0[3], v1[3], a0[3], a1[3];
+#pragma unroll
+      for (int q = p; q < 4; ++q) {
+        const double* cr = S + tri(o + 8 * q + g) + o;
+        v0[q - p] = cr[cc]; v1[q - p] = cr[cc + 1];
+        a0[q - p] = -cr[c0 + tq]; a1[q - p] = -cr[c0 + 4 + tq];
+      }
+#pragma unroll
+      for (int q = p; q < 4; ++q) dmma884(v0[q - p], v1[q - p], a0[q - p], b0);
+#pragma unroll
+      for (int q = p; q < 4; ++q) dmma884(v0[q - p], v1[q - p], a1[q - p], b1);
+#pragma unroll
+      for (int q = p; q < 4; ++q) {
+        double* cr = S + tri(o + 8 * q + g) + o;
+        const int r = 8 * q + g;
+        if (cc <= r) cr[cc] = v0[q - p];
+        if (cc + 1 <= r) cr[cc + 1] = v1[q - p];
+      }
+    }
+#else
     for (int p = b + 1; p < 4; ++p) {
       const double* br = S + tri(o + 8 * p + g) + o;
       const double b0 = br[c0 + tq], b1 = br[c0 + 4 + tq];
@@ -197,6 +229,7 @@ __device__ __noinline__ int potf2_32_warp_t(double* S, int o, double* dinv, doub
         if (cc + 1 <= r) cr[cc + 1] = v1;
       }
     }
+#endif
     __syncwarp();
   }
   return bad;
